@@ -1,0 +1,152 @@
+/*
+ * b200knn — C ABI of the B200-native exact k-nearest-neighbour engine that replaces the DCI
+ * native core of ningyu1991/InclusiveGAN on the IMLE matching path.
+ *
+ * Plain C, plain pointers and sizes; no Python, NumPy, torch or TensorFlow types.  The shared
+ * library (inclusivegan_b200/libb200knn.so) is what a reference-side FFI binds; the host-side
+ * mirror of the reference's Python API (inclusivegan_b200/dci.py, class DCI) calls it via ctypes.
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Each entry point cites the reference interface it replaces
+ * (paths relative to the reference root, ningyu1991/InclusiveGAN):
+ *     C core      dci_code/include/dci.h:76-89   dci_init / dci_add / dci_query / dci_clear / dci_reset / dci_free
+ *     extension   dci_code/src/py_dci.c:311-321  _dci.new / add / query / clear / reset / get_num_points / ...
+ *
+ * Conventions
+ *   - every function returns B200KNN_OK (0) or a negative B200KNN_E* code; b200knn_last_error()
+ *     returns a thread-local human-readable message for the last failure on the calling thread
+ *     (the reference's C core has no error channel: it assert()s and abort()s, dci.c:122-123).
+ *   - matrices are row-major: `rows x dim` elements with a leading dimension `ld` (elements between
+ *     consecutive rows, ld >= dim).  This is the NumPy layout the reference takes
+ *     (py_dci.c:106-107: "py_data->data is N x D").
+ *   - distances are Euclidean (sqrt of the sum of squared differences) like util.c:62-69, unless
+ *     B200KNN_FLAG_SQUARED is set (metrics/precision_recall.py:20-57 works on squared L2).
+ *   - results are exact: the approximation knobs of dci_query_config (dci.h:62-74) have no
+ *     counterpart here.  Per query exactly kk = min(k, num_points) neighbours are produced,
+ *     ascending by (distance, index); ties resolve to the lower index.
+ *   - there is NO CPU fallback: with no usable CUDA device every compute entry point fails with
+ *     B200KNN_ENODEVICE.
+ *   - not re-entrant per handle (same as the reference, which holds no locks: SURVEY.md §8b).
+ */
+#ifndef B200KNN_H
+#define B200KNN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200KNN_ABI_VERSION 1
+
+/* status codes */
+#define B200KNN_OK          0
+#define B200KNN_EINVAL     -1   /* bad argument */
+#define B200KNN_ESTATE     -2   /* e.g. add() on a non-empty index (dci.py:228-229), query on an empty one */
+#define B200KNN_ENODEVICE  -3   /* no CUDA device / driver, or device is not sm_100 */
+#define B200KNN_ECUDA      -4   /* a CUDA runtime / driver call failed */
+#define B200KNN_ENOMEM     -5   /* host or device allocation failed */
+
+/* element types of caller buffers */
+#define B200KNN_F64 0           /* float64 — the only dtype the reference accepts (dci.py:116-117) */
+#define B200KNN_F32 1           /* float32 — extension: halves PCIe bytes, skips the f64 blow-up */
+
+/* query flags */
+#define B200KNN_FLAG_SQUARED      1u   /* return squared distances */
+#define B200KNN_FLAG_NO_CERTIFY   2u   /* debug: skip the exactness certificate + exact second pass */
+#define B200KNN_FLAG_FORCE_SCAN   4u   /* debug: answer with the exact CUDA-core scan only (no tensor-core pass) */
+
+typedef struct b200knn_index b200knn_index;
+
+/* ---- life cycle --------------------------------------------------------------------------- */
+
+/* Replaces dci_init (dci.h:76, dci.c:73-93) / _dci.new (py_dci.c:66-83).
+ * dim: feature dimensionality.  n_devices / device_ids: GPUs the pool is row-sharded over
+ * (n_devices <= 0: the current device only; device_ids may be NULL for 0..n_devices-1).
+ * No device work happens here, so a handle can be created (and argument errors tested) on a
+ * machine without a GPU; the device is touched on the first add(). */
+int b200knn_create(int dim, int n_devices, const int *device_ids, b200knn_index **out);
+
+/* Replaces dci_free (dci.h:89) / the capsule destructor py_dci_free (py_dci.c:53-64). */
+int b200knn_destroy(b200knn_index *index);
+
+/* Replaces dci_clear and dci_reset (dci.h:83-86; py_dci.c:214-259): drop the pool, keep the handle.
+ * (dci_reset also redraws DCI's random projections — exact search has none.) */
+int b200knn_clear(b200knn_index *index);
+
+/* Replaces _dci.get_num_points (py_dci.c:262-272). */
+int64_t b200knn_num_points(const b200knn_index *index);
+int b200knn_dim(const b200knn_index *index);
+
+/* ---- host-buffer entry points (what the DCI Python class calls) ---------------------------- */
+
+/* Replaces dci_add (dci.h:79, dci.c:108-337) / _dci.add (py_dci.c:86-128).
+ * data: HOST pointer, n x dim row-major (ld elements per row), dtype B200KNN_F64|F32.
+ * The rows are copied to the device(s) (the reference instead borrows the caller's buffer,
+ * py_dci.c:118-123), converted to BF16 + norms there, and row-sharded across the handle's GPUs.
+ * Fails with B200KNN_ESTATE when the index already holds points (dci.py:228-229). */
+int b200knn_add(b200knn_index *index, const void *data, int dtype, int64_t n, int64_t ld);
+
+/* Replaces dci_query (dci.h:81, dci.c:788-828) / _dci.query (py_dci.c:130-211).
+ * query: HOST pointer, nq x dim row-major.  out_idx (int32) / out_dist (float64): caller-allocated
+ * HOST buffers of nq x kk, kk = min(k, num_points) (rectangular — the reference malloc()s ragged
+ * per-query arrays the caller must free, dci.c:812-821).  Indices are row positions in the array
+ * passed to add() (py_dci.c:185).  *out_kk receives kk (may be NULL). */
+int b200knn_query(b200knn_index *index, const void *query, int dtype, int64_t nq, int64_t ld, int k,
+                  unsigned flags, int32_t *out_idx, double *out_dist, int *out_kk);
+
+/* ---- device-buffer entry points (inputs already resident in HBM; single-device handles) ---- */
+
+/* Launch all work of this handle on `stream` (a cudaStream_t passed as void*, NULL = the
+ * library's own stream).  Lets a host that owns streams (e.g. torch) time and order the work. */
+int b200knn_set_stream(b200knn_index *index, void *stream);
+
+/* As b200knn_add, but `data` is a DEVICE pointer on the handle's device; the rows are NOT copied:
+ * the index borrows the buffer until clear/destroy (the reference's ownership model, dci.h:78).
+ * index_base is added to every returned index (row offset of this shard in a pool that is
+ * row-sharded across processes; py_dci.c:185's data_idx_offset). */
+int b200knn_add_device(b200knn_index *index, const void *d_data, int dtype, int64_t n, int64_t ld,
+                       int64_t index_base);
+
+/* As b200knn_query with DEVICE query / output buffers; asynchronous on the handle's stream unless
+ * an exact second pass is needed (then it synchronises once).  d_out_idx: int32 nq x kk,
+ * d_out_dist: float64 nq x kk. */
+int b200knn_query_device(b200knn_index *index, const void *d_query, int dtype, int64_t nq, int64_t ld, int k,
+                         unsigned flags, int32_t *d_out_idx, double *d_out_dist, int *out_kk);
+
+/* k-way merge of `n_lists` per-shard results (each nq x kk, ascending) into the global nq x kk result.
+ * d_idx / d_dist: DEVICE buffers laid out [n_lists][nq][kk] (what an NCCL all-gather of the local
+ * results produces).  Ties -> lower index.  Runs on `stream`. */
+int b200knn_merge_topk_device(const int32_t *d_idx, const double *d_dist, int n_lists, int64_t nq, int kk,
+                              int32_t *d_out_idx, double *d_out_dist, void *stream);
+
+/* ---- introspection -------------------------------------------------------------------------- */
+
+typedef struct b200knn_stats {
+    int64_t kernel_launches;       /* kernels of this library launched by this handle since creation */
+    int64_t queries;               /* query rows answered */
+    int64_t uncertified;           /* query rows whose tensor-core shortlist could not be certified exact
+                                      and were re-answered by the exact scan */
+    double  ms_convert;            /* accumulated device time per kernel family, profiling mode only */
+    double  ms_distance;
+    double  ms_rerank;
+    double  ms_scan;
+    int64_t distance_launches;     /* launches of the tcgen05 distance kernel counted in ms_distance */
+    double  distance_flops;        /* 2*nq*n*dim summed over those launches */
+} b200knn_stats;
+
+/* profiling != 0: bracket every kernel with CUDA events on the launching stream; read with get_stats. */
+int b200knn_set_profiling(b200knn_index *index, int profiling);
+int b200knn_get_stats(b200knn_index *index, b200knn_stats *out);   /* synchronises the handle's stream(s) */
+int b200knn_reset_stats(b200knn_index *index);
+
+/* Thread-local message for the last failing call on this thread ("" if none). */
+const char *b200knn_last_error(void);
+int b200knn_abi_version(void);
+/* Number of usable sm_100 devices (0 on a machine without a GPU; never fails). */
+int b200knn_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200KNN_H */

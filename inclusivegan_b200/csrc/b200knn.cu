@@ -1,0 +1,775 @@
+// libb200knn — host side and C ABI (include/b200knn.h) of the B200-native exact kNN engine.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC (see build.py).
+// No CPU fallback: every compute entry point needs an sm_100 device and fails loudly without one.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_segmented_radix_sort.cuh>
+
+#include "../../include/b200knn.h"
+#include "kernels.cuh"
+
+namespace {
+
+using namespace b200;
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                    \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return fail(_e == cudaErrorMemoryAllocation ? B200KNN_ENOMEM : B200KNN_ECUDA, "%s failed: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(_e), __FILE__, __LINE__);                                    \
+    } while (0)
+#define TRY(expr)                \
+    do {                         \
+        int _r = (expr);         \
+        if (_r != B200KNN_OK) return _r; \
+    } while (0)
+
+// --------------------------------------------------------------------------------------------
+// driver entry point for TMA descriptors (resolved at run time: the .so loads without libcuda)
+// --------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled g_encode = nullptr;
+
+int resolve_driver() {
+    if (g_encode) return B200KNN_OK;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+        return fail(B200KNN_ENODEVICE, "cuTensorMapEncodeTiled not available from the CUDA driver (%s)", cudaGetErrorString(e));
+    g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    return B200KNN_OK;
+}
+
+// BF16 row-major [rows, kp] -> 2-D tensor map with a (BK x box_rows) SWIZZLE_128B box
+int make_tmap(CUtensorMap *m, const void *base, uint64_t rows, uint64_t kp, uint32_t box_rows) {
+    TRY(resolve_driver());
+    cuuint64_t dims[2] = {kp, rows};
+    cuuint64_t strides[1] = {kp * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B200KNN_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu kp=%llu)", (int)r,
+                                      (unsigned long long)rows, (unsigned long long)kp);
+    return B200KNN_OK;
+}
+
+template <typename T>
+struct DevBuf {   // grow-only device buffer
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return B200KNN_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        CU_TRY(cudaMalloc(reinterpret_cast<void **>(&p), n * sizeof(T)));
+        cap = n;
+        return B200KNN_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+enum Kind { K_CONVERT = 0, K_DISTANCE = 1, K_RERANK = 2, K_SCAN = 3, K_NKINDS = 4 };
+
+struct Shard {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;   // the one work is launched on (own or user-provided)
+    bool ready = false;
+
+    // ---- pool ----
+    const void *x_raw = nullptr;     // original rows (f64 or f32), ld_x elements apart
+    void *x_owned = nullptr;         // set when the library owns the copy
+    int x_dtype = B200KNN_F64;
+    int64_t n = 0, ld_x = 0, index_base = 0;
+    DevBuf<__nv_bfloat16> x_bf;
+    DevBuf<float> xnorm_bf, xnorm_ex;
+    DevBuf<unsigned int> scalars;    // [0] max ||x~||^2 bits, [1] max ||x||^2 bits, [2] query max bf, [3] query max ex, [4] uncert count
+    CUtensorMap tmap_x;
+
+    // ---- query workspace ----
+    DevBuf<__nv_bfloat16> q_bf;
+    DevBuf<float> qnorm_bf, qnorm_ex;
+    DevBuf<float> cand_s;
+    DevBuf<int> cand_i;
+    DevBuf<int> uncert_list;
+    DevBuf<double> scan_d2, scan_d2_sorted;
+    DevBuf<int> scan_iota, scan_vals_sorted, scan_offsets;
+    DevBuf<unsigned char> cub_tmp;
+    DevBuf<unsigned char> q_stage;   // host API: device copy of the caller's query rows
+    DevBuf<int32_t> out_idx;
+    DevBuf<double> out_dist;
+    int *h_count = nullptr;          // pinned
+
+    // ---- stats ----
+    b200knn_stats stats{};
+    bool profiling = false;
+    struct Ev { cudaEvent_t a, b; int kind; double flops; };
+    std::vector<Ev> events;
+
+    int init(int dev) {
+        device = dev;
+        CU_TRY(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CU_TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            return fail(B200KNN_ENODEVICE, "device %d (%s, sm_%d%d) is not an sm_100 (B200) GPU; libb200knn has no other code path",
+                        device, prop.name, prop.major, prop.minor);
+        num_sms = prop.multiProcessorCount;
+        CU_TRY(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+        stream = own_stream;
+        TRY(scalars.ensure(8));
+        CU_TRY(cudaMemsetAsync(scalars.p, 0, 8 * sizeof(unsigned int), stream));
+        CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&h_count), sizeof(int)));
+        TRY(set_kernel_attrs());
+        ready = true;
+        return B200KNN_OK;
+    }
+    int set_kernel_attrs() {
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIST_SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIST_SMEM_BYTES));
+        return B200KNN_OK;
+    }
+    void prof_begin(int kind, double flops = 0.0) {
+        stats.kernel_launches++;
+        if (!profiling) return;
+        Ev e;
+        cudaEventCreate(&e.a);
+        cudaEventCreate(&e.b);
+        e.kind = kind;
+        e.flops = flops;
+        cudaEventRecord(e.a, stream);
+        events.push_back(e);
+    }
+    void prof_end() {
+        if (!profiling) return;
+        cudaEventRecord(events.back().b, stream);
+    }
+    void drain_events() {
+        for (auto &e : events) {
+            cudaEventSynchronize(e.b);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e.a, e.b);
+            switch (e.kind) {
+                case K_CONVERT: stats.ms_convert += ms; break;
+                case K_DISTANCE: stats.ms_distance += ms; stats.distance_launches++; stats.distance_flops += e.flops; break;
+                case K_RERANK: stats.ms_rerank += ms; break;
+                default: stats.ms_scan += ms; break;
+            }
+            cudaEventDestroy(e.a);
+            cudaEventDestroy(e.b);
+        }
+        events.clear();
+    }
+    void clear_pool() {
+        if (!ready) return;
+        cudaSetDevice(device);
+        cudaStreamSynchronize(stream);
+        if (x_owned) cudaFree(x_owned);
+        x_owned = nullptr;
+        x_raw = nullptr;
+        n = 0;
+        x_bf.release();
+        xnorm_bf.release();
+        xnorm_ex.release();
+    }
+    void destroy() {
+        if (!ready) return;
+        clear_pool();
+        drain_events();
+        q_bf.release(); qnorm_bf.release(); qnorm_ex.release(); cand_s.release(); cand_i.release(); uncert_list.release();
+        scan_d2.release(); scan_d2_sorted.release(); scan_iota.release(); scan_vals_sorted.release(); scan_offsets.release();
+        cub_tmp.release(); q_stage.release(); out_idx.release(); out_dist.release(); scalars.release();
+        if (h_count) cudaFreeHost(h_count);
+        if (own_stream) cudaStreamDestroy(own_stream);
+        ready = false;
+    }
+
+    // ------------------------------------------------------------------ kernels: convert
+    int launch_convert(const void *src, int dtype, int64_t rows, int64_t ld, int dim, int kp, __nv_bfloat16 *dst, float *nbf,
+                       float *nex, unsigned int *maxbits /* [2] */) {
+        if (rows <= 0) return B200KNN_OK;
+        const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
+        const int vec = (dim % 8 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0) && ((ld * esz) % 16 == 0);
+        const int warps_per_block = 8;
+        int64_t blocks = (rows + warps_per_block - 1) / warps_per_block;
+        blocks = std::min<int64_t>(blocks, static_cast<int64_t>(num_sms) * 8);
+        prof_begin(K_CONVERT);
+        if (dtype == B200KNN_F64)
+            convert_norm_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+                static_cast<const double *>(src), rows, ld, dim, kp, vec, dst, nbf, nex, maxbits, maxbits + 1);
+        else
+            convert_norm_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+                static_cast<const float *>(src), rows, ld, dim, kp, vec, dst, nbf, nex, maxbits, maxbits + 1);
+        prof_end();
+        CU_TRY(cudaGetLastError());
+        return B200KNN_OK;
+    }
+
+    // ------------------------------------------------------------------ pool
+    int attach_pool(const void *d_rows, bool owned, int dtype, int64_t rows, int64_t ld, int dim, int kp, int64_t base) {
+        x_raw = d_rows;
+        x_owned = owned ? const_cast<void *>(d_rows) : nullptr;
+        x_dtype = dtype;
+        n = rows;
+        ld_x = ld;
+        index_base = base;
+        TRY(x_bf.ensure(static_cast<size_t>(rows) * kp));
+        TRY(xnorm_bf.ensure(rows));
+        TRY(xnorm_ex.ensure(rows));
+        CU_TRY(cudaMemsetAsync(scalars.p, 0, 2 * sizeof(unsigned int), stream));
+        TRY(make_tmap(&tmap_x, x_bf.p, rows, kp, BN));
+        return B200KNN_OK;
+    }
+
+    // ------------------------------------------------------------------ schedule
+    struct Sched { int qt, nt, chunks, tiles_per_chunk, qgroup, grid; };
+    Sched plan(int64_t nq, int kp) const {
+        Sched s;
+        s.qt = static_cast<int>((nq + BM - 1) / BM);
+        s.nt = static_cast<int>((n + BN - 1) / BN);
+        int64_t best_cost = -1;
+        s.chunks = 1;
+        s.tiles_per_chunk = s.nt;
+        for (int c = 1; c <= std::min(s.nt, MAX_CHUNKS); c++) {
+            const int t = (s.nt + c - 1) / c;
+            const int c2 = (s.nt + t - 1) / t;
+            const int64_t items = static_cast<int64_t>(s.qt) * c2;
+            const int64_t waves = (items + num_sms - 1) / num_sms;
+            const int64_t cost = waves * t * 64 + c2;   // sweep length dominates; fewer shortlists break ties
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; s.chunks = c2; s.tiles_per_chunk = t; }
+        }
+        const int64_t a_tile_bytes = static_cast<int64_t>(BM) * kp * 2;
+        s.qgroup = static_cast<int>(std::max<int64_t>(4, std::min<int64_t>(64, (32ll << 20) / std::max<int64_t>(a_tile_bytes, 1))));
+        s.grid = static_cast<int>(std::min<int64_t>(num_sms, static_cast<int64_t>(s.qt) * s.chunks));
+        return s;
+    }
+
+    // ------------------------------------------------------------------ exact scan of a query subset
+    template <typename TX, typename TQ>
+    int scan_typed(const TQ *d_query, int64_t ld_q, const int *d_qlist, int nsub, int dim, int kk, unsigned flags,
+                   int32_t *d_out_idx, double *d_out_dist) {
+        const TX *x = static_cast<const TX *>(x_raw);
+        // sub-batches bounded to ~1.5 GB of scratch
+        int64_t per_q = n * (kk > 32 ? 24 : 8);
+        int batch = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nsub, (1536ll << 20) / std::max<int64_t>(per_q, 1))));
+        batch = std::max(1, std::min(batch, 4096));
+        TRY(scan_d2.ensure(static_cast<size_t>(batch) * n));
+        for (int s0 = 0; s0 < nsub; s0 += batch) {
+            const int ns = std::min(batch, nsub - s0);
+            // qlist == nullptr means rows s0..s0+ns of the query matrix
+            const TQ *qbase = d_qlist ? d_query : d_query + static_cast<int64_t>(s0) * ld_q;
+            const int *ql = d_qlist ? d_qlist + s0 : nullptr;
+            dim3 grid(static_cast<unsigned>((n + SCAN_TX - 1) / SCAN_TX), static_cast<unsigned>((ns + SCAN_TQ - 1) / SCAN_TQ));
+            prof_begin(K_SCAN);
+            scan_dist_kernel<TX, TQ><<<grid, 256, 0, stream>>>(x, ld_x, static_cast<int>(n), qbase, ld_q, ql, ns, dim, scan_d2.p);
+            prof_end();
+            CU_TRY(cudaGetLastError());
+            int32_t *oi = d_qlist ? d_out_idx : d_out_idx + static_cast<int64_t>(s0) * kk;
+            double *od = d_qlist ? d_out_dist : d_out_dist + static_cast<int64_t>(s0) * kk;
+            if (kk <= 32) {
+                prof_begin(K_SCAN);
+                scan_select_kernel<<<ns, 256, 0, stream>>>(scan_d2.p, static_cast<int>(n), ql, kk, index_base, flags, oi, od);
+                prof_end();
+                CU_TRY(cudaGetLastError());
+            } else {
+                const int64_t total = static_cast<int64_t>(ns) * n;
+                TRY(scan_d2_sorted.ensure(total));
+                TRY(scan_iota.ensure(total));
+                TRY(scan_vals_sorted.ensure(total));
+                TRY(scan_offsets.ensure(ns + 1));
+                std::vector<int> off(ns + 1);
+                for (int i = 0; i <= ns; i++) off[i] = static_cast<int>(static_cast<int64_t>(i) * n);
+                if (total > 0x7fffffffll) return fail(B200KNN_EINVAL, "scan batch too large");
+                CU_TRY(cudaMemcpyAsync(scan_offsets.p, off.data(), (ns + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+                CU_TRY(cudaStreamSynchronize(stream));   // `off` is a stack-lifetime host buffer
+                prof_begin(K_SCAN);
+                iota_kernel<<<num_sms * 4, 256, 0, stream>>>(scan_iota.p, total, static_cast<int>(n));
+                prof_end();
+                size_t tmp_bytes = 0;
+                cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp_bytes, scan_d2.p, scan_d2_sorted.p, scan_iota.p, scan_vals_sorted.p,
+                                                         static_cast<int>(total), ns, scan_offsets.p, scan_offsets.p + 1, 0, 64, stream);
+                TRY(cub_tmp.ensure(tmp_bytes));
+                stats.kernel_launches++;
+                CU_TRY(cub::DeviceSegmentedRadixSort::SortPairs(cub_tmp.p, tmp_bytes, scan_d2.p, scan_d2_sorted.p, scan_iota.p,
+                                                                scan_vals_sorted.p, static_cast<int>(total), ns, scan_offsets.p,
+                                                                scan_offsets.p + 1, 0, 64, stream));
+                prof_begin(K_SCAN);
+                scatter_sorted_kernel<<<num_sms * 4, 256, 0, stream>>>(scan_d2_sorted.p, scan_vals_sorted.p, static_cast<int>(n), ql, ns, kk,
+                                                                      index_base, flags, oi, od);
+                prof_end();
+                CU_TRY(cudaGetLastError());
+            }
+        }
+        return B200KNN_OK;
+    }
+    int scan(const void *d_query, int q_dtype, int64_t ld_q, const int *d_qlist, int nsub, int dim, int kk, unsigned flags,
+             int32_t *d_out_idx, double *d_out_dist) {
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
+            return scan_typed<double, double>(static_cast<const double *>(d_query), ld_q, d_qlist, nsub, dim, kk, flags, d_out_idx, d_out_dist);
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
+            return scan_typed<double, float>(static_cast<const float *>(d_query), ld_q, d_qlist, nsub, dim, kk, flags, d_out_idx, d_out_dist);
+        if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
+            return scan_typed<float, double>(static_cast<const double *>(d_query), ld_q, d_qlist, nsub, dim, kk, flags, d_out_idx, d_out_dist);
+        return scan_typed<float, float>(static_cast<const float *>(d_query), ld_q, d_qlist, nsub, dim, kk, flags, d_out_idx, d_out_dist);
+    }
+
+    // ------------------------------------------------------------------ rerank dispatch
+    template <int C>
+    int launch_rerank(const void *d_query, int q_dtype, int64_t nq, const RerankParams &rp) {
+        prof_begin(K_RERANK);
+        const unsigned g = static_cast<unsigned>(nq);
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
+            rerank_kernel<double, double, C><<<g, 128, 0, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), rp);
+        else if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
+            rerank_kernel<double, float, C><<<g, 128, 0, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), rp);
+        else if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
+            rerank_kernel<float, double, C><<<g, 128, 0, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), rp);
+        else
+            rerank_kernel<float, float, C><<<g, 128, 0, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), rp);
+        prof_end();
+        CU_TRY(cudaGetLastError());
+        return B200KNN_OK;
+    }
+
+    template <int C>
+    int tensor_pass(const void *d_query, int q_dtype, int64_t nq, int64_t ld_q, int dim, int kp, int kk, unsigned flags,
+                    int32_t *d_out_idx, double *d_out_dist) {
+        TRY(q_bf.ensure(static_cast<size_t>(nq) * kp));
+        TRY(qnorm_bf.ensure(nq));
+        TRY(qnorm_ex.ensure(nq));
+        TRY(launch_convert(d_query, q_dtype, nq, ld_q, dim, kp, q_bf.p, qnorm_bf.p, qnorm_ex.p, scalars.p + 2));
+        CUtensorMap tmap_q;
+        TRY(make_tmap(&tmap_q, q_bf.p, nq, kp, BM));
+        const Sched s = plan(nq, kp);
+        TRY(cand_s.ensure(static_cast<size_t>(nq) * s.chunks * C));
+        TRY(cand_i.ensure(static_cast<size_t>(nq) * s.chunks * C));
+        DistParams dp;
+        dp.xnorm = xnorm_bf.p;
+        dp.n = static_cast<int>(n);
+        dp.nq = static_cast<int>(nq);
+        dp.num_kb = (kp + BK - 1) / BK;
+        dp.num_qtiles = s.qt;
+        dp.num_ntiles = s.nt;
+        dp.tiles_per_chunk = s.tiles_per_chunk;
+        dp.num_chunks = s.chunks;
+        dp.qgroup = s.qgroup;
+        dp.cand_s = cand_s.p;
+        dp.cand_i = cand_i.p;
+        prof_begin(K_DISTANCE, 2.0 * static_cast<double>(nq) * static_cast<double>(n) * dim);
+        dist_topc_kernel<C><<<s.grid, DIST_THREADS, DIST_SMEM_BYTES, stream>>>(tmap_q, tmap_x, dp);
+        prof_end();
+        CU_TRY(cudaGetLastError());
+
+        TRY(uncert_list.ensure(nq));
+        RerankParams rp;
+        rp.cand_s = cand_s.p;
+        rp.cand_i = cand_i.p;
+        rp.num_chunks = s.chunks;
+        rp.dim = dim;
+        rp.ld_x = ld_x;
+        rp.ld_q = ld_q;
+        rp.n = static_cast<int>(n);
+        rp.kk = kk;
+        rp.index_base = index_base;
+        rp.flags = flags;
+        rp.qnorm_bf = qnorm_bf.p;
+        rp.qnorm_ex = qnorm_ex.p;
+        rp.max_xnorm_bf_bits = scalars.p;
+        rp.max_xnorm_ex_bits = scalars.p + 1;
+        rp.kp = kp;
+        rp.out_idx = d_out_idx;
+        rp.out_dist = d_out_dist;
+        rp.uncert_count = reinterpret_cast<int *>(scalars.p + 4);
+        rp.uncert_list = uncert_list.p;
+        CU_TRY(cudaMemsetAsync(scalars.p + 4, 0, sizeof(unsigned int), stream));
+        TRY(launch_rerank<C>(d_query, q_dtype, nq, rp));
+        if (!(flags & B200KNN_FLAG_NO_CERTIFY)) {
+            CU_TRY(cudaMemcpyAsync(h_count, scalars.p + 4, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CU_TRY(cudaStreamSynchronize(stream));
+            const int nun = *h_count;
+            if (nun > 0) {
+                stats.uncertified += nun;
+                TRY(scan(d_query, q_dtype, ld_q, uncert_list.p, nun, dim, kk, flags, d_out_idx, d_out_dist));
+            }
+        }
+        return B200KNN_OK;
+    }
+
+    // queries and outputs on this device; nq bounded by the caller's chunking
+    int query_device(const void *d_query, int q_dtype, int64_t nq, int64_t ld_q, int dim, int kp, int k, unsigned flags,
+                     int32_t *d_out_idx, double *d_out_dist) {
+        if (nq <= 0) return B200KNN_OK;
+        CU_TRY(cudaSetDevice(device));
+        const int kk = static_cast<int>(std::min<int64_t>(k, n));
+        stats.queries += nq;
+        if (kk > 16 || (flags & B200KNN_FLAG_FORCE_SCAN))
+            return scan(d_query, q_dtype, ld_q, nullptr, static_cast<int>(nq), dim, kk, flags, d_out_idx, d_out_dist);
+        if (kk <= 4) return tensor_pass<16>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist);
+        return tensor_pass<32>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist);
+    }
+};
+
+constexpr int64_t QUERY_CHUNK = 32768;   // query rows per device pass (bounds workspace; 256 query tiles)
+
+}  // namespace
+
+struct b200knn_index {
+    int dim = 0;
+    int kp = 0;
+    std::vector<int> device_ids;
+    std::vector<Shard> shards;
+    int64_t n_total = 0;
+    bool devices_ready = false;
+    void *user_stream = nullptr;
+    bool profiling = false;
+    // multi-device gather buffers on shard 0
+    DevBuf<int32_t> g_idx;
+    DevBuf<double> g_dist;
+
+    int ensure_devices() {
+        if (devices_ready) return B200KNN_OK;
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count <= 0) {
+            cudaGetLastError();
+            return fail(B200KNN_ENODEVICE, "no CUDA device available (%s); libb200knn has no CPU fallback",
+                        e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        }
+        if (device_ids.empty()) {
+            int cur = 0;
+            cudaGetDevice(&cur);
+            device_ids.push_back(cur);
+        }
+        for (int d : device_ids)
+            if (d < 0 || d >= count) return fail(B200KNN_EINVAL, "device id %d out of range (%d devices)", d, count);
+        shards.resize(device_ids.size());
+        for (size_t i = 0; i < shards.size(); i++) {
+            TRY(shards[i].init(device_ids[i]));
+            shards[i].profiling = profiling;
+            if (user_stream && shards.size() == 1) shards[i].stream = static_cast<cudaStream_t>(user_stream);
+        }
+        for (size_t i = 0; i < shards.size(); i++)
+            for (size_t j = 0; j < shards.size(); j++)
+                if (i != j) {
+                    cudaSetDevice(device_ids[i]);
+                    cudaDeviceEnablePeerAccess(device_ids[j], 0);
+                    cudaGetLastError();
+                }
+        devices_ready = true;
+        return B200KNN_OK;
+    }
+};
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char *b200knn_last_error(void) { return g_last_error.c_str(); }
+int b200knn_abi_version(void) { return B200KNN_ABI_VERSION; }
+
+int b200knn_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int d = 0; d < count; d++) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) ok++;
+    }
+    return ok;
+}
+
+int b200knn_create(int dim, int n_devices, const int *device_ids, b200knn_index **out) {
+    if (!out) return fail(B200KNN_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (dim <= 0) return fail(B200KNN_EINVAL, "dim must be positive (got %d)", dim);
+    if (n_devices > MERGE_MAX_LISTS) return fail(B200KNN_EINVAL, "at most %d devices per handle", MERGE_MAX_LISTS);
+    b200knn_index *ix = new (std::nothrow) b200knn_index();
+    if (!ix) return fail(B200KNN_ENOMEM, "out of host memory");
+    ix->dim = dim;
+    ix->kp = (dim + 7) / 8 * 8;   // BF16 row pitch must be a multiple of 16 bytes for TMA
+    for (int i = 0; i < n_devices; i++) ix->device_ids.push_back(device_ids ? device_ids[i] : i);
+    *out = ix;
+    return B200KNN_OK;
+}
+
+int b200knn_destroy(b200knn_index *ix) {
+    if (!ix) return B200KNN_OK;
+    for (auto &s : ix->shards) {
+        if (s.ready) cudaSetDevice(s.device);
+        s.destroy();
+    }
+    if (ix->devices_ready && !ix->shards.empty()) {
+        cudaSetDevice(ix->shards[0].device);
+        ix->g_idx.release();
+        ix->g_dist.release();
+    }
+    delete ix;
+    return B200KNN_OK;
+}
+
+int b200knn_clear(b200knn_index *ix) {
+    if (!ix) return fail(B200KNN_EINVAL, "index is NULL");
+    for (auto &s : ix->shards) s.clear_pool();
+    ix->n_total = 0;
+    return B200KNN_OK;
+}
+
+int64_t b200knn_num_points(const b200knn_index *ix) { return ix ? ix->n_total : 0; }
+int b200knn_dim(const b200knn_index *ix) { return ix ? ix->dim : 0; }
+
+int b200knn_set_stream(b200knn_index *ix, void *stream) {
+    if (!ix) return fail(B200KNN_EINVAL, "index is NULL");
+    if (ix->device_ids.size() > 1) return fail(B200KNN_EINVAL, "set_stream is only valid for single-device handles");
+    ix->user_stream = stream;
+    for (auto &s : ix->shards) s.stream = stream ? static_cast<cudaStream_t>(stream) : s.own_stream;
+    return B200KNN_OK;
+}
+
+int b200knn_set_profiling(b200knn_index *ix, int profiling) {
+    if (!ix) return fail(B200KNN_EINVAL, "index is NULL");
+    ix->profiling = profiling != 0;
+    for (auto &s : ix->shards) s.profiling = ix->profiling;
+    return B200KNN_OK;
+}
+
+int b200knn_get_stats(b200knn_index *ix, b200knn_stats *out) {
+    if (!ix || !out) return fail(B200KNN_EINVAL, "NULL argument");
+    std::memset(out, 0, sizeof(*out));
+    for (auto &s : ix->shards) {
+        if (!s.ready) continue;
+        cudaSetDevice(s.device);
+        cudaStreamSynchronize(s.stream);
+        s.drain_events();
+        out->kernel_launches += s.stats.kernel_launches;
+        out->queries = std::max(out->queries, s.stats.queries);
+        out->uncertified += s.stats.uncertified;
+        out->ms_convert += s.stats.ms_convert;
+        out->ms_distance += s.stats.ms_distance;
+        out->ms_rerank += s.stats.ms_rerank;
+        out->ms_scan += s.stats.ms_scan;
+        out->distance_launches += s.stats.distance_launches;
+        out->distance_flops += s.stats.distance_flops;
+    }
+    return B200KNN_OK;
+}
+
+int b200knn_reset_stats(b200knn_index *ix) {
+    if (!ix) return fail(B200KNN_EINVAL, "index is NULL");
+    for (auto &s : ix->shards) {
+        if (s.ready) { cudaSetDevice(s.device); cudaStreamSynchronize(s.stream); s.drain_events(); }
+        s.stats = b200knn_stats{};
+    }
+    return B200KNN_OK;
+}
+
+static int check_matrix_args(const b200knn_index *ix, const void *p, int dtype, int64_t rows, int64_t ld, const char *what) {
+    if (!ix) return fail(B200KNN_EINVAL, "index is NULL");
+    if (!p && rows > 0) return fail(B200KNN_EINVAL, "%s pointer is NULL", what);
+    if (dtype != B200KNN_F64 && dtype != B200KNN_F32) return fail(B200KNN_EINVAL, "%s dtype %d is not B200KNN_F64/F32", what, dtype);
+    if (rows < 0) return fail(B200KNN_EINVAL, "%s row count is negative", what);
+    if (ld < ix->dim) return fail(B200KNN_EINVAL, "%s leading dimension %lld < dim %d", what, (long long)ld, ix->dim);
+    if (rows > 0x7fffffffll - 512) return fail(B200KNN_EINVAL, "%s has too many rows (%lld)", what, (long long)rows);
+    return B200KNN_OK;
+}
+
+int b200knn_add_device(b200knn_index *ix, const void *d_data, int dtype, int64_t n, int64_t ld, int64_t index_base) {
+    TRY(check_matrix_args(ix, d_data, dtype, n, ld, "data"));
+    if (ix->n_total > 0) return fail(B200KNN_ESTATE, "index already holds %lld points; clear() it first", (long long)ix->n_total);
+    if (ix->device_ids.size() > 1) return fail(B200KNN_EINVAL, "add_device is only valid for single-device handles");
+    if (n == 0) return B200KNN_OK;
+    TRY(ix->ensure_devices());
+    Shard &s = ix->shards[0];
+    CU_TRY(cudaSetDevice(s.device));
+    TRY(s.attach_pool(d_data, false, dtype, n, ld, ix->dim, ix->kp, index_base));
+    TRY(s.launch_convert(d_data, dtype, n, ld, ix->dim, ix->kp, s.x_bf.p, s.xnorm_bf.p, s.xnorm_ex.p, s.scalars.p));
+    ix->n_total = n;
+    return B200KNN_OK;
+}
+
+int b200knn_add(b200knn_index *ix, const void *data, int dtype, int64_t n, int64_t ld) {
+    TRY(check_matrix_args(ix, data, dtype, n, ld, "data"));
+    if (ix->n_total > 0) return fail(B200KNN_ESTATE, "index already holds %lld points; clear() it first", (long long)ix->n_total);
+    if (n == 0) return B200KNN_OK;
+    TRY(ix->ensure_devices());
+    const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
+    const int G = static_cast<int>(ix->shards.size());
+    const int64_t per = (n + G - 1) / G;
+    for (int g = 0; g < G; g++) {
+        Shard &s = ix->shards[g];
+        const int64_t r0 = std::min<int64_t>(n, per * g), r1 = std::min<int64_t>(n, per * (g + 1));
+        const int64_t rows = r1 - r0;
+        if (rows <= 0) { s.n = 0; continue; }
+        CU_TRY(cudaSetDevice(s.device));
+        void *d_rows = nullptr;
+        CU_TRY(cudaMalloc(&d_rows, static_cast<size_t>(rows) * ix->dim * esz));
+        int r = s.attach_pool(d_rows, true, dtype, rows, ix->dim, ix->dim, ix->kp, r0);
+        if (r != B200KNN_OK) return r;
+        // upload in row blocks so the convert kernel of block i overlaps the copy of block i+1
+        const int64_t block_rows = std::max<int64_t>(1, (256ll << 20) / (static_cast<int64_t>(ix->dim) * esz));
+        const char *src = static_cast<const char *>(data) + static_cast<size_t>(r0) * ld * esz;
+        for (int64_t b0 = 0; b0 < rows; b0 += block_rows) {
+            const int64_t br = std::min(block_rows, rows - b0);
+            char *dst = static_cast<char *>(d_rows) + static_cast<size_t>(b0) * ix->dim * esz;
+            CU_TRY(cudaMemcpy2DAsync(dst, ix->dim * esz, src + static_cast<size_t>(b0) * ld * esz, ld * esz, ix->dim * esz, br,
+                                     cudaMemcpyHostToDevice, s.stream));
+            TRY(s.launch_convert(dst, dtype, br, ix->dim, ix->dim, ix->kp, s.x_bf.p + static_cast<size_t>(b0) * ix->kp,
+                                 s.xnorm_bf.p + b0, s.xnorm_ex.p + b0, s.scalars.p));
+        }
+    }
+    for (auto &s : ix->shards) {
+        CU_TRY(cudaSetDevice(s.device));
+        CU_TRY(cudaStreamSynchronize(s.stream));   // the caller may free / overwrite `data` after return
+    }
+    ix->n_total = n;
+    return B200KNN_OK;
+}
+
+int b200knn_merge_topk_device(const int32_t *d_idx, const double *d_dist, int n_lists, int64_t nq, int kk, int32_t *d_out_idx,
+                              double *d_out_dist, void *stream) {
+    if (!d_idx || !d_dist || !d_out_idx || !d_out_dist) return fail(B200KNN_EINVAL, "NULL buffer");
+    if (n_lists <= 0 || n_lists > MERGE_MAX_LISTS) return fail(B200KNN_EINVAL, "n_lists must be in 1..%d", MERGE_MAX_LISTS);
+    if (nq < 0 || kk <= 0) return fail(B200KNN_EINVAL, "bad nq/kk");
+    if (nq == 0) return B200KNN_OK;
+    const unsigned blocks = static_cast<unsigned>((nq + 127) / 128);
+    merge_topk_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_idx, d_dist, n_lists, nq, kk, d_out_idx, d_out_dist);
+    CU_TRY(cudaGetLastError());
+    return B200KNN_OK;
+}
+
+int b200knn_query_device(b200knn_index *ix, const void *d_query, int dtype, int64_t nq, int64_t ld, int k, unsigned flags,
+                         int32_t *d_out_idx, double *d_out_dist, int *out_kk) {
+    TRY(check_matrix_args(ix, d_query, dtype, nq, ld, "query"));
+    if (k <= 0) return fail(B200KNN_EINVAL, "k must be positive (got %d)", k);
+    if (ix->n_total <= 0) return fail(B200KNN_ESTATE, "query on an empty index");
+    if (ix->shards.size() != 1) return fail(B200KNN_EINVAL, "query_device is only valid for single-device handles");
+    if (!d_out_idx || !d_out_dist) return fail(B200KNN_EINVAL, "output buffer is NULL");
+    Shard &s = ix->shards[0];
+    const int kk = static_cast<int>(std::min<int64_t>(k, s.n));
+    if (out_kk) *out_kk = kk;
+    const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
+    for (int64_t q0 = 0; q0 < nq; q0 += QUERY_CHUNK) {
+        const int64_t cq = std::min(QUERY_CHUNK, nq - q0);
+        TRY(s.query_device(static_cast<const char *>(d_query) + static_cast<size_t>(q0) * ld * esz, dtype, cq, ld, ix->dim, ix->kp, k, flags,
+                           d_out_idx + q0 * kk, d_out_dist + q0 * kk));
+    }
+    return B200KNN_OK;
+}
+
+int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, int64_t ld, int k, unsigned flags, int32_t *out_idx,
+                  double *out_dist, int *out_kk) {
+    TRY(check_matrix_args(ix, query, dtype, nq, ld, "query"));
+    if (k <= 0) return fail(B200KNN_EINVAL, "k must be positive (got %d)", k);
+    if (ix->n_total <= 0) return fail(B200KNN_ESTATE, "query on an empty index");
+    if (nq > 0 && (!out_idx || !out_dist)) return fail(B200KNN_EINVAL, "output buffer is NULL");
+    const int kk = static_cast<int>(std::min<int64_t>(k, ix->n_total));
+    if (out_kk) *out_kk = kk;
+    if (nq == 0) return B200KNN_OK;
+    const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
+    const int G = static_cast<int>(ix->shards.size());
+    const int dim = ix->dim;
+    // host chunks: bounded staging, and the H2D of chunk i+1 can overlap the compute of chunk i
+    const int64_t chunk = std::max<int64_t>(BM, std::min<int64_t>(QUERY_CHUNK, (256ll << 20) / (static_cast<int64_t>(dim) * esz) / BM * BM));
+    for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+        const int64_t cq = std::min(chunk, nq - q0);
+        const char *src = static_cast<const char *>(query) + static_cast<size_t>(q0) * ld * esz;
+        int active = 0;
+        for (int g = 0; g < G; g++) {
+            Shard &s = ix->shards[g];
+            if (s.n <= 0) continue;
+            active++;
+            CU_TRY(cudaSetDevice(s.device));
+            TRY(s.q_stage.ensure(static_cast<size_t>(cq) * dim * esz));
+            // a shard may hold fewer than k rows: its list is padded to kk with (-1, DBL_MAX) by the merge input contract
+            TRY(s.out_idx.ensure(static_cast<size_t>(cq) * kk));
+            TRY(s.out_dist.ensure(static_cast<size_t>(cq) * kk));
+            CU_TRY(cudaMemcpy2DAsync(s.q_stage.p, dim * esz, src, ld * esz, dim * esz, cq, cudaMemcpyHostToDevice, s.stream));
+        }
+        if (active == 1 && G == 1) {
+            Shard &s = ix->shards[0];
+            TRY(s.query_device(s.q_stage.p, dtype, cq, dim, dim, ix->kp, k, flags, s.out_idx.p, s.out_dist.p));
+            CU_TRY(cudaMemcpyAsync(out_idx + q0 * kk, s.out_idx.p, static_cast<size_t>(cq) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+            CU_TRY(cudaMemcpyAsync(out_dist + q0 * kk, s.out_dist.p, static_cast<size_t>(cq) * kk * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+            CU_TRY(cudaStreamSynchronize(s.stream));
+            continue;
+        }
+        // ---- multi-device: local top-k per shard, gather to shard 0 over NVLink, k-way merge there ----
+        Shard &s0 = ix->shards[0];
+        CU_TRY(cudaSetDevice(s0.device));
+        TRY(ix->g_idx.ensure(static_cast<size_t>(G) * cq * kk));
+        TRY(ix->g_dist.ensure(static_cast<size_t>(G) * cq * kk));
+        int lists = 0;
+        std::vector<cudaEvent_t> done;
+        for (int g = 0; g < G; g++) {
+            Shard &s = ix->shards[g];
+            if (s.n <= 0) continue;
+            CU_TRY(cudaSetDevice(s.device));
+            const int kg = static_cast<int>(std::min<int64_t>(kk, s.n));
+            if (kg < kk) {   // pad: fill with (-1, +inf) first, then the kg real columns are written by a strided copy below
+                return fail(B200KNN_EINVAL, "a shard holds fewer rows (%lld) than k=%d; use fewer devices", (long long)s.n, kk);
+            }
+            TRY(s.query_device(s.q_stage.p, dtype, cq, dim, dim, ix->kp, kk, flags, s.out_idx.p, s.out_dist.p));
+            CU_TRY(cudaMemcpyPeerAsync(ix->g_idx.p + static_cast<size_t>(lists) * cq * kk, s0.device, s.out_idx.p, s.device,
+                                       static_cast<size_t>(cq) * kk * sizeof(int32_t), s.stream));
+            CU_TRY(cudaMemcpyPeerAsync(ix->g_dist.p + static_cast<size_t>(lists) * cq * kk, s0.device, s.out_dist.p, s.device,
+                                       static_cast<size_t>(cq) * kk * sizeof(double), s.stream));
+            cudaEvent_t ev;
+            CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            CU_TRY(cudaEventRecord(ev, s.stream));
+            done.push_back(ev);
+            lists++;
+        }
+        CU_TRY(cudaSetDevice(s0.device));
+        for (auto ev : done) {
+            CU_TRY(cudaStreamWaitEvent(s0.stream, ev, 0));
+        }
+        TRY(s0.out_idx.ensure(static_cast<size_t>(cq) * kk));
+        TRY(b200knn_merge_topk_device(ix->g_idx.p, ix->g_dist.p, lists, cq, kk, s0.out_idx.p, s0.out_dist.p, s0.stream));
+        s0.stats.kernel_launches++;
+        CU_TRY(cudaMemcpyAsync(out_idx + q0 * kk, s0.out_idx.p, static_cast<size_t>(cq) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s0.stream));
+        CU_TRY(cudaMemcpyAsync(out_dist + q0 * kk, s0.out_dist.p, static_cast<size_t>(cq) * kk * sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
+        CU_TRY(cudaStreamSynchronize(s0.stream));
+        for (auto ev : done) cudaEventDestroy(ev);
+    }
+    return B200KNN_OK;
+}
+
+}  // extern "C"
