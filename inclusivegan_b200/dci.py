@@ -1,0 +1,491 @@
+"""Drop-in `dci` module: the reference's `DCI` Python class over the B200 exact-kNN C ABI.
+
+The reference trainer does `sys.path.append('./dci_code'); from dci import DCI`
+(training/training_loop.py:21-23) and then uses `DCI(dim, num_comp_indices, num_simp_indices)`,
+`reset()`, `add(...)`, `query(...)` (training_loop.py:197,367-368,383,398).  This module keeps that
+surface — names, argument meaning, defaults, return types and the exception types/messages of the
+reference's dci_code/src/dci.py — but every call lands in inclusivegan_b200/libb200knn.so
+(include/b200knn.h) via ctypes over NumPy buffers.  No TensorFlow, Triton or torch on the path.
+
+Differences from the reference, all deliberate:
+  * results are EXACT (the reference is approximate); per query exactly min(k, num_points)
+    neighbours come back.  The approximation knobs (num_levels, field_of_view, blind,
+    num_to_visit, num_to_retrieve, prop_to_visit, prop_to_retrieve) are validated like the
+    reference validates them and then ignored.  `blind=True` returns true distances, not
+    projection-space priorities (reference: dci.c:446-457).
+  * add() copies the rows to the GPU(s); the reference borrows the caller's buffer
+    (py_dci.c:118-123).  A Python reference to `data` is still held until clear()/reset(), like
+    dci.py:270.
+  * float32 arrays are accepted as an extension where the reference raises TypeError; pass
+    strict=True to the constructor to get the reference's float64-only behaviour.
+  * there is NO CPU fallback: without a usable sm_100 GPU, add()/query() raise RuntimeError.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+__all__ = ["DCI", "DeviceKNN", "ProtectedArray", "B200KNNError", "load_library"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "libb200knn.so"
+_lib = None
+
+F64, F32 = 0, 1
+FLAG_SQUARED, FLAG_NO_CERTIFY, FLAG_FORCE_SCAN = 1, 2, 4
+
+
+class B200KNNError(RuntimeError):
+    """A libb200knn call failed (carries the library's status code and message)."""
+
+    def __init__(self, code, message):
+        RuntimeError.__init__(self, "libb200knn error %d: %s" % (code, message))
+        self.code = code
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("kernel_launches", ctypes.c_int64), ("queries", ctypes.c_int64), ("uncertified", ctypes.c_int64),
+                ("ms_convert", ctypes.c_double), ("ms_distance", ctypes.c_double), ("ms_rerank", ctypes.c_double),
+                ("ms_scan", ctypes.c_double), ("distance_launches", ctypes.c_int64), ("distance_flops", ctypes.c_double)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+def load_library(path=None):
+    """Load libb200knn.so (in-tree build).  Fails loudly if it is missing: there is no fallback path."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or os.environ.get("B200KNN_LIBRARY") or os.path.join(_HERE, _LIB_NAME)
+    if not os.path.exists(path):
+        raise RuntimeError("%s not found — build it with `python -m inclusivegan_b200.build` "
+                           "(nvcc, sm_100a); there is no CPU or pure-Python fallback" % path)
+    lib = ctypes.CDLL(path)
+    vp, i32, i64, u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint
+    lib.b200knn_create.restype = i32
+    lib.b200knn_create.argtypes = [i32, i32, ctypes.POINTER(i32), ctypes.POINTER(vp)]
+    lib.b200knn_destroy.restype = i32
+    lib.b200knn_destroy.argtypes = [vp]
+    lib.b200knn_clear.restype = i32
+    lib.b200knn_clear.argtypes = [vp]
+    lib.b200knn_num_points.restype = i64
+    lib.b200knn_num_points.argtypes = [vp]
+    lib.b200knn_dim.restype = i32
+    lib.b200knn_dim.argtypes = [vp]
+    lib.b200knn_add.restype = i32
+    lib.b200knn_add.argtypes = [vp, vp, i32, i64, i64]
+    lib.b200knn_query.restype = i32
+    lib.b200knn_query.argtypes = [vp, vp, i32, i64, i64, i32, u32, vp, vp, ctypes.POINTER(i32)]
+    lib.b200knn_set_stream.restype = i32
+    lib.b200knn_set_stream.argtypes = [vp, vp]
+    lib.b200knn_add_device.restype = i32
+    lib.b200knn_add_device.argtypes = [vp, vp, i32, i64, i64, i64]
+    lib.b200knn_query_device.restype = i32
+    lib.b200knn_query_device.argtypes = [vp, vp, i32, i64, i64, i32, u32, vp, vp, ctypes.POINTER(i32)]
+    lib.b200knn_merge_topk_device.restype = i32
+    lib.b200knn_merge_topk_device.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp]
+    lib.b200knn_set_profiling.restype = i32
+    lib.b200knn_set_profiling.argtypes = [vp, i32]
+    lib.b200knn_get_stats.restype = i32
+    lib.b200knn_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    lib.b200knn_reset_stats.restype = i32
+    lib.b200knn_reset_stats.argtypes = [vp]
+    lib.b200knn_last_error.restype = ctypes.c_char_p
+    lib.b200knn_last_error.argtypes = []
+    lib.b200knn_abi_version.restype = i32
+    lib.b200knn_abi_version.argtypes = []
+    lib.b200knn_device_count.restype = i32
+    lib.b200knn_device_count.argtypes = []
+    if lib.b200knn_abi_version() != 1:
+        raise RuntimeError("libb200knn ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _check(code):
+    if code != 0:
+        raise B200KNNError(code, load_library().b200knn_last_error().decode("utf-8", "replace"))
+
+
+class ProtectedArray(object):
+    """Array wrapper whose element reads/writes can be gated (same contract as dci.py:30-59)."""
+
+    def __init__(self, base_array, when_readable=None, read_error=None, when_writable=None, write_error=None):
+        self._base = base_array
+        self._when_readable = when_readable
+        self._read_error = read_error
+        self._when_writable = when_writable
+        self._write_error = write_error
+
+    def __getitem__(self, key):
+        if self._when_readable is not None and not self._when_readable(key):
+            raise (RuntimeError("array is not currently readable") if self._read_error is None else self._read_error(key))
+        return self._base[key]
+
+    def __setitem__(self, key, value):
+        if self._when_writable is not None and not self._when_writable(key):
+            raise (RuntimeError("array is not currently writable") if self._write_error is None else self._write_error(key))
+        self._base[key] = value
+
+    def __getattr__(self, name):
+        return getattr(self._base, name)
+
+    def __repr__(self):
+        return repr(self._base)
+
+
+def _require_positive_int(x):
+    # dci.py:107-111
+    if not isinstance(x, int):
+        raise TypeError("number must be an integer")
+    if x <= 0:
+        raise ValueError("number must be positive")
+
+
+def _draw_unit_directions(rows, dim):
+    """Shape-/distribution-compatible stand-in for dci_gen_proj_vec (dci.c:55-71): Gaussian unit vectors."""
+    v = np.random.standard_normal((rows, dim))
+    v /= np.maximum(np.linalg.norm(v, axis=1, keepdims=True), 1e-300)
+    return v
+
+
+class DCI(object):
+    """Exact k-nearest-neighbour index with the reference `DCI` interface (dci.py:61-340)."""
+
+    def __init__(self, dim, num_comp_indices=2, num_simp_indices=7, devices=None, strict=False):
+        """dim, num_comp_indices, num_simp_indices: as dci.py:63.  Extensions (keyword-only in spirit):
+        devices — GPU ids to row-shard the pool over (None: $B200KNN_DEVICES or the current device);
+        strict  — refuse non-float64 data like the reference (dci.py:116-117)."""
+        self._dim = int(dim)
+        self._num_comp_indices = num_comp_indices
+        self._num_simp_indices = num_simp_indices
+        self._strict = bool(strict)
+        self._lib = load_library()
+        if devices is None and os.environ.get("B200KNN_DEVICES"):
+            devices = [int(t) for t in os.environ["B200KNN_DEVICES"].split(",") if t.strip() != ""]
+        if devices is None:
+            n_dev, ids = 0, None
+        else:
+            devices = [int(d) for d in devices]
+            n_dev, ids = len(devices), (ctypes.c_int * len(devices))(*devices)
+        handle = ctypes.c_void_p()
+        _check(self._lib.b200knn_create(self._dim, n_dev, ids, ctypes.byref(handle)))
+        self._handle = handle
+        # Exact search uses no projections; the property is kept shape-correct (m*L x dim, float64) and
+        # writable-when-empty because callers may read or pin it (dci.py:69,93-105; py_dci.c:299-302).
+        self._proj_vec = _draw_unit_directions(num_comp_indices * num_simp_indices, self._dim)
+        self._array = None
+        self._orig_indices = None
+        self._num_levels = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                self._lib.b200knn_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    # ---- properties (dci.py:73-105) -------------------------------------------------------------
+    @property
+    def dim(self):
+        return self._dim
+
+    @property
+    def num_comp_indices(self):
+        return self._num_comp_indices
+
+    @property
+    def num_simp_indices(self):
+        return self._num_simp_indices
+
+    @property
+    def num_points(self):
+        return int(self._lib.b200knn_num_points(self._handle))
+
+    @property
+    def num_levels(self):
+        return self._num_levels
+
+    def _empty_guard_error(self, _=None):
+        return AttributeError("can only set projection vectors when the database is empty")
+
+    @property
+    def proj_vec(self):
+        return ProtectedArray(self._proj_vec, when_writable=lambda _: self.num_points == 0, write_error=self._empty_guard_error)
+
+    @proj_vec.setter
+    def proj_vec(self, new_proj_vec):
+        if self.num_points != 0:
+            raise self._empty_guard_error()
+        new_proj_vec = np.asarray(new_proj_vec)     # no broadcasting on direct assignment (dci.py:100-104)
+        if new_proj_vec.shape != self._proj_vec.shape:
+            raise ValueError("mismatch between the expected shape of projection vectors (%s) and the supplied shape (%s)"
+                             % (repr(self._proj_vec.shape), repr(new_proj_vec.shape)))
+        self._proj_vec[...] = new_proj_vec
+
+    def stats(self):
+        """Counters of the native library (kernel launches, uncertified queries, per-kernel ms when profiling)."""
+        s = Stats()
+        _check(self._lib.b200knn_get_stats(self._handle, ctypes.byref(s)))
+        return s.as_dict()
+
+    def set_profiling(self, on):
+        _check(self._lib.b200knn_set_profiling(self._handle, int(bool(on))))
+
+    # ---- argument checking (dci.py:107-221) -------------------------------------------------------
+    def _dtype_code(self, arr):
+        if arr.dtype == np.float64:
+            return F64
+        if arr.dtype == np.float32 and not self._strict:
+            return F32
+        raise TypeError("array must consist of double-precision floats")
+
+    def _check_dim(self, arr):
+        if arr.ndim != 2 or arr.shape[1] != self.dim:
+            raise ValueError("mismatch between array dimension (%d) and the declared dimension of this DCI instance (%d)"
+                             % (arr.shape[1] if arr.ndim == 2 else -1, self.dim))
+
+    def _check_data(self, data):
+        # dci.py:113-144: right width, float64, C-order, and not a view into another array
+        if not isinstance(data, np.ndarray):
+            raise TypeError("array must consist of double-precision floats")
+        self._check_dim(data)
+        self._dtype_code(data)
+        if not data.flags.c_contiguous:
+            raise ValueError("the memory layout of array must be in row-major (C-order)")
+        if data.base is not None:
+            root = data
+            while isinstance(root.base, np.ndarray):
+                root = root.base
+            same_start = (isinstance(root, np.ndarray) and root.base is None and root.ctypes.data == data.ctypes.data
+                          and root.size == data.size)
+            if not same_start:
+                raise ValueError("array must not be derived from another array, except via the transpose operator. "
+                                 "Pass in the original array and specify the indices or make a copy of the derived array.")
+
+    def _fix_query(self, query):
+        # dci.py:121-127: queries are silently cast to C-contiguous float64
+        query = np.asarray(query)
+        if query.ndim != 2 or query.shape[1] != self.dim:
+            raise ValueError("mismatch between array dimension (%d) and the declared dimension of this DCI instance (%d)"
+                             % (query.shape[1] if query.ndim == 2 else -1, self.dim))
+        if query.dtype == np.float64 or (query.dtype == np.float32 and not self._strict):
+            return np.ascontiguousarray(query)
+        return np.ascontiguousarray(query, dtype=np.float64)
+
+    @staticmethod
+    def _select_rows(data, indices):
+        """dci.py:146-221 — returns (is_contiguous, (start, stop) | int32 index array)."""
+        n = data.shape[0]
+        need_bounds_check = False
+        if indices is None:
+            return True, (0, n)
+        if isinstance(indices, slice):
+            start = 0 if indices.start is None else indices.start
+            stop = n if indices.stop is None else indices.stop
+            step = 1 if indices.step is None else indices.step
+            if start < 0:
+                start += n
+            if stop < 0:
+                stop += n
+            start, stop = max(start, 0), min(stop, n)
+            if step == 1:
+                return True, (start, stop)
+            return False, np.arange(start, stop, step, dtype=np.intc)
+        if isinstance(indices, (int, np.integer)) and not isinstance(indices, (bool, np.bool_)):
+            i = int(indices) + (n if indices < 0 else 0)
+            if i < 0 or i >= n:
+                raise IndexError("index out of bounds")
+            return True, (i, i + 1)
+        if isinstance(indices, np.ndarray):
+            if indices.ndim != 1:
+                raise IndexError("indices must be in an one-dimensional array")
+            if indices.dtype == np.bool_:
+                if indices.shape[0] != n:
+                    raise IndexError("mismatch between the number of boolean indices (%d) and array dimension (%d)"
+                                     % (indices.shape[0], n))
+                return False, np.nonzero(indices)[0].astype(np.intc)
+            if indices.dtype.kind in "iu":
+                sel = indices.astype(np.intc, copy=True)
+                sel[sel < 0] += n
+                need_bounds_check = True
+            else:
+                raise TypeError("indices must be integers or booleans")
+        elif isinstance(indices, list):
+            if len(indices) == 0:
+                return False, np.zeros(0, dtype=np.intc)
+            first = indices[0]
+            if isinstance(first, (bool, np.bool_)):
+                return False, np.nonzero(indices)[0].astype(np.intc)
+            if isinstance(first, (int, np.integer)):
+                sel = np.array(indices, dtype=np.intc)
+                sel[sel < 0] += n
+                need_bounds_check = True
+            elif isinstance(first, list):
+                raise IndexError("indices must be in an one-dimensional array")
+            else:
+                raise TypeError("indices must be integers or booleans")
+        else:
+            raise TypeError("indices must be None, a slice object, an integer, an array or list of integers")
+        if need_bounds_check:
+            bad = (sel < 0) | (sel >= n)
+            if np.any(bad):
+                raise IndexError("some indices (e.g. %d) out of bounds" % int(np.asarray(indices)[bad][0]))
+        return False, sel
+
+    # ---- add / query / clear / reset ------------------------------------------------------------------
+    def add(self, data, indices=None, num_levels=2, field_of_view=10, blind=False, num_to_visit=-1, num_to_retrieve=-1,
+            prop_to_visit=-1.0, prop_to_retrieve=-1.0):
+        """Index `data` (N x dim, float64, C-order, a base array) — dci.py:224-270.
+
+        One array per index (RuntimeError on a second add, dci.py:228-229).  `indices` selects rows
+        (None / slice / int / int or bool ndarray / list); results of query() refer to row numbers of
+        `data`.  The construction knobs are accepted, validated (field_of_view must be a positive int
+        when num_levels >= 3, dci.py:231-234) and otherwise unused: the index is exact."""
+        if self.num_points > 0:
+            raise RuntimeError("DCI class does not support insertion of more than one array. "
+                               "Must combine all arrays into one array before inserting")
+        if num_levels >= 3:
+            _require_positive_int(field_of_view)
+        self._check_data(data)
+        contiguous, sel = self._select_rows(data, indices)
+        code = self._dtype_code(data)
+        if contiguous:
+            start, stop = sel
+            rows = data[start:stop] if stop > start else data[0:0]
+            self._orig_indices = None
+            self._offset = start
+        else:
+            rows = np.ascontiguousarray(data[sel])       # gathered copy, results remapped below (dci.py:265-268)
+            self._orig_indices = sel
+            self._offset = 0
+        if rows.shape[0] > 0:
+            _check(self._lib.b200knn_add(self._handle, rows.ctypes.data, code, rows.shape[0], self._dim))
+        self._array = data                               # keep the caller's array alive like dci.py:270
+        self._num_levels = int(num_levels) if rows.shape[0] > 0 else 0
+
+    def query(self, query, num_neighbours=-1, field_of_view=100, blind=False, num_to_visit=-1, num_to_retrieve=-1,
+              prop_to_visit=-1.0, prop_to_retrieve=-1.0):
+        """k nearest pool rows of every query row — dci.py:273-330.
+
+        Returns (indices, distances): two lists of length Q; element i holds an int32 / float64
+        ndarray of min(k, num_points) entries, ascending Euclidean distance (ties: lower index).
+        num_neighbours < 0 means all points (dci.py:278-279)."""
+        q = self._fix_query(query)
+        num_points = self.num_points
+        if num_neighbours < 0:
+            num_neighbours = num_points
+        _require_positive_int(num_neighbours)
+        if self.num_levels >= 2:
+            _require_positive_int(field_of_view)
+        nq = q.shape[0]
+        kk = min(num_neighbours, num_points)
+        idx = np.empty((nq, kk), dtype=np.int32)
+        dist = np.empty((nq, kk), dtype=np.float64)
+        out_kk = ctypes.c_int(0)
+        _check(self._lib.b200knn_query(self._handle, q.ctypes.data, self._dtype_code(q), nq, self._dim, int(num_neighbours),
+                                       0, idx.ctypes.data, dist.ctypes.data, ctypes.byref(out_kk)))
+        assert out_kk.value == kk
+        if self._orig_indices is not None:
+            idx = self._orig_indices[idx].astype(np.int32, copy=False)
+        elif self._offset:
+            idx += np.int32(self._offset)
+        return [idx[i] for i in range(nq)], [dist[i] for i in range(nq)]
+
+    def query_arrays(self, query, num_neighbours, squared=False, flags=0):
+        """Extension: same search, rectangular ndarray results (idx int32 [Q,kk], dist float64 [Q,kk])."""
+        q = self._fix_query(query)
+        _require_positive_int(num_neighbours)
+        nq = q.shape[0]
+        kk = min(num_neighbours, self.num_points)
+        idx = np.empty((nq, kk), dtype=np.int32)
+        dist = np.empty((nq, kk), dtype=np.float64)
+        _check(self._lib.b200knn_query(self._handle, q.ctypes.data, self._dtype_code(q), nq, self._dim, int(num_neighbours),
+                                       int(flags) | (FLAG_SQUARED if squared else 0), idx.ctypes.data, dist.ctypes.data, None))
+        if self._orig_indices is not None:
+            idx = self._orig_indices[idx].astype(np.int32, copy=False)
+        elif self._offset:
+            idx += np.int32(self._offset)
+        return idx, dist
+
+    def clear(self):
+        """Drop the pool (dci.py:332-335)."""
+        _check(self._lib.b200knn_clear(self._handle))
+        self._array = None
+        self._orig_indices = None
+        self._offset = 0
+        self._num_levels = 0
+
+    def reset(self):
+        """Drop the pool and redraw the (inert) projection directions (dci.py:337-340, dci.c:859-863)."""
+        self.clear()
+        self._proj_vec[...] = _draw_unit_directions(*self._proj_vec.shape)
+
+    _offset = 0
+
+
+class DeviceKNN(object):
+    """Device-pointer face of the C ABI (b200knn_add_device / query_device / merge_topk_device).
+
+    For hosts that already own device memory and streams (bench.py uses torch for that plumbing):
+    every buffer is passed as a raw device address (int), nothing is copied, and all work is issued on
+    the stream given to set_stream().  One handle = one GPU = one row shard of the pool; `index_base`
+    is the shard's first global row (multi-process sharding: one rank per GPU)."""
+
+    def __init__(self, dim, device=None):
+        self._lib = load_library()
+        self.dim = int(dim)
+        handle = ctypes.c_void_p()
+        if device is None:
+            _check(self._lib.b200knn_create(self.dim, 0, None, ctypes.byref(handle)))
+        else:
+            ids = (ctypes.c_int * 1)(int(device))
+            _check(self._lib.b200knn_create(self.dim, 1, ids, ctypes.byref(handle)))
+        self._handle = handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                self._lib.b200knn_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    @property
+    def num_points(self):
+        return int(self._lib.b200knn_num_points(self._handle))
+
+    def set_stream(self, stream_ptr):
+        _check(self._lib.b200knn_set_stream(self._handle, ctypes.c_void_p(stream_ptr or 0)))
+
+    def set_profiling(self, on):
+        _check(self._lib.b200knn_set_profiling(self._handle, int(bool(on))))
+
+    def add(self, data_ptr, dtype, n, ld=None, index_base=0):
+        _check(self._lib.b200knn_add_device(self._handle, ctypes.c_void_p(data_ptr), int(dtype), int(n),
+                                            int(ld if ld is not None else self.dim), int(index_base)))
+
+    def query(self, query_ptr, dtype, nq, k, out_idx_ptr, out_dist_ptr, ld=None, flags=0):
+        kk = ctypes.c_int(0)
+        _check(self._lib.b200knn_query_device(self._handle, ctypes.c_void_p(query_ptr), int(dtype), int(nq),
+                                              int(ld if ld is not None else self.dim), int(k), int(flags),
+                                              ctypes.c_void_p(out_idx_ptr), ctypes.c_void_p(out_dist_ptr), ctypes.byref(kk)))
+        return kk.value
+
+    def merge(self, idx_ptr, dist_ptr, n_lists, nq, kk, out_idx_ptr, out_dist_ptr, stream_ptr=0):
+        _check(self._lib.b200knn_merge_topk_device(ctypes.c_void_p(idx_ptr), ctypes.c_void_p(dist_ptr), int(n_lists), int(nq),
+                                                   int(kk), ctypes.c_void_p(out_idx_ptr), ctypes.c_void_p(out_dist_ptr),
+                                                   ctypes.c_void_p(stream_ptr or 0)))
+
+    def clear(self):
+        _check(self._lib.b200knn_clear(self._handle))
+
+    def stats(self):
+        s = Stats()
+        _check(self._lib.b200knn_get_stats(self._handle, ctypes.byref(s)))
+        return s.as_dict()
+
+    def reset_stats(self):
+        _check(self._lib.b200knn_reset_stats(self._handle))
