@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py — IMLE kNN matching throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|c1|small] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One step = one pass of the hot path over one batch: all Q queries of the workload matched against the
+resident generated pool (exact kNN).  Prints ONE JSON line (rank 0).
+
+  value     queries/s with the pool index built and the query matrix already resident in HBM
+            (C-ABI device entry points, CUDA-event timed on the launching stream, max over ranks).
+  e2e       the same metric through the host-buffer C-ABI call the DCI Python class makes
+            (b200knn_query): pinned HOST float64 queries in, HOST results out, H2D/D2H inside the timed region.
+  roofline  the tcgen05 distance kernel: 2*Q*N*d FLOPs per launch / its CUDA-event time, vs MEASURED_PEAKS.json.
+  cpu_baseline  the UNMODIFIED reference DCI (oracle/_ref/_dci.so) on this box's host cores, bounded sample.
+
+torch is used for device memory, streams, events and torch.distributed only; no torch op is on the path.
+Multi-GPU: pool row-sharded over ranks, queries replicated, local exact top-k per rank, NCCL all-gather of
+(index, distance) lists, k-way merge kernel on every rank.  Total work is fixed as N grows -> "strong".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N pool, Q queries, dim, k, description)   — BASELINE.json configs
+    "c3": (300000, 30000, 3072, 1, "CelebA-128 IMLE match: 30k queries vs 300k pool, d=3072, k=1 (BASELINE.json configs[2]; north_star target shape)"),
+    "c2": (240000, 24000, 3072, 1, "Stacked MNIST IMLE match: 24k queries vs 240k pool, d=3072, k=1 (configs[1])"),
+    "c4": (50000, 50000, 2048, 4, "precision/recall self-kNN: 50k vs 50k, d=2048, k=3(+self) (configs[3])"),
+    "c1": (10000, 100, 5000, 10, "dci_code/example.py shape: 10k pool, 100 queries, d=5000, k=10 (configs[0])"),
+    "small": (20000, 2048, 512, 1, "smoke-sized"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return {"bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+            self.fh.close()
+            sm, mx, reasons, power = [], [], set(), []
+            with open(self.path) as fh:
+                for line in fh:
+                    f = [t.strip() for t in line.split(",")]
+                    if len(f) < 9:
+                        continue
+                    try:
+                        sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                    except ValueError:
+                        continue
+                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                        if val.lower().startswith("active"):
+                            reasons.add(name)
+            os.unlink(self.path)
+            if sm:
+                # median over samples under load (power above idle)
+                load = [s for s, p in zip(sm, power) if p > 300.0] or sm
+                out = {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                       "power_w_max": max(power)}
+        except Exception:
+            pass
+        return out
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the unmodified reference DCI on host cores, bounded sample of the workload
+# ---------------------------------------------------------------------------------------------------------
+def reference_sample(workload, steps, warmup, budget_s=25.0):
+    """Times oracle/_ref (reference DCI, training hyper-parameters training_loop.py:197,368,398).
+
+    Sample: the workload's dim and k, a pool subsample sized for the box's core count and a query
+    subsample per step (per-query cost does not depend on Q: dci.c:801 parallelises over queries)."""
+    from oracle import ref_dci
+    n, q, d, k, _ = WORKLOADS[workload]
+    cores = host_cores()
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    if not ref_dci.available():
+        return None
+    ns = int(min(n, 60000))
+    qs = int(min(q, max(64, 16 * cores)))
+    rng = np.random.default_rng(0)
+    pool = rng.standard_normal((ns, d))
+    queries = np.random.default_rng(1).standard_normal((qs, d))
+    if workload == "c1":
+        m, L, levels, cfov, cpr, qfov, qpr = 2, 7, 2, 10, 0.002, 100, 0.05      # dci_code/example.py:44-66
+    else:
+        m, L, levels, cfov, cpr, qfov, qpr = 3, 15, 3, 10, 0.002, 200, 1.0       # training/training_loop.py:197,368,398
+    db = ref_dci.RefDCI(d, m, L)
+    t0 = time.perf_counter()
+    db.add(pool, num_levels=levels, field_of_view=cfov, prop_to_retrieve=cpr)
+    t_add = time.perf_counter() - t0
+    times = []
+    t_begin = time.perf_counter()
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        db.query(queries, k, field_of_view=qfov, prop_to_retrieve=qpr)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_begin > 4 * budget_s and len(times) >= 1:
+            break
+    db.clear()
+    total = float(np.sum(times))
+    return {"qps": qs * len(times) / total, "ms_per_step": 1e3 * total / len(times), "steps_done": len(times), "cores": cores,
+            "add_s": t_add,
+            "sample": "reference DCI (oracle/_ref, unmodified dci.c) m=%d L=%d levels=%d; pool subsample %d x %d float64 N(0,1) of the "
+                      "%d-row workload, %d queries/step, k=%d, OMP threads=%d; add() took %.1f s (not in value)" % (
+                          m, L, levels, ns, d, n, qs, k, cores, t_add)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    r = reference_sample(args.workload, args.steps, max(args.warmup, 1))
+    n, q, d, k, desc = WORKLOADS[args.workload]
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/_dci.so missing (build with `make -C oracle ref` where /root/reference exists)"}))
+        return 0
+    line = {"impl": "reference", "metric": "imle_knn_queries_per_sec", "value": r["qps"], "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": r["steps_done"], "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %s" % (args.workload, desc), "pool": n, "queries": q, "dim": d, "k": k},
+            "cpu_baseline": {"value": r["qps"], "unit": "queries/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"]},
+            "e2e": {"value": r["qps"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from inclusivegan_b200.dci import DeviceKNN, F64, load_library
+    import ctypes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, q, d, k, desc = WORKLOADS[args.workload]
+    # ---- synthetic features (float64, the dtype of the reference's interface), identical on every rank ----
+    per = (n + world - 1) // world
+    r0, r1 = min(n, per * rank), min(n, per * (rank + 1))
+    # the pool is generated in 8 fixed row blocks, each seeded by its block id, so 1/2/4/8-GPU runs see the same rows
+    pool = torch.empty(r1 - r0, d, device=dev, dtype=torch.float64)
+    blk = (n + 7) // 8
+    for b in range(8):
+        b0, b1 = max(r0, b * blk), min(r1, (b + 1) * blk, n)
+        if b1 <= b0:
+            continue
+        g = torch.Generator(device=dev)
+        g.manual_seed(1000 + b)
+        full = torch.randn(min((b + 1) * blk, n) - b * blk, d, device=dev, dtype=torch.float64, generator=g)
+        pool[b0 - r0:b1 - r0] = full[b0 - b * blk:b1 - b * blk]
+        del full
+    gq = torch.Generator(device=dev)
+    gq.manual_seed(1)
+    queries = torch.randn(q, d, device=dev, dtype=torch.float64, generator=gq)
+
+    stream = torch.cuda.current_stream()
+    ix = DeviceKNN(d, local_rank)
+    ix.set_stream(stream.cuda_stream)
+    ix.add(pool.data_ptr(), F64, r1 - r0, index_base=r0)
+    torch.cuda.synchronize()
+    kk = min(k, n)
+    loc_i = torch.empty(q, kk, device=dev, dtype=torch.int32)
+    loc_d = torch.empty(q, kk, device=dev, dtype=torch.float64)
+    out_i = torch.empty(q, kk, device=dev, dtype=torch.int32)
+    out_d = torch.empty(q, kk, device=dev, dtype=torch.float64)
+    if world > 1:
+        all_i = torch.empty(world, q, kk, device=dev, dtype=torch.int32)
+        all_d = torch.empty(world, q, kk, device=dev, dtype=torch.float64)
+
+    def step_device():
+        ix.query(queries.data_ptr(), F64, q, k, loc_i.data_ptr(), loc_d.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(all_i.view(world * q, kk), loc_i)
+            dist.all_gather_into_tensor(all_d.view(world * q, kk), loc_d)
+            ix.merge(all_i.data_ptr(), all_d.data_ptr(), world, q, kk, out_i.data_ptr(), out_d.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident arm ------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    ix.reset_stats()
+    ix.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    st = ix.stats()
+    ix.set_profiling(False)
+    launches = st["kernel_launches"] + (args.steps if world > 1 else 0)
+
+    # ---- end-to-end arm: host-buffer C-ABI call (what DCI.query makes), pinned host queries ----------
+    lib = load_library()
+    hq = torch.empty(q, d, dtype=torch.float64).pin_memory()
+    hq.copy_(queries)
+    torch.cuda.synchronize()
+    hx = ctypes.c_void_p()
+    ids = (ctypes.c_int * 1)(local_rank)
+    assert lib.b200knn_create(d, 1, ids, ctypes.byref(hx)) == 0
+    assert lib.b200knn_set_stream(hx, ctypes.c_void_p(stream.cuda_stream)) == 0
+    assert lib.b200knn_add_device(hx, ctypes.c_void_p(pool.data_ptr()), F64, r1 - r0, d, r0) == 0, lib.b200knn_last_error()
+    h_i = torch.empty(q, kk, dtype=torch.int32).pin_memory()
+    h_d = torch.empty(q, kk, dtype=torch.float64).pin_memory()
+    res_i = torch.empty(q, kk, dtype=torch.int32).pin_memory()
+    res_d = torch.empty(q, kk, dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        rc = lib.b200knn_query(hx, ctypes.c_void_p(hq.data_ptr()), F64, q, d, k, 0, ctypes.c_void_p(h_i.data_ptr()),
+                               ctypes.c_void_p(h_d.data_ptr()), None)
+        if rc != 0:
+            raise RuntimeError(lib.b200knn_last_error().decode())
+        if world > 1:     # shard results back to the device for the NVLink exchange, merged result back to the host
+            loc_i.copy_(h_i, non_blocking=True)
+            loc_d.copy_(h_d, non_blocking=True)
+            dist.all_gather_into_tensor(all_i.view(world * q, kk), loc_i)
+            dist.all_gather_into_tensor(all_d.view(world * q, kk), loc_d)
+            ix.merge(all_i.data_ptr(), all_d.data_ptr(), world, q, kk, out_i.data_ptr(), out_d.data_ptr(), stream.cuda_stream)
+            res_i.copy_(out_i, non_blocking=True)
+            res_d.copy_(out_d, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    e2e_ms = timed(step_e2e, e2e_steps)
+    lib.b200knn_destroy(hx)
+
+    # ---- self-check of the last device result against a float64 torch brute force on a query subsample ----
+    check = None
+    if rank == 0 and world == 1:
+        nchk = min(q, 64)
+        sub = queries[:nchk]
+        d2 = (sub * sub).sum(1, keepdim=True) + (pool * pool).sum(1)[None, :] - 2.0 * sub @ pool.T
+        ref = torch.topk(d2, kk, dim=1, largest=False).indices.to(torch.int32)
+        check = bool((ref == loc_i[:nchk]).all().item())
+
+    if rank == 0:
+        peaks = load_peaks()
+        ms_step = total_ms / args.steps
+        dist_ms = st["ms_distance"] / max(st["distance_launches"], 1)
+        ach = st["distance_flops"] / max(st["ms_distance"], 1e-9) / 1e9     # TFLOP/s per GPU (this rank)
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "dist_kernel_ncu.json")
+        if os.path.exists(prof):
+            try:
+                with open(prof) as fh:
+                    traffic = json.load(fh).get(args.workload, {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "imle_knn_queries_per_sec", "value": q / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16 (tensor pass) + f64 (exact re-rank)", "data": "synthetic",
+            "config": {"workload": "%s: %s" % (args.workload, desc), "pool": n, "queries": q, "dim": d, "k": k,
+                       "features": "float64 N(0,1), seeded", "parallelism": "pool row-sharded x%d, queries replicated, NCCL all-gather + merge" % world
+                       if world > 1 else "single GPU", "l2": "inputs exceed L2 (BF16 pool shard %.2f GB > 126 MB); no explicit flush" % ((r1 - r0) * d * 2 / 1e9),
+                       "timing": "CUDA events on the launching stream, max over ranks"},
+            "tensor_peak_frac": 2.0 * q * n * d / (ms_step * 1e-3) / 1e12 / (peaks["bf16_tflops"] * world),
+            "roofline": {"bound": "tensor", "kernel": "dist_topc_kernel (tcgen05 BF16 distance GEMM + fused top-C)",
+                         "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+                         "frac_of_sustained_peak": (ach / peaks["bf16_tflops_sustained"]) if peaks.get("bf16_tflops_sustained") else None,
+                         "peak_source": peaks["source"] + ", burst figure", "ms_per_launch": dist_ms, "launches": st["distance_launches"],
+                         "flops_per_launch": st["distance_flops"] / max(st["distance_launches"], 1), "traffic": traffic},
+            "kernel_ms_per_step": {"convert": st["ms_convert"] / args.steps, "distance": st["ms_distance"] / args.steps,
+                                   "rerank": st["ms_rerank"] / args.steps, "second_pass": st["ms_scan"] / args.steps},
+            "uncertified_per_step": st["uncertified"] / args.steps,
+            "e2e": {"value": q / (e2e_ms / e2e_steps * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                    "h2d_bytes_per_step": q * d * 8, "d2h_bytes_per_step": q * kk * 12,
+                    "api": "b200knn_query (host buffers; the call inclusivegan_b200.dci.DCI.query makes)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "self_check_top%d_vs_torch_f64" % kk: check,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                r = reference_sample(args.workload, steps=2, warmup=1)
+                if r is not None:
+                    line["cpu_baseline"] = {"value": r["qps"], "unit": "queries/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"]}
+                else:
+                    line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": host_cores(), "kind": "reference",
+                                            "sample": "unavailable: oracle/_ref/_dci.so missing"}
+            except Exception as e:   # the baseline must never take the GPU number down with it
+                line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": host_cores(), "kind": "reference", "sample": "failed: %r" % (e,)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -74,42 +74,70 @@ def pair_dist(data, query, qrow, xrow):
     return out
 
 
-def exact_knn_numpy(data, query, k, squared=False, qblock=256, slack=8):
-    """Blocked float64 brute force.  `data`/`query` may be float32 or float64 (upcast per block)."""
+def exact_knn_numpy(data, query, k, squared=False, qblock=256, xblock=65536, slack=8):
+    """Blocked float64 brute force.  `data`/`query` may be float32 or float64 (upcast block by block, so a
+    full-size float32 pool never has to exist in float64).  Selection by the GEMM form keeps a shortlist of
+    kk+slack per query over pool blocks; the shortlist is then re-evaluated with the direct float64
+    sum of squared differences, and a completeness guard falls back to a full direct evaluation."""
     n, d = data.shape
     nq = query.shape[0]
     kk = min(int(k), n)
-    c = min(n, kk + slack)                       # shortlist size; re-evaluated exactly below
-    x64 = np.asarray(data, dtype=np.float64)
-    xn = np.einsum("ij,ij->i", x64, x64)
+    c = min(n, kk + slack)
     idx = np.empty((nq, kk), dtype=np.int32)
     dist = np.empty((nq, kk), dtype=np.float64)
+    xn_max = 0.0
     for s in range(0, nq, qblock):
         q = np.asarray(query[s:s + qblock], dtype=np.float64)
-        approx = xn[None, :] - 2.0 * (q @ x64.T)            # + ||q||^2 is constant per row
-        if c < n:
-            cand = np.argpartition(approx, c - 1, axis=1)[:, :c]
-        else:
-            cand = np.broadcast_to(np.arange(n), (q.shape[0], n)).copy()
-        diff = x64[cand] - q[:, None, :]                     # [b, c, d]
-        d2 = np.einsum("bcd,bcd->bc", diff, diff)
-        # guard: the shortlist must strictly contain the answer — its worst exact distance must
-        # clear the kk-th by more than the cancellation error of the GEMM form
-        order = np.lexsort((cand, d2), axis=1)
-        cand_s = np.take_along_axis(cand, order, axis=1)
+        b = q.shape[0]
+        qn = np.einsum("ij,ij->i", q, q)
+        best_v = np.full((b, c), np.inf)
+        best_i = np.zeros((b, c), dtype=np.int64)
+        for x0 in range(0, n, xblock):
+            x = np.asarray(data[x0:x0 + xblock], dtype=np.float64)
+            xn = np.einsum("ij,ij->i", x, x)
+            xn_max = max(xn_max, float(xn.max()))
+            approx = xn[None, :] - 2.0 * (q @ x.T)              # + ||q||^2 is constant per row
+            m = min(c, x.shape[0])
+            part = np.argpartition(approx, m - 1, axis=1)[:, :m] if m < x.shape[0] else np.broadcast_to(np.arange(x.shape[0]), (b, x.shape[0]))
+            cand_v = np.concatenate([best_v, np.take_along_axis(approx, part, axis=1)], axis=1)
+            cand_i = np.concatenate([best_i, part + x0], axis=1)
+            keep = np.argpartition(cand_v, c - 1, axis=1)[:, :c]
+            best_v = np.take_along_axis(cand_v, keep, axis=1)
+            best_i = np.take_along_axis(cand_i, keep, axis=1)
+        # exact re-evaluation of the shortlist
+        d2 = np.empty((b, c))
+        for j in range(c):
+            diff = np.asarray(data[best_i[:, j]], dtype=np.float64) - q
+            d2[:, j] = np.einsum("ij,ij->i", diff, diff)
+        order = np.lexsort((best_i, d2), axis=1)
+        cand_s = np.take_along_axis(best_i, order, axis=1)
         d2_s = np.take_along_axis(d2, order, axis=1)
         if c < n:
-            qn = np.einsum("ij,ij->i", q, q)
-            boundary = np.take_along_axis(approx, cand, axis=1).max(axis=1) + qn   # <= every excluded point
-            eps = 1e-9 * (qn + xn.max())
-            for b in np.nonzero(d2_s[:, kk - 1] > boundary - eps)[0]:             # not provably complete
-                full = x64 - q[b]
-                fd2 = np.einsum("ij,ij->i", full, full)
+            boundary = best_v.max(axis=1) + qn                  # <= the GEMM-form value of every excluded point
+            eps = 1e-9 * (qn + xn_max)
+            for r in np.nonzero(d2_s[:, kk - 1] > boundary - eps)[0]:      # not provably complete: direct scan
+                fd2 = np.empty(n)
+                for x0 in range(0, n, xblock):
+                    diff = np.asarray(data[x0:x0 + xblock], dtype=np.float64) - q[r]
+                    fd2[x0:x0 + xblock] = np.einsum("ij,ij->i", diff, diff)
                 o = np.lexsort((np.arange(n), fd2))[:c]
-                cand_s[b], d2_s[b] = o, fd2[o]
+                cand_s[r], d2_s[r] = o, fd2[o]
         idx[s:s + qblock] = cand_s[:, :kk]
         dist[s:s + qblock] = d2_s[:, :kk] if squared else np.sqrt(d2_s[:, :kk])
     return idx, dist
+
+
+def merge_topk_numpy(all_idx, all_dist):
+    """CPU restatement of the k-way merge of per-shard results (contract of b200knn_merge_topk_device):
+    inputs [G, Q, kk] ascending per shard -> [Q, kk] ascending by (distance, index); index -1 = empty slot."""
+    all_idx = np.asarray(all_idx)
+    all_dist = np.asarray(all_dist, dtype=np.float64)
+    g, nq, kk = all_idx.shape
+    ci = np.transpose(all_idx, (1, 0, 2)).reshape(nq, g * kk)
+    cd = np.transpose(all_dist, (1, 0, 2)).reshape(nq, g * kk).copy()
+    cd[ci < 0] = np.inf
+    order = np.lexsort((ci, cd), axis=1)[:, :kk]
+    return np.take_along_axis(ci, order, axis=1).astype(np.int32), np.take_along_axis(cd, order, axis=1)
 
 
 def compare_knn(idx, dist, ref_idx, ref_dist, data=None, query=None, tie_rtol=1e-6, dist_rtol=1e-5):
