@@ -125,14 +125,15 @@ int b200knn_merge_topk_device(const int32_t *d_idx, const double *d_dist, int n_
 typedef struct b200knn_stats {
     int64_t kernel_launches;       /* kernels of this library launched by this handle since creation */
     int64_t queries;               /* query rows answered */
-    int64_t uncertified;           /* query rows whose tensor-core shortlist could not be certified exact
-                                      and were re-answered by the exact scan */
+    int64_t uncertified;           /* query rows whose tensor-core shortlist could not be certified exact and
+                                      were re-answered by the second (threshold-collection) tensor pass */
     double  ms_convert;            /* accumulated device time per kernel family, profiling mode only */
     double  ms_distance;
     double  ms_rerank;
-    double  ms_scan;
+    double  ms_scan;               /* second pass (gather + collection GEMM + list re-rank) and exact scan */
     int64_t distance_launches;     /* launches of the tcgen05 distance kernel counted in ms_distance */
     double  distance_flops;        /* 2*nq*n*dim summed over those launches */
+    int64_t exact_scanned;         /* query rows whose second-pass list overflowed: answered by the exact CUDA-core scan */
 } b200knn_stats;
 
 /* profiling != 0: bracket every kernel with CUDA events on the launching stream; read with get_stats. */

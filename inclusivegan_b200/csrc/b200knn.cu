@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -117,13 +118,25 @@ struct Shard {
     int x_dtype = B200KNN_F64;
     int64_t n = 0, ld_x = 0, index_base = 0;
     DevBuf<__nv_bfloat16> x_bf;
-    DevBuf<float> xnorm_bf, xnorm_ex;
-    DevBuf<unsigned int> scalars;    // [0] max ||x~||^2 bits, [1] max ||x||^2 bits, [2] query max bf, [3] query max ex, [4] uncert count
-    CUtensorMap tmap_x;
+    DevBuf<float> xnorm_bf, x_err;
+    DevBuf<unsigned int> scalars;    // [0] max ||x~||^2 bits, [1] max ||x - x~|| bits, [2],[3] same for queries (unused), [4] uncertified count, [5] overflow count
+    CUtensorMap tmap_x;              // pool, 256-row box (1-CTA kernel)
+    CUtensorMap tmap_x128;           // pool, 128-row box (each CTA of a pair stages half of the 256-row tile)
+    int forced_cg = 0;               // $B200KNN_CTA_GROUP=1|2 pins the kernel flavour (A/B measurements)
+    unsigned opt_flags = 4;          // $B200KNN_OPT: kernel tuning switches (see DistParams::opt)
+    int a_budget_mb = 64;            // $B200KNN_A_BUDGET_MB: L2 budget for the query tiles of one round
+    int sync_tiles = 16;             // $B200KNN_SYNC_TILES: lockstep interval of the workers sharing a pool-tile stream
+    int max_pairs = 74;              // CTA pairs that can be co-resident (cudaOccupancyMaxActiveClusters)
 
     // ---- query workspace ----
     DevBuf<__nv_bfloat16> q_bf;
-    DevBuf<float> qnorm_bf, qnorm_ex;
+    DevBuf<float> qnorm_bf, q_err;
+    DevBuf<__nv_bfloat16> q_bf2;     // second pass: BF16 rows of the uncertified queries
+    DevBuf<float> uncert_thr;
+    DevBuf<int> coll_count, coll_idx, overflow_list;
+    DevBuf<WorkItem> sched_items;
+    DevBuf<unsigned int> stream_sync;
+    DevBuf<int> sched_slots;
     DevBuf<float> cand_s;
     DevBuf<int> cand_i;
     DevBuf<int> uncert_list;
@@ -131,6 +144,9 @@ struct Shard {
     DevBuf<int> scan_iota, scan_vals_sorted, scan_offsets;
     DevBuf<unsigned char> cub_tmp;
     DevBuf<unsigned char> q_stage;   // host API: device copy of the caller's query rows
+    DevBuf<unsigned char> q_stage2;  // second buffer: the upload of chunk i+1 overlaps the compute of chunk i
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     DevBuf<int32_t> out_idx;
     DevBuf<double> out_dist;
     int *h_count = nullptr;          // pinned
@@ -152,6 +168,11 @@ struct Shard {
         num_sms = prop.multiProcessorCount;
         CU_TRY(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
         stream = own_stream;
+        CU_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU_TRY(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&ev_consumed[i], cudaEventDisableTiming));
+        }
         TRY(scalars.ensure(8));
         CU_TRY(cudaMemsetAsync(scalars.p, 0, 8 * sizeof(unsigned int), stream));
         CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&h_count), sizeof(int)));
@@ -160,8 +181,37 @@ struct Shard {
         return B200KNN_OK;
     }
     int set_kernel_attrs() {
-        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIST_SMEM_BYTES));
-        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIST_SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<16, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<1>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<32, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<1>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<16, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<1>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<16, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<32, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<16, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
+        if (const char *o = getenv("B200KNN_OPT")) opt_flags = static_cast<unsigned>(atoi(o));
+        if (const char *o = getenv("B200KNN_A_BUDGET_MB")) a_budget_mb = std::max(1, atoi(o));
+        if (const char *o = getenv("B200KNN_SYNC_TILES")) sync_tiles = std::max(0, atoi(o));
+        const char *e = getenv("B200KNN_CTA_GROUP");
+        if (e && (e[0] == '1' || e[0] == '2')) forced_cg = e[0] - '0';
+        // a persistent, statically-strided grid must be fully co-resident: ask how many CTA pairs fit at once
+        {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(num_sms / 2 * 2);
+            cfg.blockDim = dim3(DIST_THREADS);
+            cfg.dynamicSmemBytes = DistCfg<2>::SMEM_BYTES;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, dist_topc_kernel<16, false, 2>, &cfg) == cudaSuccess && nc > 0) max_pairs = std::min(nc, num_sms / 2);
+            else { cudaGetLastError(); max_pairs = num_sms / 2; }
+            const char *g = getenv("B200KNN_MAX_PAIRS");
+            if (g && atoi(g) > 0) max_pairs = atoi(g);
+            if (getenv("B200KNN_VERBOSE")) fprintf(stderr, "[b200knn] device %d: %d SMs, %d co-resident CTA pairs (occupancy query %d)\n", device, num_sms, max_pairs, nc);
+        }
         return B200KNN_OK;
     }
     void prof_begin(int kind, double flops = 0.0) {
@@ -205,17 +255,22 @@ struct Shard {
         n = 0;
         x_bf.release();
         xnorm_bf.release();
-        xnorm_ex.release();
+        x_err.release();
     }
     void destroy() {
         if (!ready) return;
         clear_pool();
         drain_events();
-        q_bf.release(); qnorm_bf.release(); qnorm_ex.release(); cand_s.release(); cand_i.release(); uncert_list.release();
+        q_bf.release(); qnorm_bf.release(); q_err.release(); q_bf2.release(); uncert_thr.release(); coll_count.release(); coll_idx.release(); overflow_list.release(); sched_items.release(); sched_slots.release(); stream_sync.release(); cand_s.release(); cand_i.release(); uncert_list.release();
         scan_d2.release(); scan_d2_sorted.release(); scan_iota.release(); scan_vals_sorted.release(); scan_offsets.release();
-        cub_tmp.release(); q_stage.release(); out_idx.release(); out_dist.release(); scalars.release();
+        cub_tmp.release(); q_stage.release(); q_stage2.release(); out_idx.release(); out_dist.release(); scalars.release();
         if (h_count) cudaFreeHost(h_count);
         if (own_stream) cudaStreamDestroy(own_stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        for (int i = 0; i < 2; i++) {
+            if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
+            if (ev_consumed[i]) cudaEventDestroy(ev_consumed[i]);
+        }
         ready = false;
     }
 
@@ -250,33 +305,100 @@ struct Shard {
         index_base = base;
         TRY(x_bf.ensure(static_cast<size_t>(rows) * kp));
         TRY(xnorm_bf.ensure(rows));
-        TRY(xnorm_ex.ensure(rows));
+        TRY(x_err.ensure(rows));
         CU_TRY(cudaMemsetAsync(scalars.p, 0, 2 * sizeof(unsigned int), stream));
         TRY(make_tmap(&tmap_x, x_bf.p, rows, kp, BN));
+        TRY(make_tmap(&tmap_x128, x_bf.p, rows, kp, BN / 2));
         return B200KNN_OK;
     }
 
     // ------------------------------------------------------------------ schedule
-    struct Sched { int qt, nt, chunks, tiles_per_chunk, qgroup, grid; };
-    Sched plan(int64_t nq, int kp) const {
-        Sched s;
-        s.qt = static_cast<int>((nq + BM - 1) / BM);
+    // ------------------------------------------------------------------ schedule
+    // One round per group of query tiles: the group's `gs` tiles x `rc` chunks of the pool are processed side by side
+    // (gs * rc <= workers), every worker sweeping NT/rc pool tiles (+-1).  The group's BF16 query rows (gs tiles) stay
+    // in L2 for the whole round while `rc` pool-tile streams pass through once, each shared by `gs` workers that run
+    // in lockstep: HBM traffic per round is ~ one pass over the pool instead of one per worker.
+    struct Sched {
+        int cg, qt, nt, workers, nrounds, max_slots, grid;
+        std::vector<WorkItem> items;        // [nrounds][workers]
+        std::vector<int> slots_per_qtile;   // [qt]
+    };
+    int plan(Sched &s, int64_t nq, int kp, int max_slots_allowed) const {
+        s.cg = forced_cg ? forced_cg : (nq > BM ? 2 : 1);
+        s.workers = std::max(1, s.cg == 2 ? max_pairs : num_sms);
+        const int W = s.workers;
+        const int qrows = BM * s.cg;
+        s.qt = static_cast<int>((nq + qrows - 1) / qrows);
         s.nt = static_cast<int>((n + BN - 1) / BN);
-        int64_t best_cost = -1;
-        s.chunks = 1;
-        s.tiles_per_chunk = s.nt;
-        for (int c = 1; c <= std::min(s.nt, MAX_CHUNKS); c++) {
-            const int t = (s.nt + c - 1) / c;
-            const int c2 = (s.nt + t - 1) / t;
-            const int64_t items = static_cast<int64_t>(s.qt) * c2;
-            const int64_t waves = (items + num_sms - 1) / num_sms;
-            const int64_t cost = waves * t * 64 + c2;   // sweep length dominates; fewer shortlists break ties
-            if (best_cost < 0 || cost < best_cost) { best_cost = cost; s.chunks = c2; s.tiles_per_chunk = t; }
+        // group size: as many query tiles as the L2 budget for the A operand allows, preferring sizes that tile the
+        // worker count exactly
+        const int64_t a_tile_bytes = static_cast<int64_t>(qrows) * kp * 2;
+        const int g_cap = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(W, (static_cast<int64_t>(a_budget_mb) << 20) / std::max<int64_t>(a_tile_bytes, 1))));
+        int qg = 1;
+        double best_util = -1.0;
+        for (int g = 1; g <= std::min(g_cap, s.qt); g++) {
+            const int rc = std::min(std::min(W / g, s.nt), max_slots_allowed);
+            const double util = static_cast<double>(g) * rc / W;
+            if (util >= best_util - 1e-12) { best_util = util; qg = g; }   // ties -> larger group (fewer rounds)
         }
-        const int64_t a_tile_bytes = static_cast<int64_t>(BM) * kp * 2;
-        s.qgroup = static_cast<int>(std::max<int64_t>(4, std::min<int64_t>(64, (32ll << 20) / std::max<int64_t>(a_tile_bytes, 1))));
-        s.grid = static_cast<int>(std::min<int64_t>(num_sms, static_cast<int64_t>(s.qt) * s.chunks));
-        return s;
+        s.items.clear();
+        s.slots_per_qtile.assign(s.qt, 0);
+        s.nrounds = 0;
+        s.max_slots = 1;
+        for (int q0 = 0; q0 < s.qt; q0 += qg) {
+            const int gs = std::min(qg, s.qt - q0);
+            const int rc = std::max(1, std::min(std::min(W / gs, s.nt), max_slots_allowed));
+            s.max_slots = std::max(s.max_slots, rc);
+            s.items.resize(static_cast<size_t>(s.nrounds + 1) * W, WorkItem{-1, 0, 0, 0});
+            WorkItem *row = s.items.data() + static_cast<size_t>(s.nrounds) * W;
+            // chunk-major: workers sharing a pool-tile stream are neighbours
+            for (int c = 0; c < rc; c++) {
+                const int t0 = static_cast<int>(static_cast<int64_t>(c) * s.nt / rc);
+                const int t1 = static_cast<int>(static_cast<int64_t>(c + 1) * s.nt / rc);
+                for (int g = 0; g < gs; g++) row[c * gs + g] = WorkItem{q0 + g, t0, t1, c | (gs << 16)};
+            }
+            for (int g = 0; g < gs; g++) s.slots_per_qtile[q0 + g] = rc;
+            s.nrounds++;
+        }
+        s.grid = s.cg * W;
+        return B200KNN_OK;
+    }
+    // upload the schedule (small: a few KB) and reset the round barrier
+    int upload_schedule(const Sched &s, bool with_slots) {
+        TRY(sched_items.ensure(s.items.size()));
+        CU_TRY(cudaMemcpyAsync(sched_items.p, s.items.data(), s.items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, stream));
+        if (with_slots) {
+            TRY(sched_slots.ensure(s.slots_per_qtile.size()));
+            CU_TRY(cudaMemcpyAsync(sched_slots.p, s.slots_per_qtile.data(), s.slots_per_qtile.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        }
+        // (copies from pageable host memory are staged before cudaMemcpyAsync returns: no synchronisation needed)
+        CU_TRY(cudaMemsetAsync(scalars.p + 6, 0, sizeof(unsigned int), stream));
+        TRY(stream_sync.ensure(static_cast<size_t>(s.nrounds) * s.max_slots));
+        CU_TRY(cudaMemsetAsync(stream_sync.p, 0, static_cast<size_t>(s.nrounds) * s.max_slots * sizeof(unsigned int), stream));
+        return B200KNN_OK;
+    }
+
+    template <int C, bool COLLECT>
+    int launch_dist(const Sched &s, const CUtensorMap &tmap_q, const DistParams &dp) {
+        if (s.cg == 2) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(s.grid);
+            cfg.blockDim = dim3(DIST_THREADS);
+            cfg.dynamicSmemBytes = DistCfg<2>::SMEM_BYTES;
+            cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            CU_TRY(cudaLaunchKernelEx(&cfg, dist_topc_kernel<C, COLLECT, 2>, tmap_q, tmap_x128, dp));
+        } else {
+            dist_topc_kernel<C, COLLECT, 1><<<s.grid, DIST_THREADS, DistCfg<1>::SMEM_BYTES, stream>>>(tmap_q, tmap_x, dp);
+        }
+        CU_TRY(cudaGetLastError());
+        return B200KNN_OK;
     }
 
     // ------------------------------------------------------------------ exact scan of a query subset
@@ -366,40 +488,118 @@ struct Shard {
         return B200KNN_OK;
     }
 
+    DistParams base_dist_params(int64_t nq, int kp, const Sched &s) const {
+        DistParams dp{};
+        dp.xnorm = xnorm_bf.p;
+        dp.n = static_cast<int>(n);
+        dp.nq = static_cast<int>(nq);
+        dp.num_kb = (kp + BK - 1) / BK;
+        dp.items = sched_items.p;
+        dp.nrounds = s.nrounds;
+        dp.workers = s.workers;
+        dp.round_counter = scalars.p + 6;
+        dp.stream_sync = stream_sync.p;
+        dp.sync_tiles = sync_tiles;
+        dp.max_slots = s.max_slots;
+        dp.opt = opt_flags;
+        return dp;
+    }
+
+    // Second pass for the `nun` queries the certificate rejected: the same tcgen05 GEMM, but the epilogue collects
+    // every pool row whose score is within the query's error margin; those short lists are re-ranked exactly.
+    // Lists that overflow go to the exact CUDA-core scan.
+    int second_pass(const void *d_query, int q_dtype, int64_t ld_q, int nun, int dim, int kp, int kk, unsigned flags,
+                    int32_t *d_out_idx, double *d_out_dist) {
+        TRY(q_bf2.ensure(static_cast<size_t>(nun) * kp));
+        TRY(coll_count.ensure(nun));
+        TRY(coll_idx.ensure(static_cast<size_t>(nun) * COLLECT_CAP));
+        TRY(overflow_list.ensure(nun));
+        prof_begin(K_SCAN);
+        gather_rows_kernel<<<std::min<int64_t>(num_sms * 4, (static_cast<int64_t>(nun) * (kp / 8) + 255) / 256), 256, 0, stream>>>(
+            q_bf.p, uncert_list.p, nun, kp, q_bf2.p);
+        prof_end();
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemsetAsync(coll_count.p, 0, static_cast<size_t>(nun) * sizeof(int), stream));
+        CU_TRY(cudaMemsetAsync(scalars.p + 5, 0, sizeof(unsigned int), stream));
+        CUtensorMap tmap_q2;
+        TRY(make_tmap(&tmap_q2, q_bf2.p, nun, kp, BM));
+        Sched s;
+        TRY(plan(s, nun, kp, 1 << 20));
+        TRY(upload_schedule(s, false));
+        DistParams dp = base_dist_params(nun, kp, s);
+        dp.thr = uncert_thr.p;
+        dp.coll_count = coll_count.p;
+        dp.coll_idx = coll_idx.p;
+        dp.coll_cap = COLLECT_CAP;
+        prof_begin(K_SCAN);
+        const int rc2 = launch_dist<16, true>(s, tmap_q2, dp);
+        prof_end();
+        TRY(rc2);
+        CollectRerankParams cp{};
+        cp.uncert_list = uncert_list.p;
+        cp.coll_count = coll_count.p;
+        cp.coll_idx = coll_idx.p;
+        cp.dim = dim;
+        cp.ld_x = ld_x;
+        cp.ld_q = ld_q;
+        cp.kk = kk;
+        cp.index_base = index_base;
+        cp.flags = flags;
+        cp.out_idx = d_out_idx;
+        cp.out_dist = d_out_dist;
+        cp.overflow_count = reinterpret_cast<int *>(scalars.p + 5);
+        cp.overflow_list = overflow_list.p;
+        prof_begin(K_SCAN);
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
+            rerank_collect_kernel<double, double><<<nun, 256, 0, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), cp);
+        else if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
+            rerank_collect_kernel<double, float><<<nun, 256, 0, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), cp);
+        else if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
+            rerank_collect_kernel<float, double><<<nun, 256, 0, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), cp);
+        else
+            rerank_collect_kernel<float, float><<<nun, 256, 0, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), cp);
+        prof_end();
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(h_count, scalars.p + 5, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        const int nov = *h_count;
+        if (nov > 0) {
+            stats.exact_scanned += nov;
+            TRY(scan(d_query, q_dtype, ld_q, overflow_list.p, nov, dim, kk, flags, d_out_idx, d_out_dist));
+        }
+        return B200KNN_OK;
+    }
+
     template <int C>
     int tensor_pass(const void *d_query, int q_dtype, int64_t nq, int64_t ld_q, int dim, int kp, int kk, unsigned flags,
                     int32_t *d_out_idx, double *d_out_dist) {
         TRY(q_bf.ensure(static_cast<size_t>(nq) * kp));
         TRY(qnorm_bf.ensure(nq));
-        TRY(qnorm_ex.ensure(nq));
-        TRY(launch_convert(d_query, q_dtype, nq, ld_q, dim, kp, q_bf.p, qnorm_bf.p, qnorm_ex.p, scalars.p + 2));
+        TRY(q_err.ensure(nq));
+        TRY(launch_convert(d_query, q_dtype, nq, ld_q, dim, kp, q_bf.p, qnorm_bf.p, q_err.p, scalars.p + 2));
         CUtensorMap tmap_q;
         TRY(make_tmap(&tmap_q, q_bf.p, nq, kp, BM));
-        const Sched s = plan(nq, kp);
-        TRY(cand_s.ensure(static_cast<size_t>(nq) * s.chunks * C));
-        TRY(cand_i.ensure(static_cast<size_t>(nq) * s.chunks * C));
-        DistParams dp;
-        dp.xnorm = xnorm_bf.p;
-        dp.n = static_cast<int>(n);
-        dp.nq = static_cast<int>(nq);
-        dp.num_kb = (kp + BK - 1) / BK;
-        dp.num_qtiles = s.qt;
-        dp.num_ntiles = s.nt;
-        dp.tiles_per_chunk = s.tiles_per_chunk;
-        dp.num_chunks = s.chunks;
-        dp.qgroup = s.qgroup;
+        Sched s;
+        TRY(plan(s, nq, kp, MAX_KEYS / C));
+        TRY(upload_schedule(s, true));
+        TRY(cand_s.ensure(static_cast<size_t>(nq) * s.max_slots * C));
+        TRY(cand_i.ensure(static_cast<size_t>(nq) * s.max_slots * C));
+        DistParams dp = base_dist_params(nq, kp, s);
         dp.cand_s = cand_s.p;
         dp.cand_i = cand_i.p;
         prof_begin(K_DISTANCE, 2.0 * static_cast<double>(nq) * static_cast<double>(n) * dim);
-        dist_topc_kernel<C><<<s.grid, DIST_THREADS, DIST_SMEM_BYTES, stream>>>(tmap_q, tmap_x, dp);
+        const int rc1 = launch_dist<C, false>(s, tmap_q, dp);
         prof_end();
-        CU_TRY(cudaGetLastError());
+        TRY(rc1);
 
         TRY(uncert_list.ensure(nq));
-        RerankParams rp;
+        TRY(uncert_thr.ensure(nq));
+        RerankParams rp{};
         rp.cand_s = cand_s.p;
         rp.cand_i = cand_i.p;
-        rp.num_chunks = s.chunks;
+        rp.max_slots = s.max_slots;
+        rp.slots_per_qtile = sched_slots.p;
+        rp.qtile_rows = BM * s.cg;
         rp.dim = dim;
         rp.ld_x = ld_x;
         rp.ld_q = ld_q;
@@ -408,14 +608,15 @@ struct Shard {
         rp.index_base = index_base;
         rp.flags = flags;
         rp.qnorm_bf = qnorm_bf.p;
-        rp.qnorm_ex = qnorm_ex.p;
+        rp.q_err = q_err.p;
         rp.max_xnorm_bf_bits = scalars.p;
-        rp.max_xnorm_ex_bits = scalars.p + 1;
+        rp.max_x_err_bits = scalars.p + 1;
         rp.kp = kp;
         rp.out_idx = d_out_idx;
         rp.out_dist = d_out_dist;
         rp.uncert_count = reinterpret_cast<int *>(scalars.p + 4);
         rp.uncert_list = uncert_list.p;
+        rp.uncert_thr = uncert_thr.p;
         CU_TRY(cudaMemsetAsync(scalars.p + 4, 0, sizeof(unsigned int), stream));
         TRY(launch_rerank<C>(d_query, q_dtype, nq, rp));
         if (!(flags & B200KNN_FLAG_NO_CERTIFY)) {
@@ -424,7 +625,7 @@ struct Shard {
             const int nun = *h_count;
             if (nun > 0) {
                 stats.uncertified += nun;
-                TRY(scan(d_query, q_dtype, ld_q, uncert_list.p, nun, dim, kk, flags, d_out_idx, d_out_dist));
+                TRY(second_pass(d_query, q_dtype, ld_q, nun, dim, kp, kk, flags, d_out_idx, d_out_dist));
             }
         }
         return B200KNN_OK;
@@ -582,6 +783,7 @@ int b200knn_get_stats(b200knn_index *ix, b200knn_stats *out) {
         out->kernel_launches += s.stats.kernel_launches;
         out->queries = std::max(out->queries, s.stats.queries);
         out->uncertified += s.stats.uncertified;
+        out->exact_scanned += s.stats.exact_scanned;
         out->ms_convert += s.stats.ms_convert;
         out->ms_distance += s.stats.ms_distance;
         out->ms_rerank += s.stats.ms_rerank;
@@ -620,7 +822,7 @@ int b200knn_add_device(b200knn_index *ix, const void *d_data, int dtype, int64_t
     Shard &s = ix->shards[0];
     CU_TRY(cudaSetDevice(s.device));
     TRY(s.attach_pool(d_data, false, dtype, n, ld, ix->dim, ix->kp, index_base));
-    TRY(s.launch_convert(d_data, dtype, n, ld, ix->dim, ix->kp, s.x_bf.p, s.xnorm_bf.p, s.xnorm_ex.p, s.scalars.p));
+    TRY(s.launch_convert(d_data, dtype, n, ld, ix->dim, ix->kp, s.x_bf.p, s.xnorm_bf.p, s.x_err.p, s.scalars.p));
     ix->n_total = n;
     return B200KNN_OK;
 }
@@ -652,7 +854,7 @@ int b200knn_add(b200knn_index *ix, const void *data, int dtype, int64_t n, int64
             CU_TRY(cudaMemcpy2DAsync(dst, ix->dim * esz, src + static_cast<size_t>(b0) * ld * esz, ld * esz, ix->dim * esz, br,
                                      cudaMemcpyHostToDevice, s.stream));
             TRY(s.launch_convert(dst, dtype, br, ix->dim, ix->dim, ix->kp, s.x_bf.p + static_cast<size_t>(b0) * ix->kp,
-                                 s.xnorm_bf.p + b0, s.xnorm_ex.p + b0, s.scalars.p));
+                                 s.xnorm_bf.p + b0, s.x_err.p + b0, s.scalars.p));
         }
     }
     for (auto &s : ix->shards) {
@@ -706,30 +908,59 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
     const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
     const int G = static_cast<int>(ix->shards.size());
     const int dim = ix->dim;
-    // host chunks: bounded staging, and the H2D of chunk i+1 can overlap the compute of chunk i
+    auto upload = [&](Shard &s, void *dst, const char *src, int64_t rows, cudaStream_t st) -> int {
+        if (ld == dim) CU_TRY(cudaMemcpyAsync(dst, src, static_cast<size_t>(rows) * dim * esz, cudaMemcpyHostToDevice, st));
+        else CU_TRY(cudaMemcpy2DAsync(dst, dim * esz, src, ld * esz, dim * esz, rows, cudaMemcpyHostToDevice, st));
+        return B200KNN_OK;
+    };
+    if (G == 1) {
+        // ---- single device: double-buffered pipeline, the upload of chunk i+1 overlaps the compute of chunk i ----
+        Shard &s = ix->shards[0];
+        CU_TRY(cudaSetDevice(s.device));
+        int64_t chunk = QUERY_CHUNK;
+        if (nq >= 8192) chunk = std::min<int64_t>(QUERY_CHUNK, ((nq + 3) / 4 + BM - 1) / BM * BM);   // ~4 pipeline stages
+        chunk = std::max<int64_t>(BM, std::min<int64_t>(chunk, (512ll << 20) / (static_cast<int64_t>(dim) * esz) / BM * BM));
+        const int64_t nchunks = (nq + chunk - 1) / chunk;
+        TRY(s.q_stage.ensure(static_cast<size_t>(std::min(chunk, nq)) * dim * esz));
+        if (nchunks > 1) TRY(s.q_stage2.ensure(static_cast<size_t>(chunk) * dim * esz));
+        TRY(s.out_idx.ensure(static_cast<size_t>(nq) * kk));
+        TRY(s.out_dist.ensure(static_cast<size_t>(nq) * kk));
+        unsigned char *stage[2] = {s.q_stage.p, s.q_stage2.p};
+        const char *src = static_cast<const char *>(query);
+        TRY(upload(s, stage[0], src, std::min(chunk, nq), s.copy_stream));
+        CU_TRY(cudaEventRecord(s.ev_copied[0], s.copy_stream));
+        for (int64_t c = 0; c < nchunks; c++) {
+            const int b = static_cast<int>(c & 1);
+            const int64_t q0 = c * chunk, cq = std::min(chunk, nq - q0);
+            if (c + 1 < nchunks) {
+                const int nb = b ^ 1;
+                const int64_t q1 = (c + 1) * chunk, cq1 = std::min(chunk, nq - q1);
+                if (c >= 1) CU_TRY(cudaStreamWaitEvent(s.copy_stream, s.ev_consumed[nb], 0));   // chunk c-1 is done with that buffer
+                TRY(upload(s, stage[nb], src + static_cast<size_t>(q1) * ld * esz, cq1, s.copy_stream));
+                CU_TRY(cudaEventRecord(s.ev_copied[nb], s.copy_stream));
+            }
+            CU_TRY(cudaStreamWaitEvent(s.stream, s.ev_copied[b], 0));
+            TRY(s.query_device(stage[b], dtype, cq, dim, dim, ix->kp, k, flags, s.out_idx.p + q0 * kk, s.out_dist.p + q0 * kk));
+            CU_TRY(cudaEventRecord(s.ev_consumed[b], s.stream));
+        }
+        CU_TRY(cudaMemcpyAsync(out_idx, s.out_idx.p, static_cast<size_t>(nq) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        CU_TRY(cudaMemcpyAsync(out_dist, s.out_dist.p, static_cast<size_t>(nq) * kk * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        CU_TRY(cudaStreamSynchronize(s.stream));
+        return B200KNN_OK;
+    }
+    // ---- multi-device handle ----
     const int64_t chunk = std::max<int64_t>(BM, std::min<int64_t>(QUERY_CHUNK, (256ll << 20) / (static_cast<int64_t>(dim) * esz) / BM * BM));
     for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
         const int64_t cq = std::min(chunk, nq - q0);
         const char *src = static_cast<const char *>(query) + static_cast<size_t>(q0) * ld * esz;
-        int active = 0;
         for (int g = 0; g < G; g++) {
             Shard &s = ix->shards[g];
             if (s.n <= 0) continue;
-            active++;
             CU_TRY(cudaSetDevice(s.device));
             TRY(s.q_stage.ensure(static_cast<size_t>(cq) * dim * esz));
-            // a shard may hold fewer than k rows: its list is padded to kk with (-1, DBL_MAX) by the merge input contract
             TRY(s.out_idx.ensure(static_cast<size_t>(cq) * kk));
             TRY(s.out_dist.ensure(static_cast<size_t>(cq) * kk));
-            CU_TRY(cudaMemcpy2DAsync(s.q_stage.p, dim * esz, src, ld * esz, dim * esz, cq, cudaMemcpyHostToDevice, s.stream));
-        }
-        if (active == 1 && G == 1) {
-            Shard &s = ix->shards[0];
-            TRY(s.query_device(s.q_stage.p, dtype, cq, dim, dim, ix->kp, k, flags, s.out_idx.p, s.out_dist.p));
-            CU_TRY(cudaMemcpyAsync(out_idx + q0 * kk, s.out_idx.p, static_cast<size_t>(cq) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
-            CU_TRY(cudaMemcpyAsync(out_dist + q0 * kk, s.out_dist.p, static_cast<size_t>(cq) * kk * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-            CU_TRY(cudaStreamSynchronize(s.stream));
-            continue;
+            TRY(upload(s, s.q_stage.p, src, cq, s.stream));
         }
         // ---- multi-device: local top-k per shard, gather to shard 0 over NVLink, k-way merge there ----
         Shard &s0 = ix->shards[0];

@@ -1,7 +1,7 @@
 // Device code of libb200knn: the kernels of the IMLE matching path.
 //
 //   convert_norm_kernel   HBM-bound.  rows of f64/f32 -> BF16 rows (TMA-friendly pitch) + ||x~||^2 (fp32, of the
-//                         rounded values) + ||x||^2 of the unrounded values (for the exactness certificate).
+//                         rounded values) + ||x - x~||, the exact rounding perturbation (for the exactness certificate).
 //   dist_topc_kernel      tensor-bound.  Q x N distance scores  s~ = ||x~||^2 - 2 q~.x~  as a BF16 GEMM on tcgen05
 //                         (TMA -> 4-stage smem ring -> tcgen05.mma, fp32 accumulators double-buffered in TMEM) with
 //                         a fused per-row top-C selection in the epilogue: the Q x N matrix never reaches HBM.
@@ -29,13 +29,9 @@ constexpr int BM = 128;          // query rows per CTA tile (UMMA M, one TMEM la
 constexpr int BN = 256;          // pool rows per tile (UMMA N, one TMEM fp32 column per row)
 constexpr int BK = 64;           // K elements per pipeline stage: 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;       // K per tcgen05.mma for 16-bit inputs
-constexpr int STAGES = 4;
-constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int TMEM_COLS = 512;               // two 128 x 256 fp32 accumulators
 constexpr int DIST_THREADS = 192;            // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
-constexpr int DIST_SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * BN * 4 + 256;
-constexpr int MAX_CHUNKS = 64;               // shortlists per query the rerank kernel can merge
+constexpr int MAX_KEYS = 4096;               // shortlist entries per query the rerank kernel can merge (slots * C)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -58,55 +54,54 @@ __device__ __forceinline__ float warp_max(float v) {
 // Algorithmic bytes per row: dim * (sizeof(T) + 2) + 8.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __forceinline__ void load8(const T *p, float (&f)[8], double &ex);
+__device__ __forceinline__ void load8(const T *p, double (&d)[8]);
 
 template <>
-__device__ __forceinline__ void load8<double>(const double *p, float (&f)[8], double &ex) {
+__device__ __forceinline__ void load8<double>(const double *p, double (&d)[8]) {
     const double2 *p2 = reinterpret_cast<const double2 *>(p);
-    double2 v0 = __ldcs(p2), v1 = __ldcs(p2 + 1), v2 = __ldcs(p2 + 2), v3 = __ldcs(p2 + 3);
-    double d[8] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, v3.x, v3.y};
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        ex = fma(d[i], d[i], ex);
-        f[i] = static_cast<float>(d[i]);
-    }
+    const double2 v0 = __ldcs(p2), v1 = __ldcs(p2 + 1), v2 = __ldcs(p2 + 2), v3 = __ldcs(p2 + 3);
+    d[0] = v0.x; d[1] = v0.y; d[2] = v1.x; d[3] = v1.y; d[4] = v2.x; d[5] = v2.y; d[6] = v3.x; d[7] = v3.y;
 }
 template <>
-__device__ __forceinline__ void load8<float>(const float *p, float (&f)[8], double &ex) {
+__device__ __forceinline__ void load8<float>(const float *p, double (&d)[8]) {
     const float4 *p4 = reinterpret_cast<const float4 *>(p);
-    float4 v0 = __ldcs(p4), v1 = __ldcs(p4 + 1);
-    f[0] = v0.x; f[1] = v0.y; f[2] = v0.z; f[3] = v0.w;
-    f[4] = v1.x; f[5] = v1.y; f[6] = v1.z; f[7] = v1.w;
-#pragma unroll
-    for (int i = 0; i < 8; i++) ex = fma(static_cast<double>(f[i]), static_cast<double>(f[i]), ex);
+    const float4 v0 = __ldcs(p4), v1 = __ldcs(p4 + 1);
+    d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w; d[4] = v1.x; d[5] = v1.y; d[6] = v1.z; d[7] = v1.w;
 }
 
+// Outputs per row: the BF16 row x~ (zero padded to kp), ||x~||^2 (fp32 sum of the exact squares of the rounded
+// values) and err = ||x - x~|| rounded up — the EXACT size of the rounding perturbation, which is what the
+// exactness certificate needs (a worst-case 2^-9 ||x|| bound is ~2.5x looser).  Grid-wide maxima of both are
+// kept as float bit patterns (non-negative floats order like unsigned ints).
 // vec != 0 requires: dim % 8 == 0 (so kp == dim), src rows 16-byte aligned.
 template <typename T>
 __global__ void __launch_bounds__(256)
 convert_norm_kernel(const T *__restrict__ src, int64_t n, int64_t ld, int dim, int kp, int vec,
-                    __nv_bfloat16 *__restrict__ dst, float *__restrict__ norm_bf, float *__restrict__ norm_ex,
-                    unsigned int *__restrict__ max_norm_bf_bits, unsigned int *__restrict__ max_norm_ex_bits) {
+                    __nv_bfloat16 *__restrict__ dst, float *__restrict__ norm_bf, float *__restrict__ err_out,
+                    unsigned int *__restrict__ max_norm_bf_bits, unsigned int *__restrict__ max_err_bits) {
     const int lane = threadIdx.x & 31;
     const int64_t warps_per_grid = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
-    float mx_bf = 0.f, mx_ex = 0.f;
+    float mx_bf = 0.f, mx_er = 0.f;
     for (int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps_per_grid) {
         const T *s = src + row * ld;
         __nv_bfloat16 *d = dst + row * kp;
         float acc = 0.f;      // sum of squares of the ROUNDED values (exact products, fp32 accumulation)
-        double ex = 0.0;      // sum of squares of the unrounded values
+        double er = 0.0;      // sum of squares of (x - x~)
         if (vec) {
             const int groups = dim >> 3;
             for (int g = lane; g < groups; g += 32) {
-                float f[8];
-                load8<T>(s + (g << 3), f, ex);
+                double v[8];
+                load8<T>(s + (g << 3), v);
                 __nv_bfloat162 b[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    b[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                    b[i] = __floats2bfloat162_rn(static_cast<float>(v[2 * i]), static_cast<float>(v[2 * i + 1]));
                     const float lo = __low2float(b[i]), hi = __high2float(b[i]);
                     acc = fmaf(lo, lo, acc);
                     acc = fmaf(hi, hi, acc);
+                    const double e0 = v[2 * i] - static_cast<double>(lo), e1 = v[2 * i + 1] - static_cast<double>(hi);
+                    er = fma(e0, e0, er);
+                    er = fma(e1, e1, er);
                 }
                 uint4 out;
                 out.x = *reinterpret_cast<uint32_t *>(&b[0]);
@@ -117,60 +112,70 @@ convert_norm_kernel(const T *__restrict__ src, int64_t n, int64_t ld, int dim, i
             }
         } else {
             for (int e = lane; e < kp; e += 32) {
-                float f = 0.f;
-                if (e < dim) {
-                    const T v = s[e];
-                    ex = fma(static_cast<double>(v), static_cast<double>(v), ex);
-                    f = static_cast<float>(v);
-                }
-                const __nv_bfloat16 b = __float2bfloat16_rn(f);
+                double v = 0.0;
+                if (e < dim) v = static_cast<double>(s[e]);
+                const __nv_bfloat16 b = __float2bfloat16_rn(static_cast<float>(v));
                 const float fb = __bfloat162float(b);
                 acc = fmaf(fb, fb, acc);
+                const double e0 = v - static_cast<double>(fb);
+                er = fma(e0, e0, er);
                 d[e] = b;
             }
         }
         acc = warp_sum(acc);
-        ex = warp_sum(ex);
-        const float exf = __double2float_ru(ex);
+        er = warp_sum(er);
+        const float erf = __double2float_ru(sqrt(er) * (1.0 + 1e-9));
         if (lane == 0) {
             norm_bf[row] = acc;
-            norm_ex[row] = exf;
+            err_out[row] = erf;
         }
         mx_bf = fmaxf(mx_bf, acc);
-        mx_ex = fmaxf(mx_ex, exf);
+        mx_er = fmaxf(mx_er, erf);
     }
-    if (lane == 0) {   // non-negative floats order like their bit patterns
+    if (lane == 0) {
         if (mx_bf > 0.f) atomicMax(max_norm_bf_bits, __float_as_uint(mx_bf));
-        if (mx_ex > 0.f) atomicMax(max_norm_ex_bits, __float_as_uint(mx_ex));
+        if (mx_er > 0.f) atomicMax(max_err_bits, __float_as_uint(mx_er));
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Kernel 2: BF16 distance GEMM on tcgen05 with fused top-C epilogue.
 // ------------------------------------------------------------------------------------------------
+// Work schedule (built on the host, Shard::plan): `nrounds` rounds of `workers` items; worker w (a CTA, or a CTA pair
+// for cta_group::2) takes items[r * workers + w] in round r.  An item is one query tile swept over a contiguous range
+// of pool tiles.  All items of a round have the same length (+-1 tile) and the query tiles of a round form a group
+// whose BF16 rows fit in L2 next to the pool tiles being streamed, so the workers that share pool tiles stay in
+// lockstep and each pool tile is fetched from HBM once per round; a grid barrier separates rounds.
+struct WorkItem { int qtile, t0, t1, slot; };   // qtile < 0: idle in this round; slot: low 16 bits = shortlist slot of the
+                                                // query rows (= pool-tile stream of the round), high 16 bits = workers sharing the stream
+
 struct DistParams {
     const float *xnorm;      // [n] ||x~||^2
     int n;                   // pool rows in this shard
     int nq;                  // query rows
     int num_kb;              // ceil(kp / BK)
-    int num_qtiles;          // ceil(nq / BM)
-    int num_ntiles;          // ceil(n / BN)
-    int tiles_per_chunk;     // N tiles swept per work item
-    int num_chunks;          // ceil(num_ntiles / tiles_per_chunk)  (<= MAX_CHUNKS)
-    int qgroup;              // query tiles scheduled together (L2 working-set control)
-    float *cand_s;           // [nq][num_chunks][C] approximate scores, ascending
-    int *cand_i;             // [nq][num_chunks][C] shard-local row index (-1 = empty slot)
+    const WorkItem *items;   // [nrounds][workers]
+    int nrounds;
+    int workers;
+    unsigned int *round_counter;   // grid barrier between rounds (zeroed by the host before the launch)
+    unsigned int *stream_sync;     // [nrounds][max_slots] lockstep counters of the workers sharing a pool-tile stream (zeroed)
+    int sync_tiles;                // the sharers of a stream re-align every sync_tiles tiles (0 = never)
+    int max_slots;           // shortlists per query row in cand_* (row stride)
+    float *cand_s;           // [nq][max_slots][C] approximate scores, ascending
+    int *cand_i;             // [nq][max_slots][C] shard-local row index (-1 = empty slot)
+    // collect mode (second pass): every pool row whose score is <= thr[row] is appended to the row's list
+    const float *thr;        // [nq]
+    int *coll_count;         // [nq] running count (may exceed coll_cap: overflow)
+    int *coll_idx;           // [nq][coll_cap]
+    int coll_cap;
+    unsigned opt;            // tuning switches (A/B measurements): bit0 early barrier probe, bit1 double-buffered TMEM loads,
+                             // bit2 grid barrier between rounds
 };
 
-struct WorkItem { int qtile, chunk; };
-__device__ __forceinline__ WorkItem decode_item(int it, const DistParams &p) {
-    const int per_group = p.qgroup * p.num_chunks;
-    const int g = it / per_group;
-    const int r = it - g * per_group;
-    const int gsize = min(p.qgroup, p.num_qtiles - g * p.qgroup);
+__device__ __forceinline__ WorkItem load_item(const DistParams &p, int round, int worker) {
+    const int4 v = __ldg(reinterpret_cast<const int4 *>(p.items) + static_cast<int64_t>(round) * p.workers + worker);
     WorkItem w;
-    w.chunk = r / gsize;
-    w.qtile = g * p.qgroup + (r - w.chunk * gsize);
+    w.qtile = v.x; w.t0 = v.y; w.t1 = v.z; w.slot = v.w;
     return w;
 }
 
@@ -191,102 +196,166 @@ __device__ __forceinline__ void topc_insert(float (&v)[C], int (&id)[C], float s
     }
 }
 
-template <int C>
+// COLLECT == false: per-(query row, chunk) top-C shortlist.   COLLECT == true: threshold collection (second pass).
+// CG == 1: one CTA computes a 128(query) x 256(pool) tile per step.
+// CG == 2: a cluster of two CTAs (one SM pair) computes a 256 x 256 tile with tcgen05.mma.cta_group::2: each CTA
+//          stages its own 128 query rows (A half) and 128 of the 256 pool rows (B half), so per SM the operand
+//          traffic into and out of shared memory drops by a third; CTA rank 0 issues every MMA, both CTAs run
+//          the TMA producer and the epilogue for their own 128 query rows (their own TMEM lanes).
+template <int CG>
+struct DistCfg {
+    static constexpr int STAGES = (CG == 1) ? 4 : 6;
+    static constexpr int B_ROWS = BN / CG;                       // pool rows staged per CTA
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = B_ROWS * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2 * BN * 4 + 256;
+};
+
+template <int C, bool COLLECT, int CG>
 __global__ void __launch_bounds__(DIST_THREADS, 1)
 dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x, const DistParams p) {
+    using Cfg = DistCfg<CG>;
+    constexpr int NSTAGE = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
-    // SWIZZLE_128B tiles must sit on 1024-byte boundaries
+    // SWIZZLE_128B tiles must sit on 1024-byte boundaries (identical carve-up in both CTAs of a pair)
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t smem_a = base;
-    const uint32_t smem_b = base + STAGES * A_STAGE_BYTES;
-    float *xn_s = reinterpret_cast<float *>(gen + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));   // [2][BN]
-    const uint32_t bars = base + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * BN * 4;
-    const uint32_t bar_full = bars;                       // [STAGES]  TMA -> MMA
-    const uint32_t bar_empty = bars + 8 * STAGES;         // [STAGES]  MMA -> TMA
-    const uint32_t bar_tfull = bars + 16 * STAGES;        // [2]       MMA -> epilogue
-    const uint32_t bar_tempty = bars + 16 * STAGES + 16;  // [2]       epilogue -> MMA
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * BN * 4 + 16 * STAGES + 32);
+    const uint32_t smem_b = base + NSTAGE * Cfg::A_BYTES;
+    float *xn_s = reinterpret_cast<float *>(gen + NSTAGE * Cfg::STAGE_BYTES);   // [2][BN]
+    const uint32_t bars = base + NSTAGE * Cfg::STAGE_BYTES + 2 * BN * 4;
+    const uint32_t bar_full = bars;                       // [NSTAGE]  TMA -> MMA      (the leader's copy is used)
+    const uint32_t bar_empty = bars + 8 * NSTAGE;         // [NSTAGE]  MMA -> TMA      (one per CTA)
+    const uint32_t bar_tfull = bars + 16 * NSTAGE;        // [2]       MMA -> epilogue (one per CTA)
+    const uint32_t bar_tempty = bars + 16 * NSTAGE + 16;  // [2]       epilogue -> MMA (the leader's copy is used)
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + NSTAGE * Cfg::STAGE_BYTES + 2 * BN * 4 + 16 * NSTAGE + 32);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int worker = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;          // cluster (or CTA) index
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_x);
-        for (int s = 0; s < STAGES; s++) {
-            mbar_init(bar_full + 8 * s, 1);
+        for (int s = 0; s < NSTAGE; s++) {
+            mbar_init(bar_full + 8 * s, 1);       // the leader's arrive.expect_tx covers the bytes of BOTH CTAs' loads
             mbar_init(bar_empty + 8 * s, 1);
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(bar_tfull + 8 * a, 1);
-            mbar_init(bar_tempty + 8 * a, 128);
+            mbar_init(bar_tempty + 8 * a, 4 * CG);   // one arrival per epilogue warp of every CTA
         }
         fence_mbar_init();
     }
+    if (CG == 2) cluster_sync_all();   // barriers of both CTAs initialised before anyone allocates / arrives remotely
     if (warp == 1) {
-        tmem_alloc<1>(smem_u32(const_cast<uint32_t *>(tmem_slot)), TMEM_COLS);
-        tmem_relinquish<1>();
+        tmem_alloc<CG>(smem_u32(const_cast<uint32_t *>(tmem_slot)), TMEM_COLS);
+        tmem_relinquish<CG>();
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_items = p.num_qtiles * p.num_chunks;
-
     if (warp == 0) {
-        // ===================== TMA producer (one lane) =====================
+        // ===================== TMA producer (one lane per CTA) =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-                const WorkItem w = decode_item(it, p);
-                const int q0 = w.qtile * BM;
-                const int t0 = w.chunk * p.tiles_per_chunk;
-                const int t1 = min(t0 + p.tiles_per_chunk, p.num_ntiles);
-                for (int t = t0; t < t1; t++) {
-                    const int n0 = t * BN;
-                    for (int kb = 0; kb < p.num_kb; kb++) {
-                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                        mbar_expect_tx(bar_full + 8 * stage, A_STAGE_BYTES + B_STAGE_BYTES);
-                        tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_q, bar_full + 8 * stage, kb * BK, q0);
-                        tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_x, bar_full + 8 * stage, kb * BK, n0);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            uint32_t full_remote = 0;   // cluster address of the leader's full barriers
+            if (CG == 2) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(full_remote) : "r"(bar_full), "r"(0));
+            for (int round = 0; round < p.nrounds; round++) {
+                const WorkItem w = load_item(p, round, worker);
+                if (w.qtile >= 0) {
+                    const int q0 = w.qtile * (BM * CG) + static_cast<int>(cta_rank) * BM;
+                    const int sharers = w.slot >> 16;
+                    unsigned int *sync = p.stream_sync + static_cast<int64_t>(round) * p.max_slots + (w.slot & 0xffff);
+                    for (int t = w.t0; t < w.t1; t++) {
+                        // lockstep: the workers streaming the same pool tiles re-align every sync_tiles tiles, so a tile
+                        // fetched from HBM by the first of them is still in L2 when the last one asks for it
+                        if (p.sync_tiles > 0 && sharers > 1 && (CG == 1 || leader) && t > w.t0 && (t - w.t0) % p.sync_tiles == 0) {
+                            const unsigned int target = static_cast<unsigned int>((t - w.t0) / p.sync_tiles) * sharers;
+                            atomicAdd(sync, 1u);
+                            while (*reinterpret_cast<volatile unsigned int *>(sync) < target) __nanosleep(128);
+                        }
+                        const int n0 = t * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS;
+                        for (int kb = 0; kb < p.num_kb; kb++) {
+                            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                            if (CG == 1) {
+                                mbar_expect_tx(bar_full + 8 * stage, Cfg::STAGE_BYTES);
+                                tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_q, bar_full + 8 * stage, kb * BK, q0);
+                                tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_x, bar_full + 8 * stage, kb * BK, n0);
+                            } else {
+                                // all four loads of the pair (2 x A half, 2 x B half) signal the LEADER's barrier; the
+                                // peer never arrives there: its loads only complete_tx (a remote arrive per K block
+                                // would cost a cluster-scope fence each time)
+                                if (leader) mbar_expect_tx(bar_full + 8 * stage, 2 * Cfg::STAGE_BYTES);
+                                const uint32_t fb = leader ? (bar_full + 8 * stage) : (full_remote + 8 * stage);
+                                tma_load_2d_cg2(smem_a + stage * Cfg::A_BYTES, &tmap_q, fb, kb * BK, q0);
+                                tma_load_2d_cg2(smem_b + stage * Cfg::B_BYTES, &tmap_x, fb, kb * BK, n0);
+                            }
+                            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        }
                     }
+                }
+                // grid barrier: nobody starts streaming the next round's pool tiles before everyone is done issuing
+                // this round's loads (keeps the workers that share pool tiles in lockstep)
+                if ((p.opt & 4u) && round + 1 < p.nrounds) {
+                    __threadfence();
+                    atomicAdd(p.round_counter, 1u);
+                    const unsigned int target = static_cast<unsigned int>(round + 1) * gridDim.x;
+                    while (*reinterpret_cast<volatile unsigned int *>(p.round_counter) < target) __nanosleep(256);
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one lane) =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+        // ===================== MMA issuer (leader CTA only) =====================
+        // The whole warp runs the loop converged (uniform control flow, uniform registers); one elected lane issues.
+        // The issuing thread is on the critical path: per K block it must spend less than the 512 tensor cycles the
+        // four MMAs take, so the probe of the NEXT stage's barrier is issued before the current MMAs and its
+        // latency overlaps their issue.
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-                const WorkItem w = decode_item(it, p);
-                const int t0 = w.chunk * p.tiles_per_chunk;
-                const int t1 = min(t0 + p.tiles_per_chunk, p.num_ntiles);
-                for (int t = t0; t < t1; t++) {
-                    mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);     // epilogue has drained this accumulator
+            bool ready = false;     // result of the early probe of full[stage]
+            for (int round = 0; round < p.nrounds; round++) {
+                const WorkItem w = load_item(p, round, worker);
+                if (w.qtile < 0) continue;
+                for (int t = w.t0; t < w.t1; t++) {
+                    mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);     // epilogues have drained this accumulator
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + acc * BN;
                     for (int kb = 0; kb < p.num_kb; kb++) {
-                        mbar_wait(bar_full + 8 * stage, phase);        // TMA bytes have landed
+                        if (!ready) mbar_wait(bar_full + 8 * stage, phase);   // TMA bytes (of both CTAs) have landed
                         tc_fence_after();
-                        const uint64_t da = make_smem_desc_sw128(smem_a + stage * A_STAGE_BYTES);
-                        const uint64_t db = make_smem_desc_sw128(smem_b + stage * B_STAGE_BYTES);
+                        const uint32_t cur = stage;
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        ready = (p.opt & 1u) ? mbar_test_wait(bar_full + 8 * stage, phase) : false;   // early, non-blocking probe of the next stage
+                        if (elect_one()) {
+                            const uint64_t da = make_smem_desc_sw128(smem_a + cur * Cfg::A_BYTES);
+                            const uint64_t db = make_smem_desc_sw128(smem_b + cur * Cfg::B_BYTES);
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; k++) {
-                            // +32 bytes per K slice inside the 128-byte swizzle row: +2 in the (>>4) address field
-                            umma_bf16<1>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            for (int k = 0; k < BK / UMMA_K; k++) {
+                                // +32 bytes per K slice inside the 128-byte swizzle row: +2 in the (>>4) address field
+                                umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            }
+                            // frees the smem slot (in both CTAs) when the MMAs retire
+                            if (CG == 1) umma_commit(bar_empty + 8 * cur);
+                            else umma_commit_cg2(bar_empty + 8 * cur, 0x3);
+                            if (kb == p.num_kb - 1) {                      // accumulator complete -> epilogue(s)
+                                if (CG == 1) umma_commit(bar_tfull + 8 * acc);
+                                else umma_commit_cg2(bar_tfull + 8 * acc, 0x3);
+                            }
                         }
-                        umma_commit(bar_empty + 8 * stage);            // frees the smem slot when the MMAs retire
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        __syncwarp();
                     }
-                    umma_commit(bar_tfull + 8 * acc);                  // accumulator complete -> epilogue
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1;
                 }
@@ -299,14 +368,20 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const int et = threadIdx.x - 64;               // 0..127
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-            const WorkItem w = decode_item(it, p);
-            const int t0 = w.chunk * p.tiles_per_chunk;
-            const int t1 = min(t0 + p.tiles_per_chunk, p.num_ntiles);
+        for (int round = 0; round < p.nrounds; round++) {
+            const WorkItem w = load_item(p, round, worker);
+            if (w.qtile < 0) continue;
+            const int t0 = w.t0, t1 = w.t1;
             float v[C];
             int id[C];
+            const int q = w.qtile * (BM * CG) + static_cast<int>(cta_rank) * BM + row_in_tile;
+            float thr = -FLT_MAX;
+            if constexpr (COLLECT) {
+                if (q < p.nq) thr = __ldg(p.thr + q);
+            } else {
 #pragma unroll
-            for (int i = 0; i < C; i++) { v[i] = FLT_MAX; id[i] = -1; }
+                for (int i = 0; i < C; i++) { v[i] = FLT_MAX; id[i] = -1; }
+            }
             for (int t = t0; t < t1; t++) {
                 const int n0 = t * BN;
                 // stage ||x~||^2 of this tile; rows past the end of the pool can never be selected
@@ -320,30 +395,60 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; c++) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(taddr + c * 32, r);
-                    tmem_ld_wait();
+                // TMEM -> registers in 32-column slabs, double-buffered: the load of slab c+1 is in flight while
+                // slab c is scored and filtered
+                auto consume = [&](const uint32_t (&r)[32], int c) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const float s = fmaf(-2.f, __uint_as_float(r[j]), xs[c * 32 + j]);
-                        if (s < v[C - 1]) topc_insert<C>(v, id, s, n0 + c * 32 + j);
+                        if constexpr (COLLECT) {
+                            if (s <= thr) {
+                                const int pos = atomicAdd(p.coll_count + q, 1);
+                                if (pos < p.coll_cap) p.coll_idx[static_cast<int64_t>(q) * p.coll_cap + pos] = n0 + c * 32 + j;
+                            }
+                        } else {
+                            if (s < v[C - 1]) topc_insert<C>(v, id, s, n0 + c * 32 + j);
+                        }
+                    }
+                };
+                uint32_t ra[32], rb[32];
+                if (p.opt & 2u) {
+                    tmem_ld_32x32(taddr, ra);
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; c += 2) {
+                        tmem_ld_wait();
+                        tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+                        consume(ra, c);
+                        tmem_ld_wait();
+                        if (c + 2 < BN / 32) tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+                        consume(rb, c + 1);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; c++) {
+                        tmem_ld_32x32(taddr + c * 32, ra);
+                        tmem_ld_wait();
+                        consume(ra, c);
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(bar_tempty + 8 * acc);
+                __syncwarp();
+                if (lane == 0) {                       // this warp is done with the accumulator
+                    if (CG == 1 || leader) mbar_arrive(bar_tempty + 8 * acc);
+                    else mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+                }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
-            const int q = w.qtile * BM + row_in_tile;
-            if (q < p.nq) {
-                float *cs = p.cand_s + (static_cast<int64_t>(q) * p.num_chunks + w.chunk) * C;
-                int *ci = p.cand_i + (static_cast<int64_t>(q) * p.num_chunks + w.chunk) * C;
+            if constexpr (!COLLECT) {
+                if (q < p.nq) {
+                    float *cs = p.cand_s + (static_cast<int64_t>(q) * p.max_slots + (w.slot & 0xffff)) * C;
+                    int *ci = p.cand_i + (static_cast<int64_t>(q) * p.max_slots + (w.slot & 0xffff)) * C;
 #pragma unroll
-                for (int i = 0; i < C; i += 4) {
-                    *reinterpret_cast<float4 *>(cs + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    *reinterpret_cast<int4 *>(ci + i) = make_int4(id[i], id[i + 1], id[i + 2], id[i + 3]);
+                    for (int i = 0; i < C; i += 4) {
+                        *reinterpret_cast<float4 *>(cs + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        *reinterpret_cast<int4 *>(ci + i) = make_int4(id[i], id[i + 1], id[i + 2], id[i + 3]);
+                    }
                 }
             }
         }
@@ -351,9 +456,10 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();   // the peer's smem / TMEM stay alive until the leader's last MMA has retired
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<1>(tmem_base, TMEM_COLS);
+        tmem_dealloc<CG>(tmem_base, TMEM_COLS);
     }
 }
 
@@ -371,7 +477,9 @@ __device__ __forceinline__ float float_from_order_bits(uint32_t b) {
 struct RerankParams {
     const float *cand_s;
     const int *cand_i;
-    int num_chunks;
+    int max_slots;                 // row stride of cand_* in shortlists
+    const int *slots_per_qtile;    // [query tiles] shortlists actually written for the rows of that tile
+    int qtile_rows;                // query rows per tile (BM * CG)
     int dim;
     int64_t ld_x, ld_q;
     int n;                         // pool rows in the shard
@@ -379,32 +487,60 @@ struct RerankParams {
     int64_t index_base;
     unsigned flags;                // B200KNN_FLAG_*
     const float *qnorm_bf;         // [nq] ||q~||^2 (fp32, of rounded values)
-    const float *qnorm_ex;         // [nq] ||q||^2 rounded up
-    const unsigned int *max_xnorm_bf_bits;   // device scalars (pool)
-    const unsigned int *max_xnorm_ex_bits;
+    const float *q_err;            // [nq] ||q - q~|| rounded up
+    const unsigned int *max_xnorm_bf_bits;   // device scalars (pool): max ||x~||^2, max ||x - x~||
+    const unsigned int *max_x_err_bits;
     int kp;                        // padded K of the BF16 operands (accumulation length)
     int32_t *out_idx;              // [nq][kk]
     double *out_dist;              // [nq][kk]
     int *uncert_count;             // number of uncertified queries
     int *uncert_list;              // their row numbers
+    float *uncert_thr;             // score threshold for the collection pass, per list slot
 };
+
+// Error model shared by the pruning rule, the certificate and the second-pass threshold.  With q~, x~ the BF16
+// roundings:  s~ + ||q~||^2 = ||q~ - x~||^2 up to fp32 accumulation error eps_acc, and
+// | ||q - x|| - ||q~ - x~|| | <= ||q - q~|| + ||x - x~|| =: eta   (triangle inequality; both norms are computed
+// exactly by convert_norm_kernel, the pool side as a maximum over rows).
+struct ErrModel {
+    double qn_bf, eps_acc, eta;
+    __device__ __forceinline__ double lower(double s) const {   // lower bound on the true distance, given score s
+        const double v = s + qn_bf - eps_acc;
+        return (v > 0.0 ? sqrt(v) : 0.0) - eta;
+    }
+    __device__ __forceinline__ double upper(double s) const {   // upper bound on the true distance
+        const double v = s + qn_bf + eps_acc;
+        return (v > 0.0 ? sqrt(v) : 0.0) + eta;
+    }
+};
+__device__ __forceinline__ ErrModel make_err_model(const RerankParams &p, int q) {
+    ErrModel m;
+    m.qn_bf = static_cast<double>(p.qnorm_bf[q]);
+    const double xn_bf = static_cast<double>(__uint_as_float(*p.max_xnorm_bf_bits));
+    const double K = static_cast<double>(p.kp);
+    // fp32 accumulation error of the MMA (K terms of magnitude <= ||q~|| ||x~||, x2 for the -2 factor, truncating
+    // adds assumed), of the fp32 norm sums, and of forming s~ in fp32
+    m.eps_acc = (K + 8.0) * 2.4e-7 * sqrt(m.qn_bf * xn_bf) * 1.001 + (K / 16.0 + 8.0) * 1.2e-7 * (xn_bf + m.qn_bf);
+    m.eta = (static_cast<double>(p.q_err[q]) + static_cast<double>(__uint_as_float(*p.max_x_err_bits))) * (1.0 + 1e-6) + 1e-30;
+    return m;
+}
 
 template <typename TX, typename TQ, int C>
 __global__ void __launch_bounds__(128)
 rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const RerankParams p) {
-    constexpr int MAXP = MAX_CHUNKS * C;
-    __shared__ unsigned long long keys[MAXP];
+    __shared__ unsigned long long keys[MAX_KEYS];
     __shared__ double d2s[C];
+    __shared__ int m_s;
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
-    const int total = p.num_chunks * C;
+    const int total = __ldg(p.slots_per_qtile + q / p.qtile_rows) * C;
     int P = 1;
     while (P < total) P <<= 1;
 
     for (int i = tid; i < P; i += blockDim.x) {
         unsigned long long key = ~0ull;
         if (i < total) {
-            const int64_t o = static_cast<int64_t>(q) * total + i;
+            const int64_t o = static_cast<int64_t>(q) * p.max_slots * C + i;
             const int idx = p.cand_i[o];
             if (idx >= 0) key = (static_cast<unsigned long long>(float_order_bits(p.cand_s[o])) << 32) | static_cast<uint32_t>(idx);
         }
@@ -425,27 +561,49 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
             __syncthreads();
         }
     }
-    // exact float64 distances of the C best-scored candidates
+    // Pruning: candidate c (ascending score) can be among the true top-kk only if its distance lower bound does not
+    // exceed the kk-th smallest distance upper bound.  Scores are sorted, so the survivors are a prefix of length m.
+    if (tid == 0) {
+        int m = min(C, p.kk);
+        if (keys[p.kk - 1] != ~0ull) {
+            const ErrModel em = make_err_model(p, q);
+            const double u = em.upper(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(keys[p.kk - 1] >> 32))));
+            while (m < C && keys[m] != ~0ull &&
+                   em.lower(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(keys[m] >> 32)))) <= u) m++;
+        } else {
+            m = C;
+        }
+        m_s = m;
+    }
+    __syncthreads();
+    const int m = m_s;
+    // exact float64 distances of the surviving candidates (the arithmetic of util.c:62-69, pairwise-summed)
     const int warp = tid >> 5, lane = tid & 31;
     const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
     for (int c = warp; c < C; c += 4) {
         const unsigned long long key = keys[c];
-        double acc = 0.0;
-        if (key != ~0ull) {
+        double acc = DBL_MAX;
+        if (c < m && key != ~0ull) {
             const TX *xr = x + static_cast<int64_t>(static_cast<uint32_t>(key)) * p.ld_x;
-            for (int e = lane; e < p.dim; e += 32) {
-                const double diff = static_cast<double>(qr[e]) - static_cast<double>(xr[e]);
-                acc = fma(diff, diff, acc);
+            double a0 = 0.0, a1 = 0.0;
+            int e = lane;
+            for (; e + 32 < p.dim; e += 64) {
+                const double d0 = static_cast<double>(qr[e]) - static_cast<double>(xr[e]);
+                const double d1 = static_cast<double>(qr[e + 32]) - static_cast<double>(xr[e + 32]);
+                a0 = fma(d0, d0, a0);
+                a1 = fma(d1, d1, a1);
             }
-            acc = warp_sum(acc);
-        } else {
-            acc = DBL_MAX;
+            if (e < p.dim) {
+                const double d0 = static_cast<double>(qr[e]) - static_cast<double>(xr[e]);
+                a0 = fma(d0, d0, a0);
+            }
+            acc = warp_sum(a0 + a1);
         }
         if (lane == 0) d2s[c] = acc;
     }
     __syncthreads();
     if (warp == 0) {
-        // rank the C exact distances by (d2, index); C <= 32
+        // rank the exact distances by (d2, index); C <= 32
         double myd = DBL_MAX;
         uint32_t myi = 0xffffffffu;
         if (lane < C) { myd = d2s[lane]; myi = static_cast<uint32_t>(keys[lane]); }
@@ -460,39 +618,127 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
             p.out_idx[static_cast<int64_t>(q) * p.kk + rank] = static_cast<int32_t>(p.index_base + myi);
             p.out_dist[static_cast<int64_t>(q) * p.kk + rank] = (p.flags & 1u) ? myd : sqrt(myd);
         }
-        // k-th exact distance (rank kk-1), broadcast to lane 0
-        const unsigned m = __ballot_sync(0xffffffffu, lane < C && rank == p.kk - 1);
-        const double dk2 = __shfl_sync(0xffffffffu, myd, m ? (__ffs(m) - 1) : 0);
+        // k-th exact distance (rank kk-1), broadcast
+        const unsigned mk = __ballot_sync(0xffffffffu, lane < C && rank == p.kk - 1);
+        const double dk2 = __shfl_sync(0xffffffffu, myd, mk ? (__ffs(mk) - 1) : 0);
         if (lane == 0 && !(p.flags & 2u)) {
-            // ---- certificate --------------------------------------------------------------------
-            // every pool row NOT among the C kept has approximate score >= tau (the C-th kept score).
-            // In exact arithmetic  s~ + ||q~||^2 = ||q~ - x~||^2; rounding to BF16 moves a vector by at
-            // most 2^-9 of its norm, so  d(q,x) >= ||q~ - x~|| - 2^-9 (||q|| + ||x||).
+            // ---- certificate: every pool row NOT among the C kept has score >= tau (the C-th kept score), hence
+            // true distance >= lower(tau).  The answer is exact when the kk-th exact distance is below that.
             bool certified = true;
             const unsigned long long kc = keys[C - 1];
-            if (p.n > C && kc != ~0ull && m != 0) {
-                const double tau = static_cast<double>(float_from_order_bits(static_cast<uint32_t>(kc >> 32)));
-                const double qn_bf = static_cast<double>(p.qnorm_bf[q]);
-                const double qn_ex = static_cast<double>(p.qnorm_ex[q]);
-                const double xn_bf = static_cast<double>(__uint_as_float(*p.max_xnorm_bf_bits));
-                const double xn_ex = static_cast<double>(__uint_as_float(*p.max_xnorm_ex_bits));
-                const double K = static_cast<double>(p.kp);
-                // fp32 accumulation error of the MMA (K terms, magnitude <= ||q~|| ||x~||, x2 for the -2 factor),
-                // of the fp32 norm sums, and of forming s~ in fp32
-                const double eps_acc = (K + 8.0) * 2.4e-7 * sqrt(qn_bf * xn_bf) * 1.001
-                                     + (K / 16.0 + 8.0) * 1.2e-7 * (xn_bf + qn_bf);
-                const double lb2 = tau + qn_bf - eps_acc;
-                const double eta = (1.0 / 512.0) * 1.0001 * (sqrt(qn_ex) + sqrt(xn_ex)) + 1e-30;
-                const double lb = (lb2 > 0.0 ? sqrt(lb2) : 0.0) - eta;
-                certified = (lb > 0.0) && (sqrt(dk2) < lb);
-            } else if (m == 0) {
-                certified = (p.n <= C);   // fewer than kk exact candidates can only happen for tiny pools
+            const ErrModel em = make_err_model(p, q);
+            const double dk = sqrt(dk2);
+            if (p.n > C && kc != ~0ull && mk != 0) {
+                const double lb = em.lower(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(kc >> 32))));
+                certified = (lb > 0.0) && (dk < lb);
+            } else if (mk == 0) {
+                certified = (p.n <= C);
             }
             if (!certified) {
+                // second pass collects every row with score <= thr: any x with d(q,x) <= dk has
+                // ||q~ - x~|| <= dk + eta, i.e. s~ <= (dk + eta)^2 - ||q~||^2 + eps_acc.
+                const double t = (dk + em.eta) * (dk + em.eta) - em.qn_bf + em.eps_acc;
                 const int slot = atomicAdd(p.uncert_count, 1);
                 p.uncert_list[slot] = q;
+                p.uncert_thr[slot] = __double2float_ru(t + 1e-6 * fabs(t));
             }
         }
+    }
+}
+
+// Second pass, part 2: exact re-rank of the collected lists.  One block per uncertified query (list slot).
+// Lists longer than the capacity (or shorter than kk) are handed to the exact scan via the overflow list.
+constexpr int COLLECT_CAP = 1024;
+struct CollectRerankParams {
+    const int *uncert_list;      // [nun] query rows
+    const int *coll_count;       // [nun]
+    const int *coll_idx;         // [nun][COLLECT_CAP]
+    int dim;
+    int64_t ld_x, ld_q;
+    int kk;
+    int64_t index_base;
+    unsigned flags;
+    int32_t *out_idx;
+    double *out_dist;
+    int *overflow_count;
+    int *overflow_list;          // query rows that need the exact scan
+};
+
+template <typename TX, typename TQ>
+__global__ void __launch_bounds__(256)
+rerank_collect_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const CollectRerankParams p) {
+    __shared__ double d2[COLLECT_CAP];
+    __shared__ int idx[COLLECT_CAP];
+    __shared__ double sd[8];
+    __shared__ int si[8];
+    __shared__ double last_d_s;
+    __shared__ int last_i_s;
+    const int slot = blockIdx.x;
+    const int q = p.uncert_list[slot];
+    const int cnt = p.coll_count[slot];
+    if (cnt > COLLECT_CAP || cnt < p.kk) {
+        if (threadIdx.x == 0) {
+            const int o = atomicAdd(p.overflow_count, 1);
+            p.overflow_list[o] = q;
+        }
+        return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
+    for (int c = warp; c < cnt; c += 8) {
+        const int j = p.coll_idx[static_cast<int64_t>(slot) * COLLECT_CAP + c];
+        const TX *xr = x + static_cast<int64_t>(j) * p.ld_x;
+        double a0 = 0.0;
+        for (int e = lane; e < p.dim; e += 32) {
+            const double d0 = static_cast<double>(qr[e]) - static_cast<double>(xr[e]);
+            a0 = fma(d0, d0, a0);
+        }
+        a0 = warp_sum(a0);
+        if (lane == 0) { d2[c] = a0; idx[c] = j; }
+    }
+    if (threadIdx.x == 0) { last_d_s = -1.0; last_i_s = -1; }
+    __syncthreads();
+    for (int r = 0; r < p.kk; r++) {
+        const double ld = last_d_s;
+        const int li = last_i_s;
+        double bd = DBL_MAX;
+        int bi = 0x7fffffff;
+        for (int c = threadIdx.x; c < cnt; c += blockDim.x) {
+            const double d = d2[c];
+            const int j = idx[c];
+            const bool after = (d > ld) || (d == ld && j > li);
+            if (after && (d < bd || (d == bd && j < bi))) { bd = d; bi = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        __syncthreads();
+        if (lane == 0) { sd[warp] = bd; si[warp] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; w++)
+                if (sd[w] < bd || (sd[w] == bd && si[w] < bi)) { bd = sd[w]; bi = si[w]; }
+            last_d_s = bd;
+            last_i_s = bi;
+            p.out_idx[static_cast<int64_t>(q) * p.kk + r] = static_cast<int32_t>(p.index_base + bi);
+            p.out_dist[static_cast<int64_t>(q) * p.kk + r] = (p.flags & 1u) ? bd : sqrt(bd);
+        }
+        __syncthreads();
+    }
+}
+
+// gather BF16 query rows of the uncertified queries into a compact matrix for the collection pass
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const __nv_bfloat16 *__restrict__ src, const int *__restrict__ list, int nsel, int kp, __nv_bfloat16 *__restrict__ dst) {
+    const int vec_per_row = kp >> 3;   // kp is a multiple of 8: 16-byte chunks
+    const int64_t total = static_cast<int64_t>(nsel) * vec_per_row;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / vec_per_row), c = static_cast<int>(i % vec_per_row);
+        reinterpret_cast<uint4 *>(dst + static_cast<int64_t>(r) * kp)[c] =
+            reinterpret_cast<const uint4 *>(src + static_cast<int64_t>(list[r]) * kp)[c];
     }
 }
 

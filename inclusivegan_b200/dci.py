@@ -46,7 +46,8 @@ class B200KNNError(RuntimeError):
 class Stats(ctypes.Structure):
     _fields_ = [("kernel_launches", ctypes.c_int64), ("queries", ctypes.c_int64), ("uncertified", ctypes.c_int64),
                 ("ms_convert", ctypes.c_double), ("ms_distance", ctypes.c_double), ("ms_rerank", ctypes.c_double),
-                ("ms_scan", ctypes.c_double), ("distance_launches", ctypes.c_int64), ("distance_flops", ctypes.c_double)]
+                ("ms_scan", ctypes.c_double), ("distance_launches", ctypes.c_int64), ("distance_flops", ctypes.c_double),
+                ("exact_scanned", ctypes.c_int64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

@@ -31,8 +31,8 @@ def run(N, Q, d, k, dtype=np.float64, kind="gauss", seed=0, paths=("scan", "tens
             out.append("%s: EXC %s: %s" % (path, type(e).__name__, e))
             break
     st = db.stats()
-    print("N=%d Q=%d d=%d k=%d %s %s | add %.3fs oracle %.2fs | uncert=%d launches=%d" % (
-        N, Q, d, k, np.dtype(dtype).name, kind, t_add, t_or, st["uncertified"], st["kernel_launches"]))
+    print("N=%d Q=%d d=%d k=%d %s %s | add %.3fs oracle %.2fs | uncert=%d scanned=%d launches=%d" % (
+        N, Q, d, k, np.dtype(dtype).name, kind, t_add, t_or, st["uncertified"], st["exact_scanned"], st["kernel_launches"]))
     for o in out: print("    " + o)
     sys.stdout.flush()
 
@@ -50,3 +50,5 @@ if __name__ == "__main__":
         run(10000, 100, 5000, 10)
         run(300, 20, 64, 40)          # k > 32: segmented sort path
         run(7, 5, 16, 10)             # k > N
+        run(100000, 3000, 3072, 1, dtype=np.float32, paths=("full",))
+        run(50000, 5000, 2048, 4, dtype=np.float32, kind="image", paths=("full",))
