@@ -54,54 +54,63 @@ def load_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe), through NVML
+    (the library nvidia-smi itself reads) from a thread, every 10 ms; mark() delimits the timed region."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
-        self.path = None
+        self.rows = []
+        self.stop_flag = False
+        self.thread = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.fh = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=self.fh, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.gpu]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        try:
+                            rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.rows.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                          pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0, int(rs)))
+                    except Exception:
+                        pass
+                    time.sleep(0.01)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        if self.thread is None:
             return out
-        try:
-            self.proc.terminate()
-            self.proc.wait(timeout=5)
-            self.fh.close()
-            sm, mx, reasons, power = [], [], set(), []
-            with open(self.path) as fh:
-                for line in fh:
-                    f = [t.strip() for t in line.split(",")]
-                    if len(f) < 9:
-                        continue
-                    try:
-                        sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
-                    except ValueError:
-                        continue
-                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                        if val.lower().startswith("active"):
-                            reasons.add(name)
-            os.unlink(self.path)
-            if sm:
-                # median over samples under load (power above idle)
-                load = [s for s, p in zip(sm, power) if p > 300.0] or sm
-                out = {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
-                       "power_w_max": max(power)}
-        except Exception:
-            pass
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        rows = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or 1e300)] or self.rows
+        if rows:
+            mask = 0
+            for r in rows:
+                mask |= r[3]
+            out = {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": self.max_mhz,
+                   "reasons": [n for n, b in self.REASONS if mask & b], "samples": len(rows),
+                   "power_w_median": float(np.median([r[2] for r in rows])), "power_w_max": float(max(r[2] for r in rows))}
         return out
 
 
@@ -257,14 +266,16 @@ def run_b200(args):
         return float(ms.item())
 
     # ---- device-resident arm ------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step_device()
     ix.reset_stats()
     ix.set_profiling(True)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     total_ms = timed(step_device, args.steps)
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     st = ix.stats()
     ix.set_profiling(False)

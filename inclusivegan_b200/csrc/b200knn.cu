@@ -13,6 +13,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include <cub/device/device_segmented_radix_sort.cuh>
@@ -123,7 +124,7 @@ struct Shard {
     CUtensorMap tmap_x;              // pool, 256-row box (1-CTA kernel)
     CUtensorMap tmap_x128;           // pool, 128-row box (each CTA of a pair stages half of the 256-row tile)
     int forced_cg = 0;               // $B200KNN_CTA_GROUP=1|2 pins the kernel flavour (A/B measurements)
-    unsigned opt_flags = 4;          // $B200KNN_OPT: kernel tuning switches (see DistParams::opt)
+    unsigned opt_flags = 0;          // $B200KNN_OPT: kernel tuning switches (see DistParams::opt)
     int a_budget_mb = 64;            // $B200KNN_A_BUDGET_MB: L2 budget for the query tiles of one round
     int sync_tiles = 16;             // $B200KNN_SYNC_TILES: lockstep interval of the workers sharing a pool-tile stream
     int max_pairs = 74;              // CTA pairs that can be co-resident (cudaOccupancyMaxActiveClusters)
@@ -319,7 +320,7 @@ struct Shard {
     // in L2 for the whole round while `rc` pool-tile streams pass through once, each shared by `gs` workers that run
     // in lockstep: HBM traffic per round is ~ one pass over the pool instead of one per worker.
     struct Sched {
-        int cg, qt, nt, workers, nrounds, max_slots, grid;
+        int cg, qt, nt, workers, nrounds, max_slots, grid, qg;
         std::vector<WorkItem> items;        // [nrounds][workers]
         std::vector<int> slots_per_qtile;   // [qt]
     };
@@ -341,6 +342,7 @@ struct Shard {
             const double util = static_cast<double>(g) * rc / W;
             if (util >= best_util - 1e-12) { best_util = util; qg = g; }   // ties -> larger group (fewer rounds)
         }
+        s.qg = qg;
         s.items.clear();
         s.slots_per_qtile.assign(s.qt, 0);
         s.nrounds = 0;
@@ -917,26 +919,42 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
         // ---- single device: double-buffered pipeline, the upload of chunk i+1 overlaps the compute of chunk i ----
         Shard &s = ix->shards[0];
         CU_TRY(cudaSetDevice(s.device));
-        int64_t chunk = QUERY_CHUNK;
-        if (nq >= 8192) chunk = std::min<int64_t>(QUERY_CHUNK, ((nq + 3) / 4 + BM - 1) / BM * BM);   // ~4 pipeline stages
-        chunk = std::max<int64_t>(BM, std::min<int64_t>(chunk, (512ll << 20) / (static_cast<int64_t>(dim) * esz) / BM * BM));
-        const int64_t nchunks = (nq + chunk - 1) / chunk;
-        TRY(s.q_stage.ensure(static_cast<size_t>(std::min(chunk, nq)) * dim * esz));
-        if (nchunks > 1) TRY(s.q_stage2.ensure(static_cast<size_t>(chunk) * dim * esz));
+        // Chunking follows the kernel's schedule: one chunk = one full group of query tiles (a round that keeps every
+        // SM busy); the ragged remainder goes FIRST, so the first upload - the only one nothing can hide - is short.
+        std::vector<std::pair<int64_t, int64_t>> chunks;   // (first row, rows)
+        {
+            Shard::Sched sch;
+            TRY(s.plan(sch, nq, ix->kp, 64));
+            int64_t group_rows = static_cast<int64_t>(sch.qg) * BM * sch.cg;
+            const int64_t cap_rows = std::max<int64_t>(BM * 2, (512ll << 20) / (static_cast<int64_t>(dim) * esz) / (BM * 2) * (BM * 2));
+            group_rows = std::max<int64_t>(BM * 2, std::min(group_rows, cap_rows));
+            if (nq <= group_rows + group_rows / 4) {
+                chunks.emplace_back(0, nq);
+            } else {
+                const int64_t rem = nq % group_rows;
+                int64_t q0 = 0;
+                if (rem > 0) { chunks.emplace_back(0, rem); q0 = rem; }
+                for (; q0 < nq; q0 += group_rows) chunks.emplace_back(q0, std::min(group_rows, nq - q0));
+            }
+        }
+        int64_t max_rows = 0;
+        for (auto &c : chunks) max_rows = std::max(max_rows, c.second);
+        const int64_t nchunks = static_cast<int64_t>(chunks.size());
+        TRY(s.q_stage.ensure(static_cast<size_t>(max_rows) * dim * esz));
+        if (nchunks > 1) TRY(s.q_stage2.ensure(static_cast<size_t>(max_rows) * dim * esz));
         TRY(s.out_idx.ensure(static_cast<size_t>(nq) * kk));
         TRY(s.out_dist.ensure(static_cast<size_t>(nq) * kk));
         unsigned char *stage[2] = {s.q_stage.p, s.q_stage2.p};
         const char *src = static_cast<const char *>(query);
-        TRY(upload(s, stage[0], src, std::min(chunk, nq), s.copy_stream));
+        TRY(upload(s, stage[0], src + static_cast<size_t>(chunks[0].first) * ld * esz, chunks[0].second, s.copy_stream));
         CU_TRY(cudaEventRecord(s.ev_copied[0], s.copy_stream));
         for (int64_t c = 0; c < nchunks; c++) {
             const int b = static_cast<int>(c & 1);
-            const int64_t q0 = c * chunk, cq = std::min(chunk, nq - q0);
+            const int64_t q0 = chunks[c].first, cq = chunks[c].second;
             if (c + 1 < nchunks) {
                 const int nb = b ^ 1;
-                const int64_t q1 = (c + 1) * chunk, cq1 = std::min(chunk, nq - q1);
                 if (c >= 1) CU_TRY(cudaStreamWaitEvent(s.copy_stream, s.ev_consumed[nb], 0));   // chunk c-1 is done with that buffer
-                TRY(upload(s, stage[nb], src + static_cast<size_t>(q1) * ld * esz, cq1, s.copy_stream));
+                TRY(upload(s, stage[nb], src + static_cast<size_t>(chunks[c + 1].first) * ld * esz, chunks[c + 1].second, s.copy_stream));
                 CU_TRY(cudaEventRecord(s.ev_copied[nb], s.copy_stream));
             }
             CU_TRY(cudaStreamWaitEvent(s.stream, s.ev_copied[b], 0));

@@ -168,8 +168,7 @@ struct DistParams {
     int *coll_count;         // [nq] running count (may exceed coll_cap: overflow)
     int *coll_idx;           // [nq][coll_cap]
     int coll_cap;
-    unsigned opt;            // tuning switches (A/B measurements): bit0 early barrier probe, bit1 double-buffered TMEM loads,
-                             // bit2 grid barrier between rounds
+    unsigned opt;            // tuning switches (A/B measurements): bit2 grid barrier between rounds
 };
 
 __device__ __forceinline__ WorkItem load_item(const DistParams &p, int round, int worker) {
@@ -209,7 +208,8 @@ struct DistCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2 * BN * 4 + 256;
+    static constexpr int SCRATCH_BYTES = 32 * 128 * 4;            // epilogue: one 32-score slab per thread (rare path)
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2 * BN * 4 + 256 + SCRATCH_BYTES;
 };
 
 template <int C, bool COLLECT, int CG>
@@ -230,6 +230,7 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t bar_tfull = bars + 16 * NSTAGE;        // [2]       MMA -> epilogue (one per CTA)
     const uint32_t bar_tempty = bars + 16 * NSTAGE + 16;  // [2]       epilogue -> MMA (the leader's copy is used)
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + NSTAGE * Cfg::STAGE_BYTES + 2 * BN * 4 + 16 * NSTAGE + 32);
+    float *scratch = reinterpret_cast<float *>(gen + NSTAGE * Cfg::STAGE_BYTES + 2 * BN * 4 + 256);   // [32][128]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -316,15 +317,13 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // ===================== MMA issuer (leader CTA only) =====================
         // The whole warp runs the loop converged (uniform control flow, uniform registers); one elected lane issues.
         // The issuing thread is on the critical path: per K block it must spend less than the 512 tensor cycles the
-        // four MMAs take, so the probe of the NEXT stage's barrier is issued before the current MMAs and its
-        // latency overlaps their issue.
+        // four MMAs take.
         if (leader) {
             constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            bool ready = false;     // result of the early probe of full[stage]
             for (int round = 0; round < p.nrounds; round++) {
                 const WorkItem w = load_item(p, round, worker);
                 if (w.qtile < 0) continue;
@@ -333,11 +332,10 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + acc * BN;
                     for (int kb = 0; kb < p.num_kb; kb++) {
-                        if (!ready) mbar_wait(bar_full + 8 * stage, phase);   // TMA bytes (of both CTAs) have landed
+                        mbar_wait(bar_full + 8 * stage, phase);               // TMA bytes (of both CTAs) have landed
                         tc_fence_after();
                         const uint32_t cur = stage;
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                        ready = (p.opt & 1u) ? mbar_test_wait(bar_full + 8 * stage, phase) : false;   // early, non-blocking probe of the next stage
                         if (elect_one()) {
                             const uint64_t da = make_smem_desc_sw128(smem_a + cur * Cfg::A_BYTES);
                             const uint64_t db = make_smem_desc_sw128(smem_b + cur * Cfg::B_BYTES);
@@ -395,40 +393,43 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-                // TMEM -> registers in 32-column slabs, double-buffered: the load of slab c+1 is in flight while
-                // slab c is scored and filtered
-                auto consume = [&](const uint32_t (&r)[32], int c) {
+                // TMEM -> registers in 32-column slabs.  Hot path per score: FFMA + compare + predicated OR into a hit
+                // mask (no branches, compact code: the issuing warps share the SM's instruction cache with this loop).
+                // Slabs with hits park their 32 scores in shared memory and replay only the hit positions through ONE
+                // copy of the sorted-insert code.
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c++) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + c * 32, r);
+                    tmem_ld_wait();
+                    if constexpr (COLLECT) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float s = fmaf(-2.f, __uint_as_float(r[j]), xs[c * 32 + j]);
-                        if constexpr (COLLECT) {
-                            if (s <= thr) {
+                        for (int j = 0; j < 32; j++) {
+                            const float sc = fmaf(-2.f, __uint_as_float(r[j]), xs[c * 32 + j]);
+                            if (sc <= thr) {
                                 const int pos = atomicAdd(p.coll_count + q, 1);
                                 if (pos < p.coll_cap) p.coll_idx[static_cast<int64_t>(q) * p.coll_cap + pos] = n0 + c * 32 + j;
                             }
-                        } else {
-                            if (s < v[C - 1]) topc_insert<C>(v, id, s, n0 + c * 32 + j);
                         }
-                    }
-                };
-                uint32_t ra[32], rb[32];
-                if (p.opt & 2u) {
-                    tmem_ld_32x32(taddr, ra);
-#pragma unroll 1
-                    for (int c = 0; c < BN / 32; c += 2) {
-                        tmem_ld_wait();
-                        tmem_ld_32x32(taddr + (c + 1) * 32, rb);
-                        consume(ra, c);
-                        tmem_ld_wait();
-                        if (c + 2 < BN / 32) tmem_ld_32x32(taddr + (c + 2) * 32, ra);
-                        consume(rb, c + 1);
-                    }
-                } else {
-#pragma unroll 1
-                    for (int c = 0; c < BN / 32; c++) {
-                        tmem_ld_32x32(taddr + c * 32, ra);
-                        tmem_ld_wait();
-                        consume(ra, c);
+                    } else {
+                        const float worst = v[C - 1];
+                        uint32_t hits = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float sc = fmaf(-2.f, __uint_as_float(r[j]), xs[c * 32 + j]);
+                            r[j] = __float_as_uint(sc);
+                            hits |= (sc < worst) ? (1u << j) : 0u;
+                        }
+                        if (hits) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) scratch[j * 128 + et] = __uint_as_float(r[j]);
+                            do {
+                                const int j = __ffs(hits) - 1;
+                                hits &= hits - 1;
+                                const float sc = scratch[j * 128 + et];
+                                if (sc < v[C - 1]) topc_insert<C>(v, id, sc, n0 + c * 32 + j);
+                            } while (hits);
+                        }
                     }
                 }
                 tc_fence_before();

@@ -20,12 +20,8 @@ if len(sys.argv) > 1:      # single config for ncu
     run(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), reps=1)
 else:
     calibrate()
-    for rep in range(2):
-        for opt in (4, 5, 6, 7, 0):
-            run(2, 64, 16, opt=opt)
-        for sync in (8, 32, 64):
-            run(2, 64, sync)
-        for b in (50, 64, 80):
-            run(2, b, 16)
+    for rep in range(3):
+        run(2, 64, 16, opt=4)
+        run(2, 64, 16, opt=0)
         run(1, 60, 16)
     calibrate()
