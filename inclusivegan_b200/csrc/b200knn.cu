@@ -477,14 +477,17 @@ struct Shard {
     int launch_rerank(const void *d_query, int q_dtype, int64_t nq, const RerankParams &rp) {
         prof_begin(K_RERANK);
         const unsigned g = static_cast<unsigned>(nq);
+        int pk = 1;
+        while (pk < rp.max_slots * C) pk <<= 1;
+        const size_t sm = static_cast<size_t>(pk) * sizeof(unsigned long long);
         if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
-            rerank_kernel<double, double, C><<<g, 128, 0, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), rp);
+            rerank_kernel<double, double, C><<<g, 128, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), rp);
         else if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
-            rerank_kernel<double, float, C><<<g, 128, 0, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), rp);
+            rerank_kernel<double, float, C><<<g, 128, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), rp);
         else if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
-            rerank_kernel<float, double, C><<<g, 128, 0, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), rp);
+            rerank_kernel<float, double, C><<<g, 128, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), rp);
         else
-            rerank_kernel<float, float, C><<<g, 128, 0, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), rp);
+            rerank_kernel<float, float, C><<<g, 128, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), rp);
         prof_end();
         CU_TRY(cudaGetLastError());
         return B200KNN_OK;

@@ -281,7 +281,13 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         if (p.sync_tiles > 0 && sharers > 1 && (CG == 1 || leader) && t > w.t0 && (t - w.t0) % p.sync_tiles == 0) {
                             const unsigned int target = static_cast<unsigned int>((t - w.t0) / p.sync_tiles) * sharers;
                             atomicAdd(sync, 1u);
-                            while (*reinterpret_cast<volatile unsigned int *>(sync) < target) __nanosleep(128);
+                            // bounded: if a sharer is not resident (a foreign kernel holds its SM) we go on alone after
+                            // ~2 tile times — only L2 sharing is lost, never progress
+                            const uint64_t t_start = global_timer_ns();
+                            while (*reinterpret_cast<volatile unsigned int *>(sync) < target) {
+                                __nanosleep(128);
+                                if (global_timer_ns() - t_start > 40000ull) break;
+                            }
                         }
                         const int n0 = t * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS;
                         for (int kb = 0; kb < p.num_kb; kb++) {
@@ -309,7 +315,11 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     __threadfence();
                     atomicAdd(p.round_counter, 1u);
                     const unsigned int target = static_cast<unsigned int>(round + 1) * gridDim.x;
-                    while (*reinterpret_cast<volatile unsigned int *>(p.round_counter) < target) __nanosleep(256);
+                    const uint64_t t_start = global_timer_ns();
+                    while (*reinterpret_cast<volatile unsigned int *>(p.round_counter) < target) {
+                        __nanosleep(256);
+                        if (global_timer_ns() - t_start > 2000000ull) break;   // bounded (2 ms): never a deadlock
+                    }
                 }
             }
         }
@@ -529,7 +539,7 @@ __device__ __forceinline__ ErrModel make_err_model(const RerankParams &p, int q)
 template <typename TX, typename TQ, int C>
 __global__ void __launch_bounds__(128)
 rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const RerankParams p) {
-    __shared__ unsigned long long keys[MAX_KEYS];
+    extern __shared__ unsigned long long keys[];   // next_pow2(max_slots * C) entries (host-sized, <= MAX_KEYS)
     __shared__ double d2s[C];
     __shared__ int m_s;
     const int q = blockIdx.x;
@@ -578,19 +588,48 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
     }
     __syncthreads();
     const int m = m_s;
-    // exact float64 distances of the surviving candidates (the arithmetic of util.c:62-69, pairwise-summed)
+    // exact float64 distances of the surviving candidates (the arithmetic of util.c:62-69, tree-summed).  The whole
+    // block works on one candidate at a time: every thread owns a strided slice of the dimensions, keeps its slice
+    // of the query row in registers across candidates, and issues its loads of the pool row back to back.
     const int warp = tid >> 5, lane = tid & 31;
     const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
-    for (int c = warp; c < C; c += 4) {
+    constexpr int RQ = 24;                      // dims per thread held in registers (128 threads x 24 = 3072)
+    __shared__ double partial[4];
+    double qreg[RQ];
+    const bool fits = p.dim <= RQ * 128;
+    if (fits) {
+#pragma unroll
+        for (int i = 0; i < RQ; i++) {
+            const int e = tid + i * 128;
+            qreg[i] = (e < p.dim) ? static_cast<double>(qr[e]) : 0.0;
+        }
+    }
+    for (int c = 0; c < C; c++) {
         const unsigned long long key = keys[c];
-        double acc = DBL_MAX;
-        if (c < m && key != ~0ull) {
-            const TX *xr = x + static_cast<int64_t>(static_cast<uint32_t>(key)) * p.ld_x;
-            double a0 = 0.0, a1 = 0.0;
-            int e = lane;
-            for (; e + 32 < p.dim; e += 64) {
+        if (c >= m || key == ~0ull) {           // uniform across the block
+            if (tid == 0) d2s[c] = DBL_MAX;
+            continue;
+        }
+        const TX *xr = x + static_cast<int64_t>(static_cast<uint32_t>(key)) * p.ld_x;
+        double a0 = 0.0, a1 = 0.0;
+        if (fits) {
+            double xv[RQ];
+#pragma unroll
+            for (int i = 0; i < RQ; i++) {
+                const int e = tid + i * 128;
+                xv[i] = (e < p.dim) ? static_cast<double>(xr[e]) : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < RQ; i += 2) {
+                const double d0 = qreg[i] - xv[i], d1 = qreg[i + 1] - xv[i + 1];
+                a0 = fma(d0, d0, a0);
+                a1 = fma(d1, d1, a1);
+            }
+        } else {
+            int e = tid;
+            for (; e + 128 < p.dim; e += 256) {
                 const double d0 = static_cast<double>(qr[e]) - static_cast<double>(xr[e]);
-                const double d1 = static_cast<double>(qr[e + 32]) - static_cast<double>(xr[e + 32]);
+                const double d1 = static_cast<double>(qr[e + 128]) - static_cast<double>(xr[e + 128]);
                 a0 = fma(d0, d0, a0);
                 a1 = fma(d1, d1, a1);
             }
@@ -598,9 +637,12 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
                 const double d0 = static_cast<double>(qr[e]) - static_cast<double>(xr[e]);
                 a0 = fma(d0, d0, a0);
             }
-            acc = warp_sum(a0 + a1);
         }
-        if (lane == 0) d2s[c] = acc;
+        const double w = warp_sum(a0 + a1);
+        if (lane == 0) partial[warp] = w;
+        __syncthreads();
+        if (tid == 0) d2s[c] = (partial[0] + partial[1]) + (partial[2] + partial[3]);
+        __syncthreads();
     }
     __syncthreads();
     if (warp == 0) {
