@@ -20,7 +20,7 @@ HEADERS = ["kernels.cuh", "ptx.cuh", os.path.join(_ROOT, "include", "b200knn.h")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-std=c++17", "-O3", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared",
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr",
 ]

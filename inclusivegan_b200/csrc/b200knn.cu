@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -147,6 +149,14 @@ struct Shard {
     DevBuf<unsigned char> q_stage;   // host API: device copy of the caller's query rows
     DevBuf<unsigned char> q_stage2;  // second buffer: the upload of chunk i+1 overlaps the compute of chunk i
     cudaStream_t copy_stream = nullptr;
+    // pageable host sources are staged through a ring of pinned buffers filled by several host threads
+    static constexpr int RING = 3;
+    static constexpr size_t RING_BYTES = 32u << 20;
+    unsigned char *ring[RING] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ring_done[RING] = {nullptr, nullptr, nullptr};
+    bool ring_used[RING] = {false, false, false};
+    int ring_next = 0;
+    int copy_threads = 8;            // $B200KNN_COPY_THREADS
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     DevBuf<int32_t> out_idx;
     DevBuf<double> out_dist;
@@ -191,6 +201,8 @@ struct Shard {
         if (const char *o = getenv("B200KNN_OPT")) opt_flags = static_cast<unsigned>(atoi(o));
         if (const char *o = getenv("B200KNN_A_BUDGET_MB")) a_budget_mb = std::max(1, atoi(o));
         if (const char *o = getenv("B200KNN_SYNC_TILES")) sync_tiles = std::max(0, atoi(o));
+        if (const char *o = getenv("B200KNN_COPY_THREADS")) copy_threads = std::max(1, atoi(o));
+        copy_threads = std::min<int>(copy_threads, std::max(1u, std::thread::hardware_concurrency()));
         const char *e = getenv("B200KNN_CTA_GROUP");
         if (e && (e[0] == '1' || e[0] == '2')) forced_cg = e[0] - '0';
         // a persistent, statically-strided grid must be fully co-resident: ask how many CTA pairs fit at once
@@ -268,11 +280,77 @@ struct Shard {
         if (h_count) cudaFreeHost(h_count);
         if (own_stream) cudaStreamDestroy(own_stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        for (int i = 0; i < RING; i++) {
+            if (ring[i]) cudaFreeHost(ring[i]);
+            if (ring_done[i]) cudaEventDestroy(ring_done[i]);
+            ring[i] = nullptr;
+            ring_done[i] = nullptr;
+        }
         for (int i = 0; i < 2; i++) {
             if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
             if (ev_consumed[i]) cudaEventDestroy(ev_consumed[i]);
         }
         ready = false;
+    }
+
+    // ------------------------------------------------------------------ host -> device rows
+    // rows x row_bytes, source pitch src_pitch, destination packed.  Pinned / registered sources are DMA'd directly.
+    // Pageable sources (what NumPy hands over) go through the pinned ring: several host threads memcpy a 32 MB piece
+    // into a ring slot, the slot is DMA'd asynchronously, and the next piece is being filled meanwhile.
+    int upload_rows(void *dst, const char *src, int64_t rows, size_t row_bytes, size_t src_pitch, cudaStream_t st) {
+        if (rows <= 0) return B200KNN_OK;
+        cudaPointerAttributes attr;
+        bool pinned = false;
+        if (cudaPointerGetAttributes(&attr, src) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+        else cudaGetLastError();
+        const size_t total = static_cast<size_t>(rows) * row_bytes;
+        if (pinned || total <= (1u << 20)) {
+            if (src_pitch == row_bytes) CU_TRY(cudaMemcpyAsync(dst, src, total, cudaMemcpyHostToDevice, st));
+            else CU_TRY(cudaMemcpy2DAsync(dst, row_bytes, src, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, st));
+            return B200KNN_OK;
+        }
+        for (int i = 0; i < RING; i++) {
+            if (!ring[i]) {
+                CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&ring[i]), RING_BYTES));
+                CU_TRY(cudaEventCreateWithFlags(&ring_done[i], cudaEventDisableTiming));
+            }
+        }
+        const int64_t piece_rows = std::max<int64_t>(1, static_cast<int64_t>(RING_BYTES / row_bytes));
+        if (row_bytes > RING_BYTES) {   // absurdly wide rows: let the driver stage them
+            CU_TRY(cudaMemcpy2DAsync(dst, row_bytes, src, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, st));
+            return B200KNN_OK;
+        }
+        for (int64_t r0 = 0; r0 < rows; r0 += piece_rows) {
+            const int64_t pr = std::min(piece_rows, rows - r0);
+            const int slot = ring_next;
+            ring_next = (ring_next + 1) % RING;
+            if (ring_used[slot]) CU_TRY(cudaEventSynchronize(ring_done[slot]));   // its previous DMA has drained
+            unsigned char *buf = ring[slot];
+            const char *sp = src + static_cast<size_t>(r0) * src_pitch;
+            const int nt = static_cast<int>(std::min<int64_t>(copy_threads, std::max<int64_t>(1, pr)));
+            auto work = [&](int t) {
+                const int64_t a = pr * t / nt, b = pr * (t + 1) / nt;
+                if (src_pitch == row_bytes) {
+                    std::memcpy(buf + static_cast<size_t>(a) * row_bytes, sp + static_cast<size_t>(a) * src_pitch, static_cast<size_t>(b - a) * row_bytes);
+                } else {
+                    for (int64_t r = a; r < b; r++) std::memcpy(buf + static_cast<size_t>(r) * row_bytes, sp + static_cast<size_t>(r) * src_pitch, row_bytes);
+                }
+            };
+            if (nt == 1) {
+                work(0);
+            } else {
+                std::vector<std::thread> th;
+                th.reserve(nt - 1);
+                for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+                work(0);
+                for (auto &x : th) x.join();
+            }
+            CU_TRY(cudaMemcpyAsync(static_cast<char *>(dst) + static_cast<size_t>(r0) * row_bytes, buf, static_cast<size_t>(pr) * row_bytes,
+                                   cudaMemcpyHostToDevice, st));
+            CU_TRY(cudaEventRecord(ring_done[slot], st));
+            ring_used[slot] = true;
+        }
+        return B200KNN_OK;
     }
 
     // ------------------------------------------------------------------ kernels: convert
@@ -856,8 +934,7 @@ int b200knn_add(b200knn_index *ix, const void *data, int dtype, int64_t n, int64
         for (int64_t b0 = 0; b0 < rows; b0 += block_rows) {
             const int64_t br = std::min(block_rows, rows - b0);
             char *dst = static_cast<char *>(d_rows) + static_cast<size_t>(b0) * ix->dim * esz;
-            CU_TRY(cudaMemcpy2DAsync(dst, ix->dim * esz, src + static_cast<size_t>(b0) * ld * esz, ld * esz, ix->dim * esz, br,
-                                     cudaMemcpyHostToDevice, s.stream));
+            TRY(s.upload_rows(dst, src + static_cast<size_t>(b0) * ld * esz, br, ix->dim * esz, ld * esz, s.stream));
             TRY(s.launch_convert(dst, dtype, br, ix->dim, ix->dim, ix->kp, s.x_bf.p + static_cast<size_t>(b0) * ix->kp,
                                  s.xnorm_bf.p + b0, s.x_err.p + b0, s.scalars.p));
         }
@@ -914,9 +991,7 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
     const int G = static_cast<int>(ix->shards.size());
     const int dim = ix->dim;
     auto upload = [&](Shard &s, void *dst, const char *src, int64_t rows, cudaStream_t st) -> int {
-        if (ld == dim) CU_TRY(cudaMemcpyAsync(dst, src, static_cast<size_t>(rows) * dim * esz, cudaMemcpyHostToDevice, st));
-        else CU_TRY(cudaMemcpy2DAsync(dst, dim * esz, src, ld * esz, dim * esz, rows, cudaMemcpyHostToDevice, st));
-        return B200KNN_OK;
+        return s.upload_rows(dst, src, rows, static_cast<size_t>(dim) * esz, static_cast<size_t>(ld) * esz, st);
     };
     if (G == 1) {
         // ---- single device: double-buffered pipeline, the upload of chunk i+1 overlaps the compute of chunk i ----
@@ -949,21 +1024,46 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
         TRY(s.out_dist.ensure(static_cast<size_t>(nq) * kk));
         unsigned char *stage[2] = {s.q_stage.p, s.q_stage2.p};
         const char *src = static_cast<const char *>(query);
-        TRY(upload(s, stage[0], src + static_cast<size_t>(chunks[0].first) * ld * esz, chunks[0].second, s.copy_stream));
-        CU_TRY(cudaEventRecord(s.ev_copied[0], s.copy_stream));
-        for (int64_t c = 0; c < nchunks; c++) {
+        // The uploads run on their own host thread (a pageable source keeps that thread busy with memcpy) and their
+        // own stream; this thread enqueues the compute.  uploaded / consumed count chunks; the CUDA events order the
+        // streams, the counters order the host threads.
+        std::atomic<int64_t> uploaded{0}, consumed{0};
+        std::atomic<int> up_rc{B200KNN_OK};
+        std::string up_err;
+        std::thread uploader([&]() {
+            cudaSetDevice(s.device);
+            for (int64_t c = 0; c < nchunks; c++) {
+                const int b = static_cast<int>(c & 1);
+                if (c >= 2) {
+                    while (consumed.load(std::memory_order_acquire) < c - 1) std::this_thread::yield();   // chunk c-2 enqueued
+                    cudaStreamWaitEvent(s.copy_stream, s.ev_consumed[b], 0);
+                }
+                int rc = upload(s, stage[b], src + static_cast<size_t>(chunks[c].first) * ld * esz, chunks[c].second, s.copy_stream);
+                if (rc == B200KNN_OK && cudaEventRecord(s.ev_copied[b], s.copy_stream) != cudaSuccess) rc = B200KNN_ECUDA;
+                if (rc != B200KNN_OK) {
+                    up_err = g_last_error;      // thread-local in the uploader: hand it over
+                    up_rc.store(rc);
+                    uploaded.store(nchunks, std::memory_order_release);
+                    return;
+                }
+                uploaded.store(c + 1, std::memory_order_release);
+            }
+        });
+        int rc_main = B200KNN_OK;
+        for (int64_t c = 0; c < nchunks && rc_main == B200KNN_OK; c++) {
             const int b = static_cast<int>(c & 1);
             const int64_t q0 = chunks[c].first, cq = chunks[c].second;
-            if (c + 1 < nchunks) {
-                const int nb = b ^ 1;
-                if (c >= 1) CU_TRY(cudaStreamWaitEvent(s.copy_stream, s.ev_consumed[nb], 0));   // chunk c-1 is done with that buffer
-                TRY(upload(s, stage[nb], src + static_cast<size_t>(chunks[c + 1].first) * ld * esz, chunks[c + 1].second, s.copy_stream));
-                CU_TRY(cudaEventRecord(s.ev_copied[nb], s.copy_stream));
-            }
-            CU_TRY(cudaStreamWaitEvent(s.stream, s.ev_copied[b], 0));
-            TRY(s.query_device(stage[b], dtype, cq, dim, dim, ix->kp, k, flags, s.out_idx.p + q0 * kk, s.out_dist.p + q0 * kk));
-            CU_TRY(cudaEventRecord(s.ev_consumed[b], s.stream));
+            while (uploaded.load(std::memory_order_acquire) < c + 1) std::this_thread::yield();
+            if (up_rc.load() != B200KNN_OK) break;
+            if (cudaStreamWaitEvent(s.stream, s.ev_copied[b], 0) != cudaSuccess) { rc_main = fail(B200KNN_ECUDA, "cudaStreamWaitEvent failed"); break; }
+            rc_main = s.query_device(stage[b], dtype, cq, dim, dim, ix->kp, k, flags, s.out_idx.p + q0 * kk, s.out_dist.p + q0 * kk);
+            if (rc_main == B200KNN_OK && cudaEventRecord(s.ev_consumed[b], s.stream) != cudaSuccess) rc_main = fail(B200KNN_ECUDA, "cudaEventRecord failed");
+            consumed.store(c + 1, std::memory_order_release);
         }
+        consumed.store(nchunks + 2, std::memory_order_release);   // never leave the uploader waiting
+        uploader.join();
+        if (up_rc.load() != B200KNN_OK) return fail(up_rc.load(), "%s", up_err.c_str());
+        if (rc_main != B200KNN_OK) return rc_main;
         CU_TRY(cudaMemcpyAsync(out_idx, s.out_idx.p, static_cast<size_t>(nq) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         CU_TRY(cudaMemcpyAsync(out_dist, s.out_dist.p, static_cast<size_t>(nq) * kk * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         CU_TRY(cudaStreamSynchronize(s.stream));
