@@ -95,6 +95,14 @@ int b200knn_add(b200knn_index *index, const void *data, int dtype, int64_t n, in
 int b200knn_query(b200knn_index *index, const void *query, int dtype, int64_t nq, int64_t ld, int k,
                   unsigned flags, int32_t *out_idx, double *out_dist, int *out_kk);
 
+/* Ball membership for the k-NN precision/recall metric (reference metrics/precision_recall.py:96-134, the
+ * `np.any(distance_batch[..., None] <= self.D, axis=1)` test): out_member[i] = 1 iff query row i lies inside at least
+ * one ball B(x_j, sqrt(radius2[j])) around a pool row (squared Euclidean distance <= radius2[j]; the reference works on
+ * squared distances, precision_recall.py:32).  radius2: HOST float64 [num_points], indexed like the rows passed to
+ * add().  Exact (float64 decision); the reference decides in float16.  out_member: HOST uint8 [nq]. */
+int b200knn_ball_membership(b200knn_index *index, const void *query, int dtype, int64_t nq, int64_t ld, const double *radius2,
+                            unsigned char *out_member);
+
 /* ---- device-buffer entry points (inputs already resident in HBM; single-device handles) ---- */
 
 /* Launch all work of this handle on `stream` (a cudaStream_t passed as void*, NULL = the
@@ -140,6 +148,12 @@ typedef struct b200knn_stats {
 int b200knn_set_profiling(b200knn_index *index, int profiling);
 int b200knn_get_stats(b200knn_index *index, b200knn_stats *out);   /* synchronises the handle's stream(s) */
 int b200knn_reset_stats(b200knn_index *index);
+
+/* Test hook: copy out the BF16-pass shortlists of the LAST tensor pass of a single-device handle (the last query
+ * chunk): scores[nq][slots][C] (s~ = ||x~||^2 - 2 q~.x~ as computed on the tensor cores) and rows[nq][slots][C]
+ * (shard-local pool row, -1 = empty).  *nq, *slots, *c receive the geometry; the HOST buffers must hold `capacity`
+ * entries each (B200KNN_EINVAL if too small).  Used by the tests that validate the certificate's error model. */
+int b200knn_debug_shortlists(b200knn_index *index, float *scores, int32_t *rows, int64_t capacity, int64_t *nq, int *slots, int *c);
 
 /* Thread-local message for the last failing call on this thread ("" if none). */
 const char *b200knn_last_error(void);

@@ -138,6 +138,9 @@ struct Shard {
     DevBuf<float> uncert_thr;
     DevBuf<int> coll_count, coll_idx, overflow_list;
     DevBuf<WorkItem> sched_items;
+    DevBuf<double> radius2;          // ball membership: squared radii of this shard's rows
+    DevBuf<float> colterm, rowthr;
+    DevBuf<unsigned char> member;
     DevBuf<unsigned int> stream_sync;
     DevBuf<int> sched_slots;
     DevBuf<float> cand_s;
@@ -161,6 +164,8 @@ struct Shard {
     DevBuf<int32_t> out_idx;
     DevBuf<double> out_dist;
     int *h_count = nullptr;          // pinned
+    int64_t last_nq = 0;             // geometry of the last tensor pass (b200knn_debug_shortlists)
+    int last_slots = 0, last_c = 0;
 
     // ---- stats ----
     b200knn_stats stats{};
@@ -274,7 +279,7 @@ struct Shard {
         if (!ready) return;
         clear_pool();
         drain_events();
-        q_bf.release(); qnorm_bf.release(); q_err.release(); q_bf2.release(); uncert_thr.release(); coll_count.release(); coll_idx.release(); overflow_list.release(); sched_items.release(); sched_slots.release(); stream_sync.release(); cand_s.release(); cand_i.release(); uncert_list.release();
+        q_bf.release(); qnorm_bf.release(); q_err.release(); q_bf2.release(); uncert_thr.release(); coll_count.release(); coll_idx.release(); overflow_list.release(); sched_items.release(); sched_slots.release(); stream_sync.release(); radius2.release(); colterm.release(); rowthr.release(); member.release(); cand_s.release(); cand_i.release(); uncert_list.release();
         scan_d2.release(); scan_d2_sorted.release(); scan_iota.release(); scan_vals_sorted.release(); scan_offsets.release();
         cub_tmp.release(); q_stage.release(); q_stage2.release(); out_idx.release(); out_dist.release(); scalars.release();
         if (h_count) cudaFreeHost(h_count);
@@ -675,6 +680,9 @@ struct Shard {
         prof_end();
         TRY(rc1);
 
+        last_nq = nq;
+        last_slots = s.max_slots;
+        last_c = C;
         TRY(uncert_list.ensure(nq));
         TRY(uncert_thr.ensure(nq));
         RerankParams rp{};
@@ -712,6 +720,108 @@ struct Shard {
             }
         }
         return B200KNN_OK;
+    }
+
+    // ------------------------------------------------------------------ ball membership (precision/recall metric)
+    // d_out[i] |= 1 when query i lies inside any ball B(x_j, sqrt(radius2[j])) of this shard.  radius2 is already in
+    // `radius2` (device).  Tensor-core filter in collect mode + exact float64 decision; overflowed lists without a
+    // witness go to the exact scan.
+    static constexpr int MEMBER_CAP = 256;
+    int ball_membership(const void *d_query, int q_dtype, int64_t nq, int64_t ld_q, int dim, int kp, unsigned char *d_out) {
+        if (nq <= 0 || n <= 0) return B200KNN_OK;
+        CU_TRY(cudaSetDevice(device));
+        stats.queries += nq;
+        TRY(q_bf.ensure(static_cast<size_t>(nq) * kp));
+        TRY(qnorm_bf.ensure(nq));
+        TRY(q_err.ensure(nq));
+        TRY(launch_convert(d_query, q_dtype, nq, ld_q, dim, kp, q_bf.p, qnorm_bf.p, q_err.p, scalars.p + 2));
+        TRY(colterm.ensure(n));
+        TRY(rowthr.ensure(nq));
+        CU_TRY(cudaMemsetAsync(scalars.p + 7, 0, sizeof(unsigned int), stream));
+        prof_begin(K_SCAN);
+        ball_colterm_kernel<<<std::min<int64_t>(num_sms * 4, (n + 255) / 256), 256, 0, stream>>>(xnorm_bf.p, x_err.p, radius2.p, static_cast<int>(n),
+                                                                                          colterm.p, scalars.p + 7);
+        prof_end();
+        prof_begin(K_SCAN);
+        ball_rowthr_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, stream>>>(qnorm_bf.p, q_err.p, scalars.p, scalars.p + 7, kp,
+                                                                                        static_cast<int>(nq), rowthr.p);
+        prof_end();
+        CU_TRY(cudaGetLastError());
+        TRY(coll_count.ensure(nq));
+        TRY(coll_idx.ensure(static_cast<size_t>(nq) * MEMBER_CAP));
+        TRY(overflow_list.ensure(nq));
+        CU_TRY(cudaMemsetAsync(coll_count.p, 0, static_cast<size_t>(nq) * sizeof(int), stream));
+        CU_TRY(cudaMemsetAsync(scalars.p + 5, 0, sizeof(unsigned int), stream));
+        CUtensorMap tmap_q;
+        TRY(make_tmap(&tmap_q, q_bf.p, nq, kp, BM));
+        Sched s;
+        TRY(plan(s, nq, kp, 1 << 20));
+        TRY(upload_schedule(s, false));
+        DistParams dp = base_dist_params(nq, kp, s);
+        dp.xnorm = colterm.p;
+        dp.thr = rowthr.p;
+        dp.coll_count = coll_count.p;
+        dp.coll_idx = coll_idx.p;
+        dp.coll_cap = MEMBER_CAP;
+        prof_begin(K_DISTANCE, 2.0 * static_cast<double>(nq) * static_cast<double>(n) * dim);
+        const int rc = launch_dist<16, true>(s, tmap_q, dp);
+        prof_end();
+        TRY(rc);
+        MemberParams mp{};
+        mp.coll_count = coll_count.p;
+        mp.coll_idx = coll_idx.p;
+        mp.cap = MEMBER_CAP;
+        mp.radius2 = radius2.p;
+        mp.dim = dim;
+        mp.ld_x = ld_x;
+        mp.ld_q = ld_q;
+        mp.out_member = d_out;
+        mp.overflow_count = reinterpret_cast<int *>(scalars.p + 5);
+        mp.overflow_list = overflow_list.p;
+        prof_begin(K_RERANK);
+        const unsigned g = static_cast<unsigned>(nq);
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
+            ball_member_kernel<double, double><<<g, 128, 0, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), mp);
+        else if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
+            ball_member_kernel<double, float><<<g, 128, 0, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), mp);
+        else if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
+            ball_member_kernel<float, double><<<g, 128, 0, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), mp);
+        else
+            ball_member_kernel<float, float><<<g, 128, 0, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), mp);
+        prof_end();
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(h_count, scalars.p + 5, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        const int nov = *h_count;
+        if (nov > 0) {
+            stats.exact_scanned += nov;
+            TRY(scan_members(d_query, q_dtype, ld_q, nov, dim, d_out));
+        }
+        return B200KNN_OK;
+    }
+    template <typename TX, typename TQ>
+    int scan_members_typed(const TQ *d_query, int64_t ld_q, int nsub, int dim, unsigned char *d_out) {
+        const int batch = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min(nsub, 4096), (1536ll << 20) / std::max<int64_t>(n * 8, 1))));
+        TRY(scan_d2.ensure(static_cast<size_t>(batch) * n));
+        for (int s0 = 0; s0 < nsub; s0 += batch) {
+            const int ns = std::min(batch, nsub - s0);
+            dim3 grid(static_cast<unsigned>((n + SCAN_TX - 1) / SCAN_TX), static_cast<unsigned>((ns + SCAN_TQ - 1) / SCAN_TQ));
+            prof_begin(K_SCAN);
+            scan_dist_kernel<TX, TQ><<<grid, 256, 0, stream>>>(static_cast<const TX *>(x_raw), ld_x, static_cast<int>(n), d_query, ld_q,
+                                                               overflow_list.p + s0, ns, dim, scan_d2.p);
+            prof_end();
+            prof_begin(K_SCAN);
+            scan_member_kernel<<<ns, 256, 0, stream>>>(scan_d2.p, static_cast<int>(n), overflow_list.p + s0, radius2.p, d_out);
+            prof_end();
+            CU_TRY(cudaGetLastError());
+        }
+        return B200KNN_OK;
+    }
+    int scan_members(const void *d_query, int q_dtype, int64_t ld_q, int nsub, int dim, unsigned char *d_out) {
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64) return scan_members_typed<double, double>(static_cast<const double *>(d_query), ld_q, nsub, dim, d_out);
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32) return scan_members_typed<double, float>(static_cast<const float *>(d_query), ld_q, nsub, dim, d_out);
+        if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64) return scan_members_typed<float, double>(static_cast<const double *>(d_query), ld_q, nsub, dim, d_out);
+        return scan_members_typed<float, float>(static_cast<const float *>(d_query), ld_q, nsub, dim, d_out);
     }
 
     // queries and outputs on this device; nq bounded by the caller's chunking
@@ -947,6 +1057,23 @@ int b200knn_add(b200knn_index *ix, const void *data, int dtype, int64_t n, int64
     return B200KNN_OK;
 }
 
+int b200knn_debug_shortlists(b200knn_index *ix, float *scores, int32_t *rows, int64_t capacity, int64_t *nq, int *slots, int *c) {
+    if (!ix || !scores || !rows || !nq || !slots || !c) return fail(B200KNN_EINVAL, "NULL argument");
+    if (ix->shards.size() != 1 || !ix->shards[0].ready) return fail(B200KNN_ESTATE, "needs a single-device handle that has answered a query");
+    Shard &s = ix->shards[0];
+    *nq = s.last_nq;
+    *slots = s.last_slots;
+    *c = s.last_c;
+    const int64_t total = s.last_nq * s.last_slots * s.last_c;
+    if (total <= 0) return fail(B200KNN_ESTATE, "no tensor pass has run on this handle");
+    if (capacity < total) return fail(B200KNN_EINVAL, "capacity %lld < %lld entries", (long long)capacity, (long long)total);
+    CU_TRY(cudaSetDevice(s.device));
+    CU_TRY(cudaStreamSynchronize(s.stream));
+    CU_TRY(cudaMemcpy(scores, s.cand_s.p, static_cast<size_t>(total) * sizeof(float), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(rows, s.cand_i.p, static_cast<size_t>(total) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return B200KNN_OK;
+}
+
 int b200knn_merge_topk_device(const int32_t *d_idx, const double *d_dist, int n_lists, int64_t nq, int kk, int32_t *d_out_idx,
                               double *d_out_dist, void *stream) {
     if (!d_idx || !d_dist || !d_out_idx || !d_out_dist) return fail(B200KNN_EINVAL, "NULL buffer");
@@ -974,6 +1101,41 @@ int b200knn_query_device(b200knn_index *ix, const void *d_query, int dtype, int6
         const int64_t cq = std::min(QUERY_CHUNK, nq - q0);
         TRY(s.query_device(static_cast<const char *>(d_query) + static_cast<size_t>(q0) * ld * esz, dtype, cq, ld, ix->dim, ix->kp, k, flags,
                            d_out_idx + q0 * kk, d_out_dist + q0 * kk));
+    }
+    return B200KNN_OK;
+}
+
+int b200knn_ball_membership(b200knn_index *ix, const void *query, int dtype, int64_t nq, int64_t ld, const double *radius2,
+                            unsigned char *out_member) {
+    TRY(check_matrix_args(ix, query, dtype, nq, ld, "query"));
+    if (ix->n_total <= 0) return fail(B200KNN_ESTATE, "membership query on an empty index");
+    if (!radius2 || (nq > 0 && !out_member)) return fail(B200KNN_EINVAL, "NULL buffer");
+    if (nq == 0) return B200KNN_OK;
+    const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
+    const int dim = ix->dim;
+    const int64_t chunk = std::max<int64_t>(BM, std::min<int64_t>(QUERY_CHUNK, (512ll << 20) / (static_cast<int64_t>(dim) * esz) / BM * BM));
+    std::vector<unsigned char> tmp;
+    std::memset(out_member, 0, static_cast<size_t>(nq));
+    int64_t row0 = 0;
+    for (auto &s : ix->shards) {
+        if (s.n <= 0) continue;
+        CU_TRY(cudaSetDevice(s.device));
+        TRY(s.radius2.ensure(s.n));
+        CU_TRY(cudaMemcpyAsync(s.radius2.p, radius2 + row0, static_cast<size_t>(s.n) * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        row0 += s.n;
+        for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+            const int64_t cq = std::min(chunk, nq - q0);
+            TRY(s.q_stage.ensure(static_cast<size_t>(cq) * dim * esz));
+            TRY(s.member.ensure(cq));
+            CU_TRY(cudaMemsetAsync(s.member.p, 0, static_cast<size_t>(cq), s.stream));
+            TRY(s.upload_rows(s.q_stage.p, static_cast<const char *>(query) + static_cast<size_t>(q0) * ld * esz, cq, static_cast<size_t>(dim) * esz,
+                              static_cast<size_t>(ld) * esz, s.stream));
+            TRY(s.ball_membership(s.q_stage.p, dtype, cq, dim, dim, ix->kp, s.member.p));
+            tmp.resize(cq);
+            CU_TRY(cudaMemcpyAsync(tmp.data(), s.member.p, static_cast<size_t>(cq), cudaMemcpyDeviceToHost, s.stream));
+            CU_TRY(cudaStreamSynchronize(s.stream));
+            for (int64_t i = 0; i < cq; i++) out_member[q0 + i] |= tmp[i];
+        }
     }
     return B200KNN_OK;
 }

@@ -92,6 +92,10 @@ def load_library(path=None):
     lib.b200knn_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.b200knn_reset_stats.restype = i32
     lib.b200knn_reset_stats.argtypes = [vp]
+    lib.b200knn_ball_membership.restype = i32
+    lib.b200knn_ball_membership.argtypes = [vp, vp, i32, i64, i64, vp, vp]
+    lib.b200knn_debug_shortlists.restype = i32
+    lib.b200knn_debug_shortlists.argtypes = [vp, vp, vp, i64, ctypes.POINTER(i64), ctypes.POINTER(i32), ctypes.POINTER(i32)]
     lib.b200knn_last_error.restype = ctypes.c_char_p
     lib.b200knn_last_error.argtypes = []
     lib.b200knn_abi_version.restype = i32
@@ -234,6 +238,17 @@ class DCI(object):
 
     def set_profiling(self, on):
         _check(self._lib.b200knn_set_profiling(self._handle, int(bool(on))))
+
+    def debug_shortlists(self, capacity=1 << 24):
+        """Test hook: (scores float32 [Q, slots, C], rows int32 [Q, slots, C]) of the last tensor pass."""
+        sc = np.empty(capacity, dtype=np.float32)
+        rw = np.empty(capacity, dtype=np.int32)
+        nq, slots, c = ctypes.c_int64(0), ctypes.c_int(0), ctypes.c_int(0)
+        _check(self._lib.b200knn_debug_shortlists(self._handle, sc.ctypes.data, rw.ctypes.data, capacity, ctypes.byref(nq),
+                                                  ctypes.byref(slots), ctypes.byref(c)))
+        n = nq.value * slots.value * c.value
+        shape = (nq.value, slots.value, c.value)
+        return sc[:n].reshape(shape), rw[:n].reshape(shape)
 
     # ---- argument checking (dci.py:107-221) -------------------------------------------------------
     def _dtype_code(self, arr):
@@ -410,6 +425,20 @@ class DCI(object):
         elif self._offset:
             idx += np.int32(self._offset)
         return idx, dist
+
+    def ball_membership(self, query, radius2):
+        """Extension for the k-NN precision/recall metric: uint8 [Q], 1 where the query row lies inside at least one
+        ball of squared radius radius2[j] around pool row j (metrics/precision_recall.py:119-120).  Exact."""
+        if self._orig_indices is not None or self._offset:
+            raise ValueError("ball_membership needs an index built from a whole array (indices=None)")
+        q = self._fix_query(query)
+        r2 = np.ascontiguousarray(radius2, dtype=np.float64)
+        if r2.shape != (self.num_points,):
+            raise ValueError("radius2 must have one entry per indexed point")
+        out = np.zeros(q.shape[0], dtype=np.uint8)
+        _check(self._lib.b200knn_ball_membership(self._handle, q.ctypes.data, self._dtype_code(q), q.shape[0], self._dim,
+                                                 r2.ctypes.data, out.ctypes.data))
+        return out
 
     def clear(self):
         """Drop the pool (dci.py:332-335)."""

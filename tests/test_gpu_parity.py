@@ -300,3 +300,50 @@ def test_full_size_config3_properties(lib):
     assert ok, msg
     idx2, dist2 = db.query_arrays(y, 1)
     assert np.array_equal(idx, idx2) and np.array_equal(dist, dist2)
+
+
+# ------------------------------------------------------------------------------------------------ certificate's error model
+def _bf16_round(a):
+    """Round-to-nearest-even float32 -> bfloat16 (returned as float64 values), the conversion the convert kernel does."""
+    f = np.ascontiguousarray(a, dtype=np.float32)
+    u = f.view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).astype(np.float64)
+
+
+@pytest.mark.parametrize("kind,n,q,d", [("gauss", 20000, 256, 3072), ("image", 20000, 256, 3072), ("relu", 30000, 512, 2048),
+                                        ("gauss", 6000, 130, 5000)])
+def test_tensor_scores_within_the_certified_error_model(lib, kind, n, q, d):
+    """The certificate is only as good as its error model.  Pull the raw tensor-core scores of the shortlists and
+    check them against float64 arithmetic on the BF16-rounded inputs: |s~_gpu - (||x~||^2 - 2 q~.x~)| must stay
+    below the eps_acc the kernels assume (kernels.cuh make_err_model), and every kept score must bracket the true
+    distance through the exact perturbation norms ||q-q~||, ||x-x~||."""
+    from inclusivegan_b200 import DCI
+    x, y = make(kind, n, q, d, seed=d + n)
+    db = DCI(d)
+    db.add(x)
+    idx, dist = db.query_arrays(y, 1, flags=FLAG_NO_CERTIFY)
+    scores, rows = db.debug_shortlists()
+    assert scores.shape[0] == q and rows.max() < n
+    xb, yb = _bf16_round(x), _bf16_round(y)
+    xn = np.einsum("ij,ij->i", xb, xb)
+    qn = np.einsum("ij,ij->i", yb, yb)
+    kp = (d + 7) // 8 * 8
+    worst_ratio = 0.0
+    err_q = np.linalg.norm(y - yb, axis=1)
+    err_x_max = np.linalg.norm(x - xb, axis=1).max()
+    for i in range(0, q, 7):                                   # a spread of query rows
+        valid = rows[i] >= 0
+        r = rows[i][valid]
+        s_gpu = scores[i][valid].astype(np.float64)
+        s_ref = xn[r] - 2.0 * (xb[r] @ yb[i])
+        eps = (kp + 8.0) * 2.4e-7 * np.sqrt(qn[i] * xn.max()) * 1.001 + (kp / 16.0 + 8.0) * 1.2e-7 * (xn.max() + qn[i])
+        worst_ratio = max(worst_ratio, float(np.max(np.abs(s_gpu - s_ref)) / eps))
+        # bracket of the true distance (the inequality the pruning rule and the certificate rely on)
+        d_true = np.linalg.norm(x[r] - y[i], axis=1)
+        eta = err_q[i] + err_x_max
+        lo = np.sqrt(np.maximum(s_gpu + qn[i] - eps, 0.0)) - eta
+        hi = np.sqrt(np.maximum(s_gpu + qn[i] + eps, 0.0)) + eta
+        assert np.all(lo <= d_true * (1 + 1e-12)) and np.all(d_true <= hi * (1 + 1e-12))
+    assert worst_ratio < 1.0, "tensor-core accumulation error exceeds the modelled eps_acc (ratio %.3f)" % worst_ratio
+    print("max |s_gpu - s_ref| / eps_acc = %.4f" % worst_ratio)
