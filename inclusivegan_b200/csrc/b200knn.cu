@@ -137,7 +137,8 @@ struct Shard {
     DevBuf<__nv_bfloat16> q_bf2;     // second pass: BF16 rows of the uncertified queries
     DevBuf<float> uncert_thr;
     DevBuf<int> coll_count, coll_idx, overflow_list;
-    DevBuf<WorkItem> sched_items;
+    DevBuf<WorkItem> sched_items;    // first-pass schedule (cached across calls of the same shape: the trainer's 24-row loop)
+    DevBuf<WorkItem> sched_items2;   // second pass / membership schedules
     DevBuf<double> radius2;          // ball membership: squared radii of this shard's rows
     DevBuf<float> colterm, rowthr;
     DevBuf<unsigned char> member;
@@ -271,6 +272,7 @@ struct Shard {
         x_owned = nullptr;
         x_raw = nullptr;
         n = 0;
+        sched1.key_nq = -1;
         x_bf.release();
         xnorm_bf.release();
         x_err.release();
@@ -279,7 +281,7 @@ struct Shard {
         if (!ready) return;
         clear_pool();
         drain_events();
-        q_bf.release(); qnorm_bf.release(); q_err.release(); q_bf2.release(); uncert_thr.release(); coll_count.release(); coll_idx.release(); overflow_list.release(); sched_items.release(); sched_slots.release(); stream_sync.release(); radius2.release(); colterm.release(); rowthr.release(); member.release(); cand_s.release(); cand_i.release(); uncert_list.release();
+        q_bf.release(); qnorm_bf.release(); q_err.release(); q_bf2.release(); uncert_thr.release(); coll_count.release(); coll_idx.release(); overflow_list.release(); sched_items.release(); sched_items2.release(); sched_slots.release(); stream_sync.release(); radius2.release(); colterm.release(); rowthr.release(); member.release(); cand_s.release(); cand_i.release(); uncert_list.release();
         scan_d2.release(); scan_d2_sorted.release(); scan_iota.release(); scan_vals_sorted.release(); scan_offsets.release();
         cub_tmp.release(); q_stage.release(); q_stage2.release(); out_idx.release(); out_dist.release(); scalars.release();
         if (h_count) cudaFreeHost(h_count);
@@ -309,7 +311,7 @@ struct Shard {
         if (cudaPointerGetAttributes(&attr, src) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
         else cudaGetLastError();
         const size_t total = static_cast<size_t>(rows) * row_bytes;
-        if (pinned || total <= (1u << 20)) {
+        if (pinned || total <= (8u << 20)) {   // small pageable copies: the driver's own staging is faster than spawning threads
             if (src_pitch == row_bytes) CU_TRY(cudaMemcpyAsync(dst, src, total, cudaMemcpyHostToDevice, st));
             else CU_TRY(cudaMemcpy2DAsync(dst, row_bytes, src, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, st));
             return B200KNN_OK;
@@ -332,7 +334,7 @@ struct Shard {
             if (ring_used[slot]) CU_TRY(cudaEventSynchronize(ring_done[slot]));   // its previous DMA has drained
             unsigned char *buf = ring[slot];
             const char *sp = src + static_cast<size_t>(r0) * src_pitch;
-            const int nt = static_cast<int>(std::min<int64_t>(copy_threads, std::max<int64_t>(1, pr)));
+            const int nt = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(copy_threads, pr), static_cast<int64_t>(pr * row_bytes) >> 21)));
             auto work = [&](int t) {
                 const int64_t a = pr * t / nt, b = pr * (t + 1) / nt;
                 if (src_pitch == row_bytes) {
@@ -404,10 +406,18 @@ struct Shard {
     // in lockstep: HBM traffic per round is ~ one pass over the pool instead of one per worker.
     struct Sched {
         int cg, qt, nt, workers, nrounds, max_slots, grid, qg;
+        int64_t key_nq = -1, key_n = -1;
+        int key_kp = -1, key_slots = -1;
+        bool matches(int64_t nq_, int64_t n_, int kp_, int slots_) const { return key_nq == nq_ && key_n == n_ && key_kp == kp_ && key_slots == slots_; }
         std::vector<WorkItem> items;        // [nrounds][workers]
         std::vector<int> slots_per_qtile;   // [qt]
     };
+    Sched sched1;   // cached first-pass schedule
     int plan(Sched &s, int64_t nq, int kp, int max_slots_allowed) const {
+        s.key_nq = nq;
+        s.key_n = n;
+        s.key_kp = kp;
+        s.key_slots = max_slots_allowed;
         s.cg = forced_cg ? forced_cg : (nq > BM ? 2 : 1);
         s.workers = std::max(1, s.cg == 2 ? max_pairs : num_sms);
         const int W = s.workers;
@@ -448,15 +458,17 @@ struct Shard {
         s.grid = s.cg * W;
         return B200KNN_OK;
     }
-    // upload the schedule (small: a few KB) and reset the round barrier
-    int upload_schedule(const Sched &s, bool with_slots) {
-        TRY(sched_items.ensure(s.items.size()));
-        CU_TRY(cudaMemcpyAsync(sched_items.p, s.items.data(), s.items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, stream));
-        if (with_slots) {
-            TRY(sched_slots.ensure(s.slots_per_qtile.size()));
-            CU_TRY(cudaMemcpyAsync(sched_slots.p, s.slots_per_qtile.data(), s.slots_per_qtile.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    // upload the schedule (small: a few KB) and reset the round barrier / lockstep counters
+    int upload_schedule(const Sched &s, DevBuf<WorkItem> &items_dst, bool with_slots, bool cached) {
+        if (!cached) {
+            TRY(items_dst.ensure(s.items.size()));
+            // (copies from pageable host memory are staged before cudaMemcpyAsync returns: no synchronisation needed)
+            CU_TRY(cudaMemcpyAsync(items_dst.p, s.items.data(), s.items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, stream));
+            if (with_slots) {
+                TRY(sched_slots.ensure(s.slots_per_qtile.size()));
+                CU_TRY(cudaMemcpyAsync(sched_slots.p, s.slots_per_qtile.data(), s.slots_per_qtile.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+            }
         }
-        // (copies from pageable host memory are staged before cudaMemcpyAsync returns: no synchronisation needed)
         CU_TRY(cudaMemsetAsync(scalars.p + 6, 0, sizeof(unsigned int), stream));
         TRY(stream_sync.ensure(static_cast<size_t>(s.nrounds) * s.max_slots));
         CU_TRY(cudaMemsetAsync(stream_sync.p, 0, static_cast<size_t>(s.nrounds) * s.max_slots * sizeof(unsigned int), stream));
@@ -563,26 +575,28 @@ struct Shard {
         int pk = 1;
         while (pk < rp.max_slots * C) pk <<= 1;
         const size_t sm = static_cast<size_t>(pk) * sizeof(unsigned long long);
+        // merging many shortlists (few queries, many pool streams) is a latency-bound sort: give it 32 warps
+        const int bt = pk >= 1024 ? 1024 : (pk >= 512 ? 512 : 128);
         if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
-            rerank_kernel<double, double, C><<<g, 128, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), rp);
+            rerank_kernel<double, double, C><<<g, bt, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), rp);
         else if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
-            rerank_kernel<double, float, C><<<g, 128, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), rp);
+            rerank_kernel<double, float, C><<<g, bt, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), rp);
         else if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
-            rerank_kernel<float, double, C><<<g, 128, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), rp);
+            rerank_kernel<float, double, C><<<g, bt, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), rp);
         else
-            rerank_kernel<float, float, C><<<g, 128, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), rp);
+            rerank_kernel<float, float, C><<<g, bt, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), rp);
         prof_end();
         CU_TRY(cudaGetLastError());
         return B200KNN_OK;
     }
 
-    DistParams base_dist_params(int64_t nq, int kp, const Sched &s) const {
+    DistParams base_dist_params(int64_t nq, int kp, const Sched &s, const WorkItem *items) const {
         DistParams dp{};
         dp.xnorm = xnorm_bf.p;
         dp.n = static_cast<int>(n);
         dp.nq = static_cast<int>(nq);
         dp.num_kb = (kp + BK - 1) / BK;
-        dp.items = sched_items.p;
+        dp.items = items;
         dp.nrounds = s.nrounds;
         dp.workers = s.workers;
         dp.round_counter = scalars.p + 6;
@@ -613,8 +627,8 @@ struct Shard {
         TRY(make_tmap(&tmap_q2, q_bf2.p, nun, kp, BM));
         Sched s;
         TRY(plan(s, nun, kp, 1 << 20));
-        TRY(upload_schedule(s, false));
-        DistParams dp = base_dist_params(nun, kp, s);
+        TRY(upload_schedule(s, sched_items2, false, false));
+        DistParams dp = base_dist_params(nun, kp, s, sched_items2.p);
         dp.thr = uncert_thr.p;
         dp.coll_count = coll_count.p;
         dp.coll_idx = coll_idx.p;
@@ -667,12 +681,13 @@ struct Shard {
         TRY(launch_convert(d_query, q_dtype, nq, ld_q, dim, kp, q_bf.p, qnorm_bf.p, q_err.p, scalars.p + 2));
         CUtensorMap tmap_q;
         TRY(make_tmap(&tmap_q, q_bf.p, nq, kp, BM));
-        Sched s;
-        TRY(plan(s, nq, kp, MAX_KEYS / C));
-        TRY(upload_schedule(s, true));
+        const bool cached = sched1.matches(nq, n, kp, MAX_KEYS / C);
+        if (!cached) TRY(plan(sched1, nq, kp, MAX_KEYS / C));
+        const Sched &s = sched1;
+        TRY(upload_schedule(s, sched_items, true, cached));
         TRY(cand_s.ensure(static_cast<size_t>(nq) * s.max_slots * C));
         TRY(cand_i.ensure(static_cast<size_t>(nq) * s.max_slots * C));
-        DistParams dp = base_dist_params(nq, kp, s);
+        DistParams dp = base_dist_params(nq, kp, s, sched_items.p);
         dp.cand_s = cand_s.p;
         dp.cand_i = cand_i.p;
         prof_begin(K_DISTANCE, 2.0 * static_cast<double>(nq) * static_cast<double>(n) * dim);
@@ -756,8 +771,8 @@ struct Shard {
         TRY(make_tmap(&tmap_q, q_bf.p, nq, kp, BM));
         Sched s;
         TRY(plan(s, nq, kp, 1 << 20));
-        TRY(upload_schedule(s, false));
-        DistParams dp = base_dist_params(nq, kp, s);
+        TRY(upload_schedule(s, sched_items2, false, false));
+        DistParams dp = base_dist_params(nq, kp, s, sched_items2.p);
         dp.xnorm = colterm.p;
         dp.thr = rowthr.p;
         dp.coll_count = coll_count.p;
@@ -1189,6 +1204,14 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
         // The uploads run on their own host thread (a pageable source keeps that thread busy with memcpy) and their
         // own stream; this thread enqueues the compute.  uploaded / consumed count chunks; the CUDA events order the
         // streams, the counters order the host threads.
+        if (nchunks == 1) {   // small calls (the trainer's 24-row loop): no helper thread, everything on one stream
+            TRY(upload(s, stage[0], src, nq, s.stream));
+            TRY(s.query_device(stage[0], dtype, nq, dim, dim, ix->kp, k, flags, s.out_idx.p, s.out_dist.p));
+            CU_TRY(cudaMemcpyAsync(out_idx, s.out_idx.p, static_cast<size_t>(nq) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+            CU_TRY(cudaMemcpyAsync(out_dist, s.out_dist.p, static_cast<size_t>(nq) * kk * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+            CU_TRY(cudaStreamSynchronize(s.stream));
+            return B200KNN_OK;
+        }
         std::atomic<int64_t> uploaded{0}, consumed{0};
         std::atomic<int> up_rc{B200KNN_OK};
         std::string up_err;

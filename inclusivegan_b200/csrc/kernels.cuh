@@ -89,7 +89,34 @@ convert_norm_kernel(const T *__restrict__ src, int64_t n, int64_t ld, int dim, i
         double er = 0.0;      // sum of squares of (x - x~)
         if (vec) {
             const int groups = dim >> 3;
-            for (int g = lane; g < groups; g += 32) {
+            // two 8-element groups per lane per step: all loads of a step are issued before the first use
+            int g = lane;
+            for (; g + 32 < groups; g += 64) {
+                double v[2][8];
+                load8<T>(s + (g << 3), v[0]);
+                load8<T>(s + ((g + 32) << 3), v[1]);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    __nv_bfloat162 b[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        b[i] = __floats2bfloat162_rn(static_cast<float>(v[h][2 * i]), static_cast<float>(v[h][2 * i + 1]));
+                        const float lo = __low2float(b[i]), hi = __high2float(b[i]);
+                        acc = fmaf(lo, lo, acc);
+                        acc = fmaf(hi, hi, acc);
+                        const double e0 = v[h][2 * i] - static_cast<double>(lo), e1 = v[h][2 * i + 1] - static_cast<double>(hi);
+                        er = fma(e0, e0, er);
+                        er = fma(e1, e1, er);
+                    }
+                    uint4 out;
+                    out.x = *reinterpret_cast<uint32_t *>(&b[0]);
+                    out.y = *reinterpret_cast<uint32_t *>(&b[1]);
+                    out.z = *reinterpret_cast<uint32_t *>(&b[2]);
+                    out.w = *reinterpret_cast<uint32_t *>(&b[3]);
+                    *reinterpret_cast<uint4 *>(d + ((g + 32 * h) << 3)) = out;
+                }
+            }
+            for (; g < groups; g += 32) {
                 double v[8];
                 load8<T>(s + (g << 3), v);
                 __nv_bfloat162 b[4];
@@ -539,7 +566,7 @@ __device__ __forceinline__ ErrModel make_err_model(const RerankParams &p, int q)
 }
 
 template <typename TX, typename TQ, int C>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(1024)
 rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const RerankParams p) {
     extern __shared__ unsigned long long keys[];   // next_pow2(max_slots * C) entries (host-sized, <= MAX_KEYS)
     __shared__ double d2s[C];
@@ -596,13 +623,14 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
     const int warp = tid >> 5, lane = tid & 31;
     const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
     constexpr int RQ = 24;                      // dims per thread held in registers (128 threads x 24 = 3072)
-    __shared__ double partial[4];
+    const int nth = blockDim.x;                 // 128, or 1024 when many shortlists have to be merged (few queries)
+    __shared__ double partial[32];
     double qreg[RQ];
-    const bool fits = p.dim <= RQ * 128;
+    const bool fits = p.dim <= RQ * nth;
     if (fits) {
 #pragma unroll
         for (int i = 0; i < RQ; i++) {
-            const int e = tid + i * 128;
+            const int e = tid + i * nth;
             qreg[i] = (e < p.dim) ? static_cast<double>(qr[e]) : 0.0;
         }
     }
@@ -618,7 +646,7 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
             double xv[RQ];
 #pragma unroll
             for (int i = 0; i < RQ; i++) {
-                const int e = tid + i * 128;
+                const int e = tid + i * nth;
                 xv[i] = (e < p.dim) ? static_cast<double>(xr[e]) : 0.0;
             }
 #pragma unroll
@@ -629,9 +657,9 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
             }
         } else {
             int e = tid;
-            for (; e + 128 < p.dim; e += 256) {
+            for (; e + nth < p.dim; e += 2 * nth) {
                 const double d0 = static_cast<double>(qr[e]) - static_cast<double>(xr[e]);
-                const double d1 = static_cast<double>(qr[e + 128]) - static_cast<double>(xr[e + 128]);
+                const double d1 = static_cast<double>(qr[e + nth]) - static_cast<double>(xr[e + nth]);
                 a0 = fma(d0, d0, a0);
                 a1 = fma(d1, d1, a1);
             }
@@ -643,7 +671,11 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
         const double w = warp_sum(a0 + a1);
         if (lane == 0) partial[warp] = w;
         __syncthreads();
-        if (tid == 0) d2s[c] = (partial[0] + partial[1]) + (partial[2] + partial[3]);
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int i = 0; i < (nth >> 5); i++) tot += partial[i];
+            d2s[c] = tot;
+        }
         __syncthreads();
     }
     __syncthreads();
