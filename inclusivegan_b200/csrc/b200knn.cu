@@ -568,6 +568,17 @@ struct Shard {
     }
 
     // ------------------------------------------------------------------ rerank dispatch
+    template <int C, int NT>
+    void launch_rerank_nt(const void *d_query, int q_dtype, unsigned g, size_t sm, const RerankParams &rp) {
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
+            rerank_kernel<double, double, C, NT><<<g, NT, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), rp);
+        else if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
+            rerank_kernel<double, float, C, NT><<<g, NT, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), rp);
+        else if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
+            rerank_kernel<float, double, C, NT><<<g, NT, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), rp);
+        else
+            rerank_kernel<float, float, C, NT><<<g, NT, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), rp);
+    }
     template <int C>
     int launch_rerank(const void *d_query, int q_dtype, int64_t nq, const RerankParams &rp) {
         prof_begin(K_RERANK);
@@ -576,15 +587,8 @@ struct Shard {
         while (pk < rp.max_slots * C) pk <<= 1;
         const size_t sm = static_cast<size_t>(pk) * sizeof(unsigned long long);
         // merging many shortlists (few queries, many pool streams) is a latency-bound sort: give it 32 warps
-        const int bt = pk >= 1024 ? 1024 : (pk >= 512 ? 512 : 128);
-        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
-            rerank_kernel<double, double, C><<<g, bt, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), rp);
-        else if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
-            rerank_kernel<double, float, C><<<g, bt, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), rp);
-        else if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
-            rerank_kernel<float, double, C><<<g, bt, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), rp);
-        else
-            rerank_kernel<float, float, C><<<g, bt, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), rp);
+        if (pk >= 1024) launch_rerank_nt<C, 1024>(d_query, q_dtype, g, sm, rp);
+        else launch_rerank_nt<C, 128>(d_query, q_dtype, g, sm, rp);
         prof_end();
         CU_TRY(cudaGetLastError());
         return B200KNN_OK;

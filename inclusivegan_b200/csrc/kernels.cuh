@@ -565,8 +565,8 @@ __device__ __forceinline__ ErrModel make_err_model(const RerankParams &p, int q)
     return m;
 }
 
-template <typename TX, typename TQ, int C>
-__global__ void __launch_bounds__(1024)
+template <typename TX, typename TQ, int C, int NT>
+__global__ void __launch_bounds__(NT)
 rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const RerankParams p) {
     extern __shared__ unsigned long long keys[];   // next_pow2(max_slots * C) entries (host-sized, <= MAX_KEYS)
     __shared__ double d2s[C];
@@ -623,7 +623,7 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
     const int warp = tid >> 5, lane = tid & 31;
     const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
     constexpr int RQ = 24;                      // dims per thread held in registers (128 threads x 24 = 3072)
-    const int nth = blockDim.x;                 // 128, or 1024 when many shortlists have to be merged (few queries)
+    constexpr int nth = NT;                     // 128, or 1024 when many shortlists have to be merged (few queries)
     __shared__ double partial[32];
     double qreg[RQ];
     const bool fits = p.dim <= RQ * nth;

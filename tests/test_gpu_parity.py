@@ -88,6 +88,7 @@ def test_golden_vectors_through_dci_class(lib, golden_dir, name):
     ("gauss", 257, 129, 72, 16, np.float64),         # k = 16 boundary of the tensor path
     ("gauss", 300, 20, 64, 40, np.float64),          # k > 32: exact scan + segmented sort
     ("gauss", 1, 3, 8, 1, np.float64),               # single pool row
+    ("image", 3000, 300, 49152, 10, np.float32),     # config-5 feature shape (128x128x3 raw pixels), k=10, reduced N
 ])
 def test_parity_vs_oracle(lib, kind, n, q, d, k, dtype):
     from inclusivegan_b200 import DCI

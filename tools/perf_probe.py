@@ -60,11 +60,10 @@ def probe(N, Q, d, k, dtype=torch.float32, reps=3, kind="gauss", cg=None):
     del ix
 
 if __name__ == "__main__":
-    for cg in (1, 2):
-        probe(300000, 30000, 3072, 1, cg=cg)
-        probe(240000, 24000, 3072, 1, cg=cg)
-        probe(50000, 50000, 2048, 4, cg=cg)
-        probe(100000, 8192, 512, 1, cg=cg)
-    probe(10000, 100, 5000, 10)
-    probe(300000, 24, 3072, 1, reps=10)
+    calibrate()
+    probe(60000, 8192, 49152, 10)            # config-5 feature shape, reduced N and Q
     probe(300000, 30000, 3072, 1, dtype=torch.float64)
+    probe(240000, 24000, 3072, 1, dtype=torch.float64)
+    probe(50000, 50000, 2048, 4)
+    probe(10000, 100, 5000, 10, dtype=torch.float64)
+    calibrate()
