@@ -49,6 +49,12 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// Opaque use of a register: everything loaded into the arguments must be issued before the compiler may start
+// consuming them (it otherwise re-fuses "load all, then convert all" into load/convert pairs that reuse three
+// registers, i.e. three loads in flight instead of twenty-four).
+__device__ __forceinline__ void keep(float &v) { asm volatile("" : "+f"(v)); }
+__device__ __forceinline__ void keep(double &v) { asm volatile("" : "+d"(v)); }
+
 // ------------------------------------------------------------------------------------------------
 // Kernel 1: convert + norms.  One warp per row, 8 elements (one 16-byte BF16 store) per lane per step.
 // Algorithmic bytes per row: dim * (sizeof(T) + 2) + 8.
@@ -628,11 +634,18 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
     double qreg[RQ];
     const bool fits = p.dim <= RQ * nth;
     if (fits) {
+        // raw loads first, conversions after: a float->double conversion placed right behind its load would make the
+        // in-order warp wait for that load before issuing the next one (24 serialized DRAM round trips)
+        TQ qraw[RQ];
 #pragma unroll
         for (int i = 0; i < RQ; i++) {
             const int e = tid + i * nth;
-            qreg[i] = (e < p.dim) ? static_cast<double>(qr[e]) : 0.0;
+            qraw[i] = (e < p.dim) ? qr[e] : TQ(0);
         }
+#pragma unroll
+        for (int i = 0; i < RQ; i++) keep(qraw[i]);
+#pragma unroll
+        for (int i = 0; i < RQ; i++) qreg[i] = static_cast<double>(qraw[i]);
     }
     for (int c = 0; c < C; c++) {
         const unsigned long long key = keys[c];
@@ -643,15 +656,17 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
         const TX *xr = x + static_cast<int64_t>(static_cast<uint32_t>(key)) * p.ld_x;
         double a0 = 0.0, a1 = 0.0;
         if (fits) {
-            double xv[RQ];
+            TX xraw[RQ];
 #pragma unroll
             for (int i = 0; i < RQ; i++) {
                 const int e = tid + i * nth;
-                xv[i] = (e < p.dim) ? static_cast<double>(xr[e]) : 0.0;
+                xraw[i] = (e < p.dim) ? xr[e] : TX(0);
             }
 #pragma unroll
+            for (int i = 0; i < RQ; i++) keep(xraw[i]);
+#pragma unroll
             for (int i = 0; i < RQ; i += 2) {
-                const double d0 = qreg[i] - xv[i], d1 = qreg[i + 1] - xv[i + 1];
+                const double d0 = qreg[i] - static_cast<double>(xraw[i]), d1 = qreg[i + 1] - static_cast<double>(xraw[i + 1]);
                 a0 = fma(d0, d0, a0);
                 a1 = fma(d1, d1, a1);
             }
