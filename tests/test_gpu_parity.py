@@ -348,3 +348,40 @@ def test_tensor_scores_within_the_certified_error_model(lib, kind, n, q, d):
         assert np.all(lo <= d_true * (1 + 1e-12)) and np.all(d_true <= hi * (1 + 1e-12))
     assert worst_ratio < 1.0, "tensor-core accumulation error exceeds the modelled eps_acc (ratio %.3f)" % worst_ratio
     print("max |s_gpu - s_ref| / eps_acc = %.4f" % worst_ratio)
+
+
+# ------------------------------------------------------------------------------------------------ C ABI corner cases
+def test_cabi_strided_rows_and_pageable_uploads(lib):
+    """ld > dim for both matrices (rows embedded in a wider host array) straight through the C ABI, large enough
+    that the pageable upload goes through the pinned ring, float64 pool + float32 queries."""
+    rng = np.random.default_rng(60)
+    n, q, d, ld = 40000, 5000, 200, 264
+    big_x = rng.standard_normal((n, ld))
+    big_q = rng.standard_normal((q, ld)).astype(np.float32)
+    h = ctypes.c_void_p()
+    assert lib.b200knn_create(d, 0, None, ctypes.byref(h)) == 0
+    assert lib.b200knn_add(h, big_x.ctypes.data, 0, n, ld) == 0, lib.b200knn_last_error()
+    assert lib.b200knn_add(h, big_x.ctypes.data, 0, n, ld) == -2          # second add refused (dci.py:228-229)
+    oi = np.empty((q, 3), np.int32); od = np.empty((q, 3))
+    kk = ctypes.c_int(0)
+    assert lib.b200knn_query(h, big_q.ctypes.data, 1, q, ld, 3, 0, oi.ctypes.data, od.ctypes.data, ctypes.byref(kk)) == 0, lib.b200knn_last_error()
+    assert kk.value == 3
+    x = np.ascontiguousarray(big_x[:, :d]); y = np.ascontiguousarray(big_q[:, :d]).astype(np.float64)
+    ri, rd = ko.exact_knn_numpy(x, y, 3)
+    ok, msg = ko.compare_knn(oi, od, ri, rd, x, y)
+    assert ok, msg
+    assert lib.b200knn_clear(h) == 0 and lib.b200knn_num_points(h) == 0
+    assert lib.b200knn_query(h, big_q.ctypes.data, 1, q, ld, 3, 0, oi.ctypes.data, od.ctypes.data, None) == -2
+    assert lib.b200knn_destroy(h) == 0
+
+
+def test_large_query_batches_are_chunked_consistently(lib):
+    """More queries than one device pass (32768) and than one upload chunk: chunk boundaries must not show."""
+    from inclusivegan_b200 import DCI
+    x, y = make("gauss", 3000, 70000, 64, seed=61, dtype=np.float32)
+    db = DCI(64)
+    db.add(x)
+    idx, dist = db.query_arrays(y, 2)
+    ri, rd = ko.exact_knn_numpy(x, y, 2)
+    ok, msg = ko.compare_knn(idx, dist, ri, rd, x, y)
+    assert ok, msg
