@@ -839,19 +839,21 @@ gather_rows_kernel(const __nv_bfloat16 *__restrict__ src, const int *__restrict_
 //   scan_dist_kernel : d2[s][j] = sum_e (q[list[s]][e] - x[j][e])^2     (32 queries x 64 pool rows per block)
 //   scan_select_kernel: kk passes of lexicographic (d2, index) arg-min  (kk <= 32)
 // ------------------------------------------------------------------------------------------------
-constexpr int SCAN_TQ = 32, SCAN_TX = 64, SCAN_TK = 16;
+constexpr int SCAN_TQ = 64, SCAN_TX = 64, SCAN_TK = 16;
 
+// 64 queries x 64 pool rows per block, 4 x 4 outputs per thread, operands staged k-major in shared memory so a thread
+// fetches its four query values and four pool values with two 16-byte loads each (float64 pipe bound, not LDS bound).
 template <typename TX, typename TQ>
 __global__ void __launch_bounds__(256)
 scan_dist_kernel(const TX *__restrict__ x, int64_t ld_x, int n, const TQ *__restrict__ qmat, int64_t ld_q,
                  const int *__restrict__ qlist, int nsub, int dim, double *__restrict__ d2) {
-    __shared__ double qs[SCAN_TQ][SCAN_TK + 1];
-    __shared__ double xs[SCAN_TX][SCAN_TK + 1];
-    const int tx = threadIdx.x & 15;    // 16 column groups x 4 pool rows
-    const int ty = threadIdx.x >> 4;    // 16 row groups x 2 queries
+    __shared__ __align__(16) double qs[SCAN_TK][SCAN_TQ + 4];
+    __shared__ __align__(16) double xs[SCAN_TK][SCAN_TX + 4];
+    const int tx = threadIdx.x & 15;    // pool rows 4*tx .. 4*tx+3
+    const int ty = threadIdx.x >> 4;    // queries   4*ty .. 4*ty+3
     const int x0 = blockIdx.x * SCAN_TX;
     const int s0 = blockIdx.y * SCAN_TQ;
-    double acc[2][4] = {};
+    double acc[4][4] = {};
     for (int k0 = 0; k0 < dim; k0 += SCAN_TK) {
         for (int i = threadIdx.x; i < SCAN_TQ * SCAN_TK; i += 256) {
             const int r = i / SCAN_TK, c = i % SCAN_TK;
@@ -861,30 +863,35 @@ scan_dist_kernel(const TX *__restrict__ x, int64_t ld_x, int n, const TQ *__rest
                 const int qrow = qlist ? qlist[s] : s;
                 v = static_cast<double>(qmat[static_cast<int64_t>(qrow) * ld_q + e]);
             }
-            qs[r][c] = v;
+            qs[c][r] = v;
         }
         for (int i = threadIdx.x; i < SCAN_TX * SCAN_TK; i += 256) {
             const int r = i / SCAN_TK, c = i % SCAN_TK;
             const int j = x0 + r, e = k0 + c;
-            xs[r][c] = (j < n && e < dim) ? static_cast<double>(x[static_cast<int64_t>(j) * ld_x + e]) : 0.0;
+            xs[c][r] = (j < n && e < dim) ? static_cast<double>(x[static_cast<int64_t>(j) * ld_x + e]) : 0.0;
         }
         __syncthreads();
 #pragma unroll
         for (int c = 0; c < SCAN_TK; c++) {
-            const double q0 = qs[ty * 2][c], q1 = qs[ty * 2 + 1][c];
+            const double2 qa = *reinterpret_cast<const double2 *>(&qs[c][ty * 4]);
+            const double2 qb = *reinterpret_cast<const double2 *>(&qs[c][ty * 4 + 2]);
+            const double2 xa = *reinterpret_cast<const double2 *>(&xs[c][tx * 4]);
+            const double2 xb = *reinterpret_cast<const double2 *>(&xs[c][tx * 4 + 2]);
+            const double qv[4] = {qa.x, qa.y, qb.x, qb.y};
+            const double xv[4] = {xa.x, xa.y, xb.x, xb.y};
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const double xv = xs[tx * 4 + b][c];
-                const double d0 = q0 - xv, d1 = q1 - xv;
-                acc[0][b] = fma(d0, d0, acc[0][b]);
-                acc[1][b] = fma(d1, d1, acc[1][b]);
-            }
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const double df = qv[a] - xv[b];
+                    acc[a][b] = fma(df, df, acc[a][b]);
+                }
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int a = 0; a < 2; a++) {
-        const int s = s0 + ty * 2 + a;
+    for (int a = 0; a < 4; a++) {
+        const int s = s0 + ty * 4 + a;
         if (s >= nsub) continue;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
