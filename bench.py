@@ -240,7 +240,34 @@ def run_b200(args):
         all_i = torch.empty(world, q, kk, device=dev, dtype=torch.int32)
         all_d = torch.empty(world, q, kk, device=dev, dtype=torch.float64)
 
+    # ---- multi-GPU exchange: NVLink peer-memory all-gather + merge (no NCCL on the path); NCCL only as a fallback ----
+    exchange = None
+    exchange_kind = "none"
+    if world > 1:
+        from inclusivegan_b200.dci import PeerExchange
+        try:
+            if args.exchange == "nccl":
+                raise RuntimeError("NCCL exchange requested")
+            exchange = PeerExchange(local_rank, rank, world, q, kk)
+            handles = [None] * world
+            dist.all_gather_object(handles, exchange.handle())       # once, at start-up: 64 bytes per rank
+            exchange.connect(handles)
+            ok = torch.tensor([1], device=dev)
+        except Exception as e:
+            exchange = None
+            ok = torch.tensor([0], device=dev)
+            if rank == 0 and args.exchange != "nccl":
+                sys.stderr.write("peer-memory exchange unavailable (%r); falling back to NCCL all-gather\n" % (e,))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)                     # all ranks or none
+        if int(ok.item()) == 0:
+            exchange = None
+        exchange_kind = "nvlink-peer-stores" if exchange is not None else "nccl-allgather"
+
     def exchange_and_merge():
+        if exchange is not None:
+            # publish kernel (P2P stores into every peer's buffer + step flag) and flag-waiting merge kernel
+            exchange.allgather_merge(loc_i.data_ptr(), loc_d.data_ptr(), q, kk, out_i.data_ptr(), out_d.data_ptr(), stream.cuda_stream)
+            return
         # NCCL all-gather of the per-shard (index, distance) lists over NVLink, then the k-way merge kernel.
         # The device-wide synchronisation keeps the collective's kernels (which may run on NCCL's own stream and
         # spin until the peer arrives) from sharing the GPU with the next step's persistent distance kernel, which
@@ -287,7 +314,7 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     st = ix.stats()
     ix.set_profiling(False)
-    launches = st["kernel_launches"] + (args.steps if world > 1 else 0)
+    launches = st["kernel_launches"] + ((2 if exchange is not None else 1) * args.steps if world > 1 else 0)
 
     # ---- end-to-end arm: host-buffer C-ABI call (what DCI.query makes), pinned host queries ----------
     lib = load_library()
@@ -367,7 +394,7 @@ def run_b200(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16 (tensor pass) + f64 (exact re-rank)", "data": "synthetic",
             "config": {"workload": "%s: %s" % (args.workload, desc), "pool": n, "queries": q, "dim": d, "k": k,
-                       "features": "float64 N(0,1), seeded", "parallelism": "pool row-sharded x%d, queries replicated, NCCL all-gather + merge" % world
+                       "features": "float64 N(0,1), seeded", "parallelism": "pool row-sharded x%d, queries replicated, exchange=%s + k-way merge kernel" % (world, exchange_kind)
                        if world > 1 else "single GPU", "l2": "inputs exceed L2 (BF16 pool shard %.2f GB > 126 MB); no explicit flush" % ((r1 - r0) * d * 2 / 1e9),
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "tensor_peak_frac": 2.0 * q * n * d / (ms_step * 1e-3) / 1e12 / (peaks["bf16_tflops"] * world),
@@ -411,6 +438,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU result exchange: NVLink peer-memory kernels (default) or NCCL all-gather")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

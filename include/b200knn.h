@@ -128,6 +128,26 @@ int b200knn_query_device(b200knn_index *index, const void *d_query, int dtype, i
 int b200knn_merge_topk_device(const int32_t *d_idx, const double *d_dist, int n_lists, int64_t nq, int kk,
                               int32_t *d_out_idx, double *d_out_dist, void *stream);
 
+/* ---- NVLink exchange: all-gather + merge over peer memory, one process per GPU, no NCCL -------------------
+ * The multi-GPU step of the path: every rank holds an exact local top-k of its pool shard; the global
+ * answer is the k-way merge of the `world` lists.  Instead of an NCCL all-gather followed by a merge, each rank
+ * STORES its lists directly into every peer's gather buffer over NVLink (CUDA IPC peer mappings) and raises a step
+ * flag there; the merge kernel on each rank waits for the `world` flags in its own buffer and merges.
+ * Two kernel launches per step, no host synchronisation, no collective library.
+ *   create  : allocate this rank's buffer (capacity max_nq * max_kk entries per rank, double-buffered).
+ *   handle  : B200KNN_IPC_BYTES opaque bytes to hand to the other ranks (e.g. torch.distributed.all_gather_object).
+ *   connect : all_handles = world * B200KNN_IPC_BYTES bytes in rank order (own entry ignored).
+ *   allgather_merge : d_idx/d_dist local [nq][kk] (device) -> d_out_* global [nq][kk]; asynchronous on `stream`.
+ *     Every rank must call it the same number of times with the same nq, kk. */
+#define B200KNN_IPC_BYTES 64
+typedef struct b200knn_exchange b200knn_exchange;
+int b200knn_exchange_create(int device, int rank, int world, int64_t max_nq, int max_kk, b200knn_exchange **out);
+int b200knn_exchange_handle(b200knn_exchange *ex, void *out_bytes);
+int b200knn_exchange_connect(b200knn_exchange *ex, const void *all_handles);
+int b200knn_exchange_allgather_merge(b200knn_exchange *ex, const int32_t *d_idx, const double *d_dist, int64_t nq, int kk,
+                                     int32_t *d_out_idx, double *d_out_dist, void *stream);
+int b200knn_exchange_destroy(b200knn_exchange *ex);
+
 /* ---- introspection -------------------------------------------------------------------------- */
 
 typedef struct b200knn_stats {

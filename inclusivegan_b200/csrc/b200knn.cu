@@ -1105,6 +1105,105 @@ int b200knn_merge_topk_device(const int32_t *d_idx, const double *d_dist, int n_
     return B200KNN_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ NVLink exchange
+struct b200knn_exchange {
+    int device = 0, rank = 0, world = 1;
+    int64_t max_items = 0;
+    void *base = nullptr;                 // one cudaMalloc: [flags world*128 B][done counter 128 B][idx 2*world*max_items][dist 2*world*max_items]
+    size_t off_idx = 0, off_dist = 0, off_done = 0, bytes = 0;
+    void *peer_base[EXCH_MAX_WORLD] = {};
+    bool connected = false;
+    unsigned int step = 0;
+};
+
+int b200knn_exchange_create(int device, int rank, int world, int64_t max_nq, int max_kk, b200knn_exchange **out) {
+    if (!out) return fail(B200KNN_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (world < 1 || world > EXCH_MAX_WORLD || rank < 0 || rank >= world || max_nq <= 0 || max_kk <= 0)
+        return fail(B200KNN_EINVAL, "bad rank/world/size (world <= %d)", EXCH_MAX_WORLD);
+    CU_TRY(cudaSetDevice(device));
+    b200knn_exchange *ex = new (std::nothrow) b200knn_exchange();
+    if (!ex) return fail(B200KNN_ENOMEM, "out of host memory");
+    ex->device = device;
+    ex->rank = rank;
+    ex->world = world;
+    ex->max_items = (max_nq * max_kk + 3) / 4 * 4;
+    ex->off_done = static_cast<size_t>(world) * 128;
+    ex->off_idx = ex->off_done + 128;
+    ex->off_dist = ex->off_idx + static_cast<size_t>(2) * world * ex->max_items * sizeof(int32_t);
+    ex->off_dist = (ex->off_dist + 255) / 256 * 256;
+    ex->bytes = ex->off_dist + static_cast<size_t>(2) * world * ex->max_items * sizeof(double);
+    cudaError_t e = cudaMalloc(&ex->base, ex->bytes);
+    if (e != cudaSuccess) { delete ex; return fail(B200KNN_ENOMEM, "cudaMalloc(%zu) for the exchange buffer failed: %s", ex->bytes, cudaGetErrorString(e)); }
+    cudaMemset(ex->base, 0, ex->off_idx);
+    ex->peer_base[rank] = ex->base;
+    if (world == 1) ex->connected = true;
+    *out = ex;
+    return B200KNN_OK;
+}
+
+int b200knn_exchange_handle(b200knn_exchange *ex, void *out_bytes) {
+    if (!ex || !out_bytes) return fail(B200KNN_EINVAL, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200KNN_IPC_BYTES, "IPC handle size");
+    CU_TRY(cudaSetDevice(ex->device));
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, ex->base));
+    std::memcpy(out_bytes, &h, sizeof(h));
+    return B200KNN_OK;
+}
+
+int b200knn_exchange_connect(b200knn_exchange *ex, const void *all_handles) {
+    if (!ex || !all_handles) return fail(B200KNN_EINVAL, "NULL argument");
+    CU_TRY(cudaSetDevice(ex->device));
+    for (int p = 0; p < ex->world; p++) {
+        if (p == ex->rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const char *>(all_handles) + static_cast<size_t>(p) * B200KNN_IPC_BYTES, sizeof(h));
+        CU_TRY(cudaIpcOpenMemHandle(&ex->peer_base[p], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    ex->connected = true;
+    return B200KNN_OK;
+}
+
+int b200knn_exchange_allgather_merge(b200knn_exchange *ex, const int32_t *d_idx, const double *d_dist, int64_t nq, int kk,
+                                     int32_t *d_out_idx, double *d_out_dist, void *stream) {
+    if (!ex || !d_idx || !d_dist || !d_out_idx || !d_out_dist) return fail(B200KNN_EINVAL, "NULL argument");
+    if (!ex->connected) return fail(B200KNN_ESTATE, "exchange is not connected to its peers");
+    const int64_t items = nq * kk;
+    if (items <= 0 || items > ex->max_items) return fail(B200KNN_EINVAL, "nq*kk = %lld exceeds the exchange capacity %lld", (long long)items, (long long)ex->max_items);
+    CU_TRY(cudaSetDevice(ex->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ex->step++;
+    ExchPeers peers{};
+    for (int p = 0; p < ex->world; p++) {
+        char *b = static_cast<char *>(ex->peer_base[p]);
+        peers.flags[p] = reinterpret_cast<unsigned int *>(b);
+        peers.idx[p] = reinterpret_cast<int32_t *>(b + ex->off_idx);
+        peers.dist[p] = reinterpret_cast<double *>(b + ex->off_dist);
+    }
+    char *lb = static_cast<char *>(ex->base);
+    const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(64, (items + 255) / 256)));
+    publish_topk_kernel<<<blocks, 256, 0, st>>>(d_idx, d_dist, items, ex->max_items, ex->rank, ex->world, ex->step, peers,
+                                                reinterpret_cast<unsigned int *>(lb + ex->off_done));
+    CU_TRY(cudaGetLastError());
+    merge_wait_kernel<<<static_cast<unsigned>((nq + 127) / 128), 128, 0, st>>>(
+        reinterpret_cast<const int32_t *>(lb + ex->off_idx), reinterpret_cast<const double *>(lb + ex->off_dist),
+        reinterpret_cast<const unsigned int *>(lb), ex->world, ex->step, ex->max_items, nq, kk, d_out_idx, d_out_dist);
+    CU_TRY(cudaGetLastError());
+    return B200KNN_OK;
+}
+
+int b200knn_exchange_destroy(b200knn_exchange *ex) {
+    if (!ex) return B200KNN_OK;
+    cudaSetDevice(ex->device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < ex->world; p++)
+        if (p != ex->rank && ex->peer_base[p]) cudaIpcCloseMemHandle(ex->peer_base[p]);
+    if (ex->base) cudaFree(ex->base);
+    delete ex;
+    return B200KNN_OK;
+}
+
 int b200knn_query_device(b200knn_index *ix, const void *d_query, int dtype, int64_t nq, int64_t ld, int k, unsigned flags,
                          int32_t *d_out_idx, double *d_out_dist, int *out_kk) {
     TRY(check_matrix_args(ix, d_query, dtype, nq, ld, "query"));

@@ -25,7 +25,7 @@ import os
 
 import numpy as np
 
-__all__ = ["DCI", "DeviceKNN", "ProtectedArray", "B200KNNError", "load_library"]
+__all__ = ["DCI", "DeviceKNN", "PeerExchange", "ProtectedArray", "B200KNNError", "load_library"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_NAME = "libb200knn.so"
@@ -92,6 +92,16 @@ def load_library(path=None):
     lib.b200knn_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.b200knn_reset_stats.restype = i32
     lib.b200knn_reset_stats.argtypes = [vp]
+    lib.b200knn_exchange_create.restype = i32
+    lib.b200knn_exchange_create.argtypes = [i32, i32, i32, i64, i32, ctypes.POINTER(vp)]
+    lib.b200knn_exchange_handle.restype = i32
+    lib.b200knn_exchange_handle.argtypes = [vp, vp]
+    lib.b200knn_exchange_connect.restype = i32
+    lib.b200knn_exchange_connect.argtypes = [vp, vp]
+    lib.b200knn_exchange_allgather_merge.restype = i32
+    lib.b200knn_exchange_allgather_merge.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp]
+    lib.b200knn_exchange_destroy.restype = i32
+    lib.b200knn_exchange_destroy.argtypes = [vp]
     lib.b200knn_ball_membership.restype = i32
     lib.b200knn_ball_membership.argtypes = [vp, vp, i32, i64, i64, vp, vp]
     lib.b200knn_debug_shortlists.restype = i32
@@ -519,3 +529,44 @@ class DeviceKNN(object):
 
     def reset_stats(self):
         _check(self._lib.b200knn_reset_stats(self._handle))
+
+
+class PeerExchange(object):
+    """NVLink all-gather + merge of per-shard results over CUDA-IPC peer memory (b200knn_exchange_*), one process per
+    GPU.  `handle()` bytes of every rank, in rank order, go to `connect()` (any out-of-band channel will do; bench.py
+    uses torch.distributed.all_gather_object once at start-up)."""
+
+    IPC_BYTES = 64
+
+    def __init__(self, device, rank, world, max_nq, max_kk):
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        _check(self._lib.b200knn_exchange_create(int(device), int(rank), int(world), int(max_nq), int(max_kk), ctypes.byref(h)))
+        self._h = h
+        self.world = world
+
+    def handle(self):
+        buf = ctypes.create_string_buffer(self.IPC_BYTES)
+        _check(self._lib.b200knn_exchange_handle(self._h, buf))
+        return bytes(buf.raw)
+
+    def connect(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == self.world * self.IPC_BYTES
+        _check(self._lib.b200knn_exchange_connect(self._h, ctypes.c_char_p(blob)))
+
+    def allgather_merge(self, idx_ptr, dist_ptr, nq, kk, out_idx_ptr, out_dist_ptr, stream_ptr=0):
+        _check(self._lib.b200knn_exchange_allgather_merge(self._h, ctypes.c_void_p(idx_ptr), ctypes.c_void_p(dist_ptr), int(nq), int(kk),
+                                                          ctypes.c_void_p(out_idx_ptr), ctypes.c_void_p(out_dist_ptr),
+                                                          ctypes.c_void_p(stream_ptr or 0)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200knn_exchange_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
