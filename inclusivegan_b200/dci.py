@@ -418,7 +418,7 @@ class DCI(object):
             idx = self._orig_indices[idx].astype(np.int32, copy=False)
         elif self._offset:
             idx += np.int32(self._offset)
-        return [idx[i] for i in range(nq)], [dist[i] for i in range(nq)]
+        return list(idx), list(dist)          # per-query row views, like dci.py:318-330
 
     def query_arrays(self, query, num_neighbours, squared=False, flags=0):
         """Extension: same search, rectangular ndarray results (idx int32 [Q,kk], dist float64 [Q,kk])."""

@@ -1,0 +1,15 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck): every kernel family once."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from inclusivegan_b200 import DCI
+from inclusivegan_b200.dci import FLAG_FORCE_SCAN
+rng = np.random.default_rng(0)
+x = rng.standard_normal((3000, 200)); y = rng.standard_normal((300, 200))
+db = DCI(200); db.add(x)
+db.query_arrays(y, 1); db.query_arrays(y, 10); db.query_arrays(y[:24], 1); db.query_arrays(y, 3, flags=FLAG_FORCE_SCAN); db.query_arrays(y[:40], 40)
+base = 40.0 + rng.standard_normal((1, 64)); xx = base + 1e-3 * rng.standard_normal((2000, 64)); yy = base + 1e-3 * rng.standard_normal((30, 64))
+db2 = DCI(64); db2.add(np.ascontiguousarray(xx)); db2.query_arrays(np.ascontiguousarray(yy), 3)      # uncertified -> collect -> overflow -> scan
+r2 = np.full(3000, 150.0); db.ball_membership(y, r2)
+xf = rng.standard_normal((1500, 129)).astype(np.float32); dbf = DCI(129); dbf.add(xf); dbf.query_arrays(xf[:100], 4, squared=True)
+print("sanitize target done", db.stats()["kernel_launches"], db2.stats())
