@@ -186,3 +186,41 @@ def test_shard_range():
             assert all(0 <= b - a <= (n + g - 1) // g for a, b in rs)
     i, d = pad_local_topk(np.zeros((3, 2), np.int32), np.ones((3, 2)), 4)
     assert i.shape == (3, 4) and (i[:, 2:] == -1).all() and np.isinf(d[:, 2:]).all()
+
+
+def test_reference_wrapper_runs_on_the_extension_stand_in(native_lib):
+    """INTEGRATION.md option B: the reference's UNMODIFIED dci.py on top of inclusivegan_b200._dci (our stand-in for
+    the compiled `_dci` extension).  Needs /root/reference, i.e. runs in the build container only; compute calls are
+    exercised on the GPU by tests/test_gpu_parity.py::test_extension_stand_in_functions."""
+    import importlib.util
+    import sys
+    path = "/root/reference/dci_code/src/dci.py"
+    if not os.path.exists(path):
+        pytest.skip("reference not present")
+    if not hasattr(np, "float"):
+        np.float = np.float64
+    if not hasattr(np, "bool"):
+        np.bool = np.bool_
+    from inclusivegan_b200 import _dci as stand_in
+    saved = sys.modules.get("_dci")
+    sys.modules["_dci"] = stand_in
+    try:
+        spec = importlib.util.spec_from_file_location("_reference_dci_on_b200", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        db = mod.DCI(32, 3, 15)
+        assert (db.dim, db.num_points, db.num_levels) == (32, 0, 0)
+        assert db.proj_vec.shape == (45, 32)
+        db.proj_vec = np.ones((45, 32))
+        with pytest.raises(ValueError):
+            db.add(np.zeros((4, 31)))                       # the reference's own checks still run first
+        if native_lib.b200knn_device_count() == 0:
+            with pytest.raises(RuntimeError, match="no CPU fallback"):
+                db.add(np.zeros((4, 32)))
+        db.clear()
+        db.reset()
+    finally:
+        if saved is None:
+            sys.modules.pop("_dci", None)
+        else:
+            sys.modules["_dci"] = saved

@@ -385,3 +385,21 @@ def test_large_query_batches_are_chunked_consistently(lib):
     ri, rd = ko.exact_knn_numpy(x, y, 2)
     ok, msg = ko.compare_knn(idx, dist, ri, rd, x, y)
     assert ok, msg
+
+
+def test_extension_stand_in_functions(lib):
+    """inclusivegan_b200._dci (stand-in for the reference's compiled `_dci`, INTEGRATION.md option B) called the way
+    dci_code/src/dci.py calls the extension: add(inst, data, start, end, ...), query(...) -> flat idx, flat dist, counts."""
+    from inclusivegan_b200 import _dci
+    x, y = make("gauss", 2500, 40, 96, seed=70)
+    inst = _dci.new(96, 2, 7)
+    assert _dci.get_num_points(inst) == 0 and _dci.get_proj_vec(inst).shape == (14, 96)
+    _dci.add(inst, x, 500, 2500, 2, False, -1, -1, 1.0, 0.002, -1)                  # dci.py:263 argument order
+    assert _dci.get_num_points(inst) == 2000 and _dci.get_num_levels(inst) == 2
+    flat_i, flat_d, counts = _dci.query(inst, y, 3, False, -1, -1, 1.0, 0.05, 100)  # dci.py:313
+    assert counts.tolist() == [3] * 40 and flat_i.dtype == np.int32 and flat_d.dtype == np.float64
+    ri, rd = ko.exact_knn_c(np.ascontiguousarray(x[500:]), y, 3)
+    ok, msg = ko.compare_knn(flat_i.reshape(40, 3), flat_d.reshape(40, 3), ri + 500, rd, x, y)
+    assert ok, msg
+    _dci.reset(inst)
+    assert _dci.get_num_points(inst) == 0
