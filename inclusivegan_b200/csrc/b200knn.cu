@@ -122,7 +122,11 @@ struct Shard {
     int64_t n = 0, ld_x = 0, index_base = 0;
     DevBuf<__nv_bfloat16> x_bf;
     DevBuf<float> xnorm_bf, x_err;
-    DevBuf<unsigned int> scalars;    // [0] max ||x~||^2 bits, [1] max ||x - x~|| bits, [2],[3] same for queries (unused), [4] uncertified count, [5] overflow count
+    DevBuf<double> col_mean;         // pool column means (subtracted from pool and queries before BF16 rounding)
+    bool centered = false;
+    bool use_centering = true;       // $B200KNN_CENTER=0 disables
+    DevBuf<unsigned int> scalars;    // [0] max ||x~||^2 bits, [1] max ||x - x~|| bits, [2],[3] same for queries (unused), [4] uncertified count,
+                                     // [5] overflow count, [6] grid-barrier counter of the distance kernel, [7] max (r_j + e_j) bits (ball membership)
     CUtensorMap tmap_x;              // pool, 256-row box (1-CTA kernel)
     CUtensorMap tmap_x128;           // pool, 128-row box (each CTA of a pair stages half of the 256-row tile)
     int forced_cg = 0;               // $B200KNN_CTA_GROUP=1|2 pins the kernel flavour (A/B measurements)
@@ -208,6 +212,7 @@ struct Shard {
         if (const char *o = getenv("B200KNN_A_BUDGET_MB")) a_budget_mb = std::max(1, atoi(o));
         if (const char *o = getenv("B200KNN_SYNC_TILES")) sync_tiles = std::max(0, atoi(o));
         if (const char *o = getenv("B200KNN_COPY_THREADS")) copy_threads = std::max(1, atoi(o));
+        if (const char *o = getenv("B200KNN_CENTER")) use_centering = atoi(o) != 0;
         copy_threads = std::min<int>(copy_threads, std::max(1u, std::thread::hardware_concurrency()));
         const char *e = getenv("B200KNN_CTA_GROUP");
         if (e && (e[0] == '1' || e[0] == '2')) forced_cg = e[0] - '0';
@@ -276,6 +281,7 @@ struct Shard {
         x_bf.release();
         xnorm_bf.release();
         x_err.release();
+        centered = false;
     }
     void destroy() {
         if (!ready) return;
@@ -360,9 +366,29 @@ struct Shard {
         return B200KNN_OK;
     }
 
+    // ------------------------------------------------------------------ pool mean (centering)
+    int compute_mean(const void *d_rows, int dtype, int64_t rows, int64_t ld, int dim) {
+        centered = false;
+        if (!use_centering || rows <= 0) return B200KNN_OK;
+        TRY(col_mean.ensure(dim));
+        CU_TRY(cudaMemsetAsync(col_mean.p, 0, static_cast<size_t>(dim) * sizeof(double), stream));
+        dim3 grid(static_cast<unsigned>((dim + 255) / 256), static_cast<unsigned>((rows + 255) / 256));
+        prof_begin(K_CONVERT);
+        if (dtype == B200KNN_F64) colsum_kernel<double><<<grid, 256, 0, stream>>>(static_cast<const double *>(d_rows), rows, ld, dim, col_mean.p);
+        else colsum_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(d_rows), rows, ld, dim, col_mean.p);
+        prof_end();
+        prof_begin(K_CONVERT);
+        scale_kernel<<<(dim + 255) / 256, 256, 0, stream>>>(col_mean.p, dim, 1.0 / static_cast<double>(rows));
+        prof_end();
+        CU_TRY(cudaGetLastError());
+        centered = true;
+        return B200KNN_OK;
+    }
+
     // ------------------------------------------------------------------ kernels: convert
     int launch_convert(const void *src, int dtype, int64_t rows, int64_t ld, int dim, int kp, __nv_bfloat16 *dst, float *nbf,
                        float *nex, unsigned int *maxbits /* [2] */) {
+        const double *mu = centered ? col_mean.p : nullptr;
         if (rows <= 0) return B200KNN_OK;
         const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
         const int vec = (dim % 8 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0) && ((ld * esz) % 16 == 0);
@@ -372,10 +398,10 @@ struct Shard {
         prof_begin(K_CONVERT);
         if (dtype == B200KNN_F64)
             convert_norm_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-                static_cast<const double *>(src), rows, ld, dim, kp, vec, dst, nbf, nex, maxbits, maxbits + 1);
+                static_cast<const double *>(src), mu, rows, ld, dim, kp, vec, dst, nbf, nex, maxbits, maxbits + 1);
         else
             convert_norm_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-                static_cast<const float *>(src), rows, ld, dim, kp, vec, dst, nbf, nex, maxbits, maxbits + 1);
+                static_cast<const float *>(src), mu, rows, ld, dim, kp, vec, dst, nbf, nex, maxbits, maxbits + 1);
         prof_end();
         CU_TRY(cudaGetLastError());
         return B200KNN_OK;
@@ -1034,12 +1060,13 @@ int b200knn_add_device(b200knn_index *ix, const void *d_data, int dtype, int64_t
     Shard &s = ix->shards[0];
     CU_TRY(cudaSetDevice(s.device));
     TRY(s.attach_pool(d_data, false, dtype, n, ld, ix->dim, ix->kp, index_base));
+    TRY(s.compute_mean(d_data, dtype, n, ld, ix->dim));
     TRY(s.launch_convert(d_data, dtype, n, ld, ix->dim, ix->kp, s.x_bf.p, s.xnorm_bf.p, s.x_err.p, s.scalars.p));
     ix->n_total = n;
     return B200KNN_OK;
 }
 
-int b200knn_add(b200knn_index *ix, const void *data, int dtype, int64_t n, int64_t ld) {
+static int add_impl(b200knn_index *ix, const void *data, int dtype, int64_t n, int64_t ld) {
     TRY(check_matrix_args(ix, data, dtype, n, ld, "data"));
     if (ix->n_total > 0) return fail(B200KNN_ESTATE, "index already holds %lld points; clear() it first", (long long)ix->n_total);
     if (n == 0) return B200KNN_OK;
@@ -1057,16 +1084,12 @@ int b200knn_add(b200knn_index *ix, const void *data, int dtype, int64_t n, int64
         CU_TRY(cudaMalloc(&d_rows, static_cast<size_t>(rows) * ix->dim * esz));
         int r = s.attach_pool(d_rows, true, dtype, rows, ix->dim, ix->dim, ix->kp, r0);
         if (r != B200KNN_OK) return r;
-        // upload in row blocks so the convert kernel of block i overlaps the copy of block i+1
-        const int64_t block_rows = std::max<int64_t>(1, (256ll << 20) / (static_cast<int64_t>(ix->dim) * esz));
+        // upload (pinned ring for pageable sources), then the column means, then one convert pass over the shard
+        // (the convert takes ~0.3 ms/GB: hiding it behind the upload would save nothing measurable)
         const char *src = static_cast<const char *>(data) + static_cast<size_t>(r0) * ld * esz;
-        for (int64_t b0 = 0; b0 < rows; b0 += block_rows) {
-            const int64_t br = std::min(block_rows, rows - b0);
-            char *dst = static_cast<char *>(d_rows) + static_cast<size_t>(b0) * ix->dim * esz;
-            TRY(s.upload_rows(dst, src + static_cast<size_t>(b0) * ld * esz, br, ix->dim * esz, ld * esz, s.stream));
-            TRY(s.launch_convert(dst, dtype, br, ix->dim, ix->dim, ix->kp, s.x_bf.p + static_cast<size_t>(b0) * ix->kp,
-                                 s.xnorm_bf.p + b0, s.x_err.p + b0, s.scalars.p));
-        }
+        TRY(s.upload_rows(d_rows, src, rows, ix->dim * esz, ld * esz, s.stream));
+        TRY(s.compute_mean(d_rows, dtype, rows, ix->dim, ix->dim));
+        TRY(s.launch_convert(d_rows, dtype, rows, ix->dim, ix->dim, ix->kp, s.x_bf.p, s.xnorm_bf.p, s.x_err.p, s.scalars.p));
     }
     for (auto &s : ix->shards) {
         CU_TRY(cudaSetDevice(s.device));
@@ -1074,6 +1097,18 @@ int b200knn_add(b200knn_index *ix, const void *data, int dtype, int64_t n, int64
     }
     ix->n_total = n;
     return B200KNN_OK;
+}
+
+int b200knn_add(b200knn_index *ix, const void *data, int dtype, int64_t n, int64_t ld) {
+    const int rc = add_impl(ix, data, dtype, n, ld);
+    if (rc != B200KNN_OK && rc != B200KNN_ESTATE && ix && ix->n_total == 0) {
+        // a failed add leaves no half-built pool behind (device memory released, handle reusable)
+        const std::string msg = g_last_error;
+        for (auto &s : ix->shards) s.clear_pool();
+        cudaGetLastError();
+        g_last_error = msg;
+    }
+    return rc;
 }
 
 int b200knn_debug_shortlists(b200knn_index *ix, float *scores, int32_t *rows, int64_t capacity, int64_t *nq, int *slots, int *c) {

@@ -75,14 +75,46 @@ __device__ __forceinline__ void load8<float>(const float *p, double (&d)[8]) {
     d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w; d[4] = v1.x; d[5] = v1.y; d[6] = v1.z; d[7] = v1.w;
 }
 
-// Outputs per row: the BF16 row x~ (zero padded to kp), ||x~||^2 (fp32 sum of the exact squares of the rounded
-// values) and err = ||x - x~|| rounded up — the EXACT size of the rounding perturbation, which is what the
-// exactness certificate needs (a worst-case 2^-9 ||x|| bound is ~2.5x looser).  Grid-wide maxima of both are
-// kept as float bit patterns (non-negative floats order like unsigned ints).
+// 8 doubles through the read-only cached path (the column means: 8*dim bytes, L1/L2 resident)
+__device__ __forceinline__ void load8_cached(const double *p, double (&d)[8]) {
+    const double2 *p2 = reinterpret_cast<const double2 *>(p);
+    const double2 v0 = __ldg(p2), v1 = __ldg(p2 + 1), v2 = __ldg(p2 + 2), v3 = __ldg(p2 + 3);
+    d[0] = v0.x; d[1] = v0.y; d[2] = v1.x; d[3] = v1.y; d[4] = v2.x; d[5] = v2.y; d[6] = v3.x; d[7] = v3.y;
+}
+
+// Column sums of the pool (float64 atomics): the pool mean is subtracted from pool AND queries before the BF16
+// rounding.  Translation changes no distance, but it removes a common offset from the norms the rounding error is
+// proportional to (features with a large mean otherwise certify nothing in the first pass).
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T *__restrict__ src, int64_t n, int64_t ld, int dim, double *__restrict__ sums) {
+    const int rows_per_block = 256;
+    const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
+    const int64_t r1 = min(r0 + rows_per_block, n);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= dim) return;
+    double a0 = 0.0, a1 = 0.0;
+    int64_t r = r0;
+    for (; r + 1 < r1; r += 2) {
+        a0 += static_cast<double>(src[r * ld + c]);
+        a1 += static_cast<double>(src[(r + 1) * ld + c]);
+    }
+    if (r < r1) a0 += static_cast<double>(src[r * ld + c]);
+    atomicAdd(sums + c, a0 + a1);
+}
+__global__ void scale_kernel(double *__restrict__ v, int dim, double f) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < dim) v[i] *= f;
+}
+
+// Outputs per row: the BF16 row x~ of (x - mu) (zero padded to kp), ||x~||^2 (fp32 sum of the exact squares of the
+// rounded values) and err = ||(x - mu) - x~|| rounded up - the EXACT size of the rounding perturbation, which is what
+// the exactness certificate needs (a worst-case 2^-9 ||x|| bound is ~2.5x looser).  Grid-wide maxima of both are kept
+// as float bit patterns (non-negative floats order like unsigned ints).
 // vec != 0 requires: dim % 8 == 0 (so kp == dim), src rows 16-byte aligned.
 template <typename T>
 __global__ void __launch_bounds__(256)
-convert_norm_kernel(const T *__restrict__ src, int64_t n, int64_t ld, int dim, int kp, int vec,
+convert_norm_kernel(const T *__restrict__ src, const double *__restrict__ mu, int64_t n, int64_t ld, int dim, int kp, int vec,
                     __nv_bfloat16 *__restrict__ dst, float *__restrict__ norm_bf, float *__restrict__ err_out,
                     unsigned int *__restrict__ max_norm_bf_bits, unsigned int *__restrict__ max_err_bits) {
     const int lane = threadIdx.x & 31;
@@ -101,6 +133,16 @@ convert_norm_kernel(const T *__restrict__ src, int64_t n, int64_t ld, int dim, i
                 double v[2][8];
                 load8<T>(s + (g << 3), v[0]);
                 load8<T>(s + ((g + 32) << 3), v[1]);
+                if (mu) {
+                    double m0[8], m1[8];
+                    load8_cached(mu + (g << 3), m0);
+                    load8_cached(mu + ((g + 32) << 3), m1);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        v[0][i] -= m0[i];
+                        v[1][i] -= m1[i];
+                    }
+                }
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     __nv_bfloat162 b[4];
@@ -125,6 +167,12 @@ convert_norm_kernel(const T *__restrict__ src, int64_t n, int64_t ld, int dim, i
             for (; g < groups; g += 32) {
                 double v[8];
                 load8<T>(s + (g << 3), v);
+                if (mu) {
+                    double m0[8];
+                    load8_cached(mu + (g << 3), m0);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[i] -= m0[i];
+                }
                 __nv_bfloat162 b[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
@@ -146,7 +194,7 @@ convert_norm_kernel(const T *__restrict__ src, int64_t n, int64_t ld, int dim, i
         } else {
             for (int e = lane; e < kp; e += 32) {
                 double v = 0.0;
-                if (e < dim) v = static_cast<double>(s[e]);
+                if (e < dim) v = static_cast<double>(s[e]) - (mu ? __ldg(mu + e) : 0.0);
                 const __nv_bfloat16 b = __float2bfloat16_rn(static_cast<float>(v));
                 const float fb = __bfloat162float(b);
                 acc = fmaf(fb, fb, acc);

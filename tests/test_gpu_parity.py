@@ -219,18 +219,43 @@ def test_non_contiguous_and_mixed_dtype_queries(lib):
 
 
 def test_uncertified_queries_are_answered_exactly(lib):
-    """Data built so the BF16 shortlist cannot be certified (near-duplicate pool rows far from the origin):
-    the second pass must still produce the exact answer, and must report that it ran."""
+    """High-dimensional i.i.d. data: neighbour gaps are of the order of the BF16 rounding perturbation, so a good part
+    of the shortlists cannot be certified; the second (collect) tensor pass must still produce the exact answer."""
+    from inclusivegan_b200 import DCI
+    x, y = make("gauss", 4000, 60, 4096, seed=77)
+    db = DCI(4096)
+    db.add(x)
+    check(db, x, y, 10)
+    assert db.stats()["uncertified"] > 0
+
+
+def test_common_offset_is_removed_by_centering(lib):
+    """Rows far from the origin with tiny mutual distances (norm ~640, distances ~0.02): uncertifiable if rounded as
+    they are, trivial once the pool mean is subtracted before the BF16 rounding (translation changes no distance)."""
     from inclusivegan_b200 import DCI
     rng = np.random.default_rng(77)
     base = 40.0 + rng.standard_normal((1, 256))
-    x = base + 1e-3 * rng.standard_normal((4000, 256))         # norms ~640, pairwise distances ~0.02
-    y = base + 1e-3 * rng.standard_normal((50, 256))
-    x, y = np.ascontiguousarray(x), np.ascontiguousarray(y)
+    x = np.ascontiguousarray(base + 1e-3 * rng.standard_normal((4000, 256)))
+    y = np.ascontiguousarray(base + 1e-3 * rng.standard_normal((50, 256)))
     db = DCI(256)
     db.add(x)
     check(db, x, y, 3)
-    assert db.stats()["uncertified"] > 0
+    assert db.stats()["uncertified"] == 0
+
+
+def test_overflowing_second_pass_falls_to_the_exact_scan(lib):
+    """Two tight clusters far apart: after centering every row is +-40 plus noise far below BF16 resolution, all
+    scores inside a cluster tie, the collect lists overflow (2000 > 1024) and the exact float64 scan answers."""
+    from inclusivegan_b200 import DCI
+    rng = np.random.default_rng(78)
+    sign = np.where(np.arange(4000) % 2 == 0, 1.0, -1.0)[:, None]
+    x = np.ascontiguousarray(40.0 * sign + 1e-3 * rng.standard_normal((4000, 256)))
+    y = np.ascontiguousarray(40.0 * np.where(np.arange(50) % 2 == 0, 1.0, -1.0)[:, None] + 1e-3 * rng.standard_normal((50, 256)))
+    db = DCI(256)
+    db.add(x)
+    check(db, x, y, 3)
+    st = db.stats()
+    assert st["uncertified"] > 0 and st["exact_scanned"] > 0
 
 
 # ------------------------------------------------------------------------------------------------ device ABI + merge
@@ -316,7 +341,7 @@ def _bf16_round(a):
                                         ("gauss", 6000, 130, 5000)])
 def test_tensor_scores_within_the_certified_error_model(lib, kind, n, q, d):
     """The certificate is only as good as its error model.  Pull the raw tensor-core scores of the shortlists and
-    check them against float64 arithmetic on the BF16-rounded inputs: |s~_gpu - (||x~||^2 - 2 q~.x~)| must stay
+    check them against float64 arithmetic on the BF16-rounded (mean-centred) inputs: |s~_gpu - (||x~||^2 - 2 q~.x~)| must stay
     below the eps_acc the kernels assume (kernels.cuh make_err_model), and every kept score must bracket the true
     distance through the exact perturbation norms ||q-q~||, ||x-x~||."""
     from inclusivegan_b200 import DCI
@@ -326,13 +351,15 @@ def test_tensor_scores_within_the_certified_error_model(lib, kind, n, q, d):
     idx, dist = db.query_arrays(y, 1, flags=FLAG_NO_CERTIFY)
     scores, rows = db.debug_shortlists()
     assert scores.shape[0] == q and rows.max() < n
-    xb, yb = _bf16_round(x), _bf16_round(y)
+    mu = x.mean(axis=0)                                        # the library subtracts the pool mean before rounding
+    xc, yc = x - mu, y - mu
+    xb, yb = _bf16_round(xc), _bf16_round(yc)
     xn = np.einsum("ij,ij->i", xb, xb)
     qn = np.einsum("ij,ij->i", yb, yb)
     kp = (d + 7) // 8 * 8
     worst_ratio = 0.0
-    err_q = np.linalg.norm(y - yb, axis=1)
-    err_x_max = np.linalg.norm(x - xb, axis=1).max()
+    err_q = np.linalg.norm(yc - yb, axis=1)
+    err_x_max = np.linalg.norm(xc - xb, axis=1).max()
     for i in range(0, q, 7):                                   # a spread of query rows
         valid = rows[i] >= 0
         r = rows[i][valid]
