@@ -135,7 +135,7 @@ def reference_sample(workload, steps, warmup, budget_s=25.0):
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     if not ref_dci.available():
         return None
-    ns = int(min(n, 60000))
+    ns = int(min(n, 120000))
     qs = int(min(q, max(64, 16 * cores)))
     rng = np.random.default_rng(0)
     pool = rng.standard_normal((ns, d))
