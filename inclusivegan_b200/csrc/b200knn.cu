@@ -208,6 +208,8 @@ struct Shard {
         CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<16, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
         CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<32, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
         CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<16, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<64, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<1>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<64, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
         if (const char *o = getenv("B200KNN_OPT")) opt_flags = static_cast<unsigned>(atoi(o));
         if (const char *o = getenv("B200KNN_A_BUDGET_MB")) a_budget_mb = std::max(1, atoi(o));
         if (const char *o = getenv("B200KNN_SYNC_TILES")) sync_tiles = std::max(0, atoi(o));
@@ -876,10 +878,11 @@ struct Shard {
         CU_TRY(cudaSetDevice(device));
         const int kk = static_cast<int>(std::min<int64_t>(k, n));
         stats.queries += nq;
-        if (kk > 16 || (flags & B200KNN_FLAG_FORCE_SCAN))
+        if (kk > 32 || (flags & B200KNN_FLAG_FORCE_SCAN))
             return scan(d_query, q_dtype, ld_q, nullptr, static_cast<int>(nq), dim, kk, flags, d_out_idx, d_out_dist);
         if (kk <= 4) return tensor_pass<16>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist);
-        return tensor_pass<32>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist);
+        if (kk <= 16) return tensor_pass<32>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist);
+        return tensor_pass<64>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist);
     }
 };
 

@@ -743,24 +743,42 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
     }
     __syncthreads();
     if (warp == 0) {
-        // rank the exact distances by (d2, index); C <= 32
-        double myd = DBL_MAX;
-        uint32_t myi = 0xffffffffu;
-        if (lane < C) { myd = d2s[lane]; myi = static_cast<uint32_t>(keys[lane]); }
-        int rank = 0;
+        // rank the exact distances by (d2, index); each lane owns candidates lane, lane + 32 (C <= 64)
+        constexpr int H = (C + 31) / 32;
+        double myd[H];
+        uint32_t myi[H];
+        int rank[H];
 #pragma unroll
-        for (int o = 0; o < C; o++) {
-            const double od = __shfl_sync(0xffffffffu, myd, o);
-            const uint32_t oi = __shfl_sync(0xffffffffu, myi, o);
-            rank += (od < myd || (od == myd && oi < myi)) ? 1 : 0;
+        for (int h = 0; h < H; h++) {
+            const int c = lane + 32 * h;
+            myd[h] = (c < C) ? d2s[c] : DBL_MAX;
+            myi[h] = (c < C) ? static_cast<uint32_t>(keys[c]) : 0xffffffffu;
+            rank[h] = 0;
         }
-        if (lane < C && rank < p.kk) {
-            p.out_idx[static_cast<int64_t>(q) * p.kk + rank] = static_cast<int32_t>(p.index_base + myi);
-            p.out_dist[static_cast<int64_t>(q) * p.kk + rank] = (p.flags & 1u) ? myd : sqrt(myd);
+#pragma unroll
+        for (int g = 0; g < H; g++) {
+#pragma unroll
+            for (int o = 0; o < 32; o++) {
+                const double od = __shfl_sync(0xffffffffu, myd[g], o);
+                const uint32_t oi = __shfl_sync(0xffffffffu, myi[g], o);
+#pragma unroll
+                for (int h = 0; h < H; h++) rank[h] += (od < myd[h] || (od == myd[h] && oi < myi[h])) ? 1 : 0;
+            }
         }
-        // k-th exact distance (rank kk-1), broadcast
-        const unsigned mk = __ballot_sync(0xffffffffu, lane < C && rank == p.kk - 1);
-        const double dk2 = __shfl_sync(0xffffffffu, myd, mk ? (__ffs(mk) - 1) : 0);
+        double dk2 = DBL_MAX;
+        unsigned mk = 0;
+#pragma unroll
+        for (int h = 0; h < H; h++) {
+            const bool valid = (lane + 32 * h) < C;
+            if (valid && rank[h] < p.kk) {
+                p.out_idx[static_cast<int64_t>(q) * p.kk + rank[h]] = static_cast<int32_t>(p.index_base + myi[h]);
+                p.out_dist[static_cast<int64_t>(q) * p.kk + rank[h]] = (p.flags & 1u) ? myd[h] : sqrt(myd[h]);
+            }
+            // k-th exact distance (rank kk-1), broadcast
+            const unsigned mh = __ballot_sync(0xffffffffu, valid && rank[h] == p.kk - 1);
+            const double dh = __shfl_sync(0xffffffffu, myd[h], mh ? (__ffs(mh) - 1) : 0);
+            if (mh) { dk2 = dh; mk = mh; }
+        }
         if (lane == 0 && !(p.flags & 2u)) {
             // ---- certificate: every pool row NOT among the C kept has score >= tau (the C-th kept score), hence
             // true distance >= lower(tau).  The answer is exact when the kk-th exact distance is below that.

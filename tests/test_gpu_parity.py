@@ -85,7 +85,10 @@ def test_golden_vectors_through_dci_class(lib, golden_dir, name):
     ("cluster", 70000, 1000, 512, 1, np.float64),    # many shortlists per query (chunked sweep)
     ("relu", 6000, 6000, 256, 4, np.float32),        # config-4-like
     ("lowrank", 10000, 100, 5000, 10, np.float64),   # config 1 (dci_code/example.py data), full size
-    ("gauss", 257, 129, 72, 16, np.float64),         # k = 16 boundary of the tensor path
+    ("gauss", 257, 129, 72, 16, np.float64),         # k = 16: last k served by the 32-entry shortlist
+    ("cluster", 20000, 300, 512, 25, np.float64),    # k = num_samples_factor default of training_loop() (:154): 64-entry shortlist
+    ("gauss", 500, 40, 64, 32, np.float64),          # k = 32 boundary of the tensor path
+    ("gauss", 500, 40, 64, 33, np.float64),          # first k on the exact-scan path
     ("gauss", 300, 20, 64, 40, np.float64),          # k > 32: exact scan + segmented sort
     ("gauss", 1, 3, 8, 1, np.float64),               # single pool row
     ("image", 3000, 300, 49152, 10, np.float32),     # config-5 feature shape (128x128x3 raw pixels), k=10, reduced N
