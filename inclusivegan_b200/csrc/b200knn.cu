@@ -1077,22 +1077,41 @@ static int add_impl(b200knn_index *ix, const void *data, int dtype, int64_t n, i
     const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
     const int G = static_cast<int>(ix->shards.size());
     const int64_t per = (n + G - 1) / G;
-    for (int g = 0; g < G; g++) {
+    // one host thread per shard: the PCIe links of the GPUs are independent, and the per-shard work is
+    // upload (pinned ring for pageable sources) -> column means -> one convert pass
+    auto shard_add = [&](int g) -> int {
         Shard &s = ix->shards[g];
         const int64_t r0 = std::min<int64_t>(n, per * g), r1 = std::min<int64_t>(n, per * (g + 1));
         const int64_t rows = r1 - r0;
-        if (rows <= 0) { s.n = 0; continue; }
+        if (rows <= 0) { s.n = 0; return B200KNN_OK; }
         CU_TRY(cudaSetDevice(s.device));
         void *d_rows = nullptr;
         CU_TRY(cudaMalloc(&d_rows, static_cast<size_t>(rows) * ix->dim * esz));
         int r = s.attach_pool(d_rows, true, dtype, rows, ix->dim, ix->dim, ix->kp, r0);
         if (r != B200KNN_OK) return r;
-        // upload (pinned ring for pageable sources), then the column means, then one convert pass over the shard
-        // (the convert takes ~0.3 ms/GB: hiding it behind the upload would save nothing measurable)
         const char *src = static_cast<const char *>(data) + static_cast<size_t>(r0) * ld * esz;
         TRY(s.upload_rows(d_rows, src, rows, ix->dim * esz, ld * esz, s.stream));
         TRY(s.compute_mean(d_rows, dtype, rows, ix->dim, ix->dim));
         TRY(s.launch_convert(d_rows, dtype, rows, ix->dim, ix->dim, ix->kp, s.x_bf.p, s.xnorm_bf.p, s.x_err.p, s.scalars.p));
+        return B200KNN_OK;
+    };
+    if (G == 1) {
+        TRY(shard_add(0));
+    } else {
+        std::vector<int> rcs(G, B200KNN_OK);
+        std::vector<std::string> errs(G);
+        const int saved_threads = ix->shards[0].copy_threads;
+        for (auto &s : ix->shards) s.copy_threads = std::max(1, saved_threads * 2 / G);
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; g++)
+            th.emplace_back([&, g]() {
+                rcs[g] = shard_add(g);
+                if (rcs[g] != B200KNN_OK) errs[g] = g_last_error;
+            });
+        for (auto &t : th) t.join();
+        for (auto &s : ix->shards) s.copy_threads = saved_threads;
+        for (int g = 0; g < G; g++)
+            if (rcs[g] != B200KNN_OK) return fail(rcs[g], "%s", errs[g].c_str());
     }
     for (auto &s : ix->shards) {
         CU_TRY(cudaSetDevice(s.device));
@@ -1395,58 +1414,136 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
         CU_TRY(cudaStreamSynchronize(s.stream));
         return B200KNN_OK;
     }
-    // ---- multi-device handle ----
-    const int64_t chunk = std::max<int64_t>(BM, std::min<int64_t>(QUERY_CHUNK, (256ll << 20) / (static_cast<int64_t>(dim) * esz) / BM * BM));
-    for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
-        const int64_t cq = std::min(chunk, nq - q0);
-        const char *src = static_cast<const char *>(query) + static_cast<size_t>(q0) * ld * esz;
-        for (int g = 0; g < G; g++) {
-            Shard &s = ix->shards[g];
-            if (s.n <= 0) continue;
-            CU_TRY(cudaSetDevice(s.device));
-            TRY(s.q_stage.ensure(static_cast<size_t>(cq) * dim * esz));
-            TRY(s.out_idx.ensure(static_cast<size_t>(cq) * kk));
-            TRY(s.out_dist.ensure(static_cast<size_t>(cq) * kk));
-            TRY(upload(s, s.q_stage.p, src, cq, s.stream));
+    // ---- multi-device handle: every chunk is uploaded ONCE (to shard 0, on its own host thread and stream, double
+    // buffered) and broadcast to the other shards over NVLink; every shard answers on its own host thread (the
+    // per-shard call synchronises its stream); results are gathered on shard 0 with peer copies and merged there ----
+    std::vector<int> active;
+    for (int g = 0; g < G; g++)
+        if (ix->shards[g].n > 0) active.push_back(g);
+    for (int g : active)
+        if (ix->shards[g].n < kk) return fail(B200KNN_EINVAL, "a shard holds fewer rows (%lld) than k=%d; use fewer devices", (long long)ix->shards[g].n, kk);
+    const int lists = static_cast<int>(active.size());
+    Shard &s0 = ix->shards[active[0]];
+    // chunks of one query-tile group of the per-shard kernel (see the single-device path)
+    std::vector<std::pair<int64_t, int64_t>> chunks;
+    {
+        Shard::Sched sch;
+        TRY(s0.plan(sch, nq, ix->kp, 64));
+        int64_t group_rows = static_cast<int64_t>(sch.qg) * BM * sch.cg;
+        const int64_t cap_rows = std::max<int64_t>(BM * 2, (512ll << 20) / (static_cast<int64_t>(dim) * esz) / (BM * 2) * (BM * 2));
+        group_rows = std::max<int64_t>(BM * 2, std::min(group_rows, cap_rows));
+        if (nq <= group_rows + group_rows / 4) {
+            chunks.emplace_back(0, nq);
+        } else {
+            const int64_t rem = nq % group_rows;
+            int64_t q0 = 0;
+            if (rem > 0) { chunks.emplace_back(0, rem); q0 = rem; }
+            for (; q0 < nq; q0 += group_rows) chunks.emplace_back(q0, std::min(group_rows, nq - q0));
         }
-        // ---- multi-device: local top-k per shard, gather to shard 0 over NVLink, k-way merge there ----
-        Shard &s0 = ix->shards[0];
-        CU_TRY(cudaSetDevice(s0.device));
-        TRY(ix->g_idx.ensure(static_cast<size_t>(G) * cq * kk));
-        TRY(ix->g_dist.ensure(static_cast<size_t>(G) * cq * kk));
-        int lists = 0;
-        std::vector<cudaEvent_t> done;
-        for (int g = 0; g < G; g++) {
-            Shard &s = ix->shards[g];
-            if (s.n <= 0) continue;
-            CU_TRY(cudaSetDevice(s.device));
-            const int kg = static_cast<int>(std::min<int64_t>(kk, s.n));
-            if (kg < kk) {   // pad: fill with (-1, +inf) first, then the kg real columns are written by a strided copy below
-                return fail(B200KNN_EINVAL, "a shard holds fewer rows (%lld) than k=%d; use fewer devices", (long long)s.n, kk);
-            }
-            TRY(s.query_device(s.q_stage.p, dtype, cq, dim, dim, ix->kp, kk, flags, s.out_idx.p, s.out_dist.p));
-            CU_TRY(cudaMemcpyPeerAsync(ix->g_idx.p + static_cast<size_t>(lists) * cq * kk, s0.device, s.out_idx.p, s.device,
-                                       static_cast<size_t>(cq) * kk * sizeof(int32_t), s.stream));
-            CU_TRY(cudaMemcpyPeerAsync(ix->g_dist.p + static_cast<size_t>(lists) * cq * kk, s0.device, s.out_dist.p, s.device,
-                                       static_cast<size_t>(cq) * kk * sizeof(double), s.stream));
-            cudaEvent_t ev;
-            CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            CU_TRY(cudaEventRecord(ev, s.stream));
-            done.push_back(ev);
-            lists++;
-        }
-        CU_TRY(cudaSetDevice(s0.device));
-        for (auto ev : done) {
-            CU_TRY(cudaStreamWaitEvent(s0.stream, ev, 0));
-        }
-        TRY(s0.out_idx.ensure(static_cast<size_t>(cq) * kk));
-        TRY(b200knn_merge_topk_device(ix->g_idx.p, ix->g_dist.p, lists, cq, kk, s0.out_idx.p, s0.out_dist.p, s0.stream));
-        s0.stats.kernel_launches++;
-        CU_TRY(cudaMemcpyAsync(out_idx + q0 * kk, s0.out_idx.p, static_cast<size_t>(cq) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s0.stream));
-        CU_TRY(cudaMemcpyAsync(out_dist + q0 * kk, s0.out_dist.p, static_cast<size_t>(cq) * kk * sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
-        CU_TRY(cudaStreamSynchronize(s0.stream));
-        for (auto ev : done) cudaEventDestroy(ev);
     }
+    const int64_t nchunks = static_cast<int64_t>(chunks.size());
+    int64_t max_rows = 0;
+    for (auto &c : chunks) max_rows = std::max(max_rows, c.second);
+    for (int g : active) {
+        Shard &s = ix->shards[g];
+        CU_TRY(cudaSetDevice(s.device));
+        TRY(s.q_stage.ensure(static_cast<size_t>(max_rows) * dim * esz));
+        if (nchunks > 1) TRY(s.q_stage2.ensure(static_cast<size_t>(max_rows) * dim * esz));
+        TRY(s.out_idx.ensure(static_cast<size_t>(max_rows) * kk));
+        TRY(s.out_dist.ensure(static_cast<size_t>(max_rows) * kk));
+    }
+    CU_TRY(cudaSetDevice(s0.device));
+    TRY(ix->g_idx.ensure(static_cast<size_t>(lists) * max_rows * kk));
+    TRY(ix->g_dist.ensure(static_cast<size_t>(lists) * max_rows * kk));
+    std::vector<cudaEvent_t> done(lists, nullptr);
+    for (int i = 0; i < lists; i++) {
+        CU_TRY(cudaSetDevice(ix->shards[active[i]].device));
+        CU_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    }
+    std::atomic<int64_t> uploaded{0}, consumed{0};
+    std::atomic<int> up_rc{B200KNN_OK};
+    std::string up_err;
+    std::thread uploader([&]() {
+        for (int64_t c = 0; c < nchunks; c++) {
+            const int b = static_cast<int>(c & 1);
+            while (consumed.load(std::memory_order_acquire) < c - 1) std::this_thread::yield();   // chunk c-2 fully done (host-synchronised)
+            cudaSetDevice(s0.device);
+            unsigned char *dst0 = b ? s0.q_stage2.p : s0.q_stage.p;
+            int rc = upload(s0, dst0, static_cast<const char *>(query) + static_cast<size_t>(chunks[c].first) * ld * esz, chunks[c].second, s0.copy_stream);
+            if (rc == B200KNN_OK && cudaEventRecord(s0.ev_copied[b], s0.copy_stream) != cudaSuccess) rc = B200KNN_ECUDA;
+            const size_t qbytes = static_cast<size_t>(chunks[c].second) * dim * esz;
+            for (int i = 1; i < lists && rc == B200KNN_OK; i++) {      // NVLink broadcast on each receiver's copy stream
+                Shard &s = ix->shards[active[i]];
+                cudaSetDevice(s.device);
+                unsigned char *dst = b ? s.q_stage2.p : s.q_stage.p;
+                if (cudaStreamWaitEvent(s.copy_stream, s0.ev_copied[b], 0) != cudaSuccess ||
+                    cudaMemcpyPeerAsync(dst, s.device, dst0, s0.device, qbytes, s.copy_stream) != cudaSuccess ||
+                    cudaEventRecord(s.ev_copied[b], s.copy_stream) != cudaSuccess)
+                    rc = B200KNN_ECUDA;
+            }
+            if (rc != B200KNN_OK) {
+                up_err = g_last_error.empty() ? std::string("query upload / broadcast failed") : g_last_error;
+                up_rc.store(rc);
+                uploaded.store(nchunks, std::memory_order_release);
+                return;
+            }
+            uploaded.store(c + 1, std::memory_order_release);
+        }
+    });
+    int rc_all = B200KNN_OK;
+    std::string err_all;
+    for (int64_t c = 0; c < nchunks && rc_all == B200KNN_OK; c++) {
+        const int b = static_cast<int>(c & 1);
+        const int64_t q0 = chunks[c].first, cq = chunks[c].second;
+        while (uploaded.load(std::memory_order_acquire) < c + 1) std::this_thread::yield();
+        if (up_rc.load() != B200KNN_OK) break;
+        std::vector<int> rcs(lists, B200KNN_OK);
+        std::vector<std::string> errs(lists);
+        auto work = [&](int i) {
+            Shard &s = ix->shards[active[i]];
+            int rc = B200KNN_OK;
+            cudaSetDevice(s.device);
+            if (cudaStreamWaitEvent(s.stream, s.ev_copied[b], 0) != cudaSuccess) rc = fail(B200KNN_ECUDA, "cudaStreamWaitEvent failed");
+            unsigned char *qp = b ? s.q_stage2.p : s.q_stage.p;
+            if (rc == B200KNN_OK) rc = s.query_device(qp, dtype, cq, dim, dim, ix->kp, kk, flags, s.out_idx.p, s.out_dist.p);
+            if (rc == B200KNN_OK) {
+                cudaError_t e = cudaMemcpyPeerAsync(ix->g_idx.p + static_cast<size_t>(i) * cq * kk, s0.device, s.out_idx.p, s.device,
+                                                    static_cast<size_t>(cq) * kk * sizeof(int32_t), s.stream);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyPeerAsync(ix->g_dist.p + static_cast<size_t>(i) * cq * kk, s0.device, s.out_dist.p, s.device,
+                                            static_cast<size_t>(cq) * kk * sizeof(double), s.stream);
+                if (e == cudaSuccess) e = cudaEventRecord(done[i], s.stream);
+                if (e != cudaSuccess) rc = fail(B200KNN_ECUDA, "gathering shard results failed: %s", cudaGetErrorString(e));
+            }
+            rcs[i] = rc;
+            if (rc != B200KNN_OK) errs[i] = g_last_error;
+        };
+        std::vector<std::thread> th;
+        for (int i = 1; i < lists; i++) th.emplace_back(work, i);
+        work(0);
+        for (auto &t : th) t.join();
+        for (int i = 0; i < lists; i++)
+            if (rcs[i] != B200KNN_OK && rc_all == B200KNN_OK) { rc_all = rcs[i]; err_all = errs[i]; }
+        if (rc_all != B200KNN_OK) break;
+        cudaSetDevice(s0.device);
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < lists && e == cudaSuccess; i++) e = cudaStreamWaitEvent(s0.stream, done[i], 0);
+        if (e == cudaSuccess) {
+            int rm = b200knn_merge_topk_device(ix->g_idx.p, ix->g_dist.p, lists, cq, kk, s0.out_idx.p, s0.out_dist.p, s0.stream);
+            if (rm != B200KNN_OK) { rc_all = rm; err_all = g_last_error; break; }
+            s0.stats.kernel_launches++;
+            e = cudaMemcpyAsync(out_idx + q0 * kk, s0.out_idx.p, static_cast<size_t>(cq) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s0.stream);
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_dist + q0 * kk, s0.out_dist.p, static_cast<size_t>(cq) * kk * sizeof(double), cudaMemcpyDeviceToHost, s0.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s0.stream);      // also: every shard is done with stage buffer b
+        if (e != cudaSuccess) { rc_all = B200KNN_ECUDA; err_all = std::string("multi-device merge failed: ") + cudaGetErrorString(e); break; }
+        consumed.store(c + 1, std::memory_order_release);
+    }
+    consumed.store(nchunks + 2, std::memory_order_release);   // never leave the uploader waiting
+    uploader.join();
+    for (auto ev : done) cudaEventDestroy(ev);
+    if (up_rc.load() != B200KNN_OK) return fail(up_rc.load(), "%s", up_err.c_str());
+    if (rc_all != B200KNN_OK) return fail(rc_all, "%s", err_all.c_str());
     return B200KNN_OK;
 }
 

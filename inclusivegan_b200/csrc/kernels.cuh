@@ -568,6 +568,35 @@ __device__ __forceinline__ float float_from_order_bits(uint32_t b) {
     return __uint_as_float((b & 0x80000000u) ? (b & 0x7fffffffu) : ~b);
 }
 
+// Canonical exact squared distance: ONE summation order for every code path that emits a distance (first-pass re-rank,
+// second-pass list re-rank, ball membership), so a result does not depend on how the pool is sharded, on the batch
+// size, or on whether the query needed the second pass.  128 virtual lanes: lane v sums the elements e = v + 128 i,
+// even i into one accumulator and odd i into another; xor-shuffle tree inside each of the 4 warps; the 4 warp sums are
+// added in order.  Executed by threads 0..127 of the block; the value is returned to every thread.
+template <typename TX, typename TQ>
+__device__ __forceinline__ double canon_d2(const TX *__restrict__ xr, const TQ *__restrict__ qr, int dim, int tid, double *partial4) {
+    if (tid < 128) {
+        double a0 = 0.0, a1 = 0.0;
+        int e = tid;
+        for (; e + 128 < dim; e += 256) {
+            const double d0 = static_cast<double>(qr[e]) - static_cast<double>(xr[e]);
+            const double d1 = static_cast<double>(qr[e + 128]) - static_cast<double>(xr[e + 128]);
+            a0 = fma(d0, d0, a0);
+            a1 = fma(d1, d1, a1);
+        }
+        if (e < dim) {
+            const double d0 = static_cast<double>(qr[e]) - static_cast<double>(xr[e]);
+            a0 = fma(d0, d0, a0);
+        }
+        const double w = warp_sum(a0 + a1);
+        if ((tid & 31) == 0) partial4[tid >> 5] = w;
+    }
+    __syncthreads();
+    const double tot = ((partial4[0] + partial4[1]) + partial4[2]) + partial4[3];
+    __syncthreads();
+    return tot;
+}
+
 struct RerankParams {
     const float *cand_s;
     const int *cand_i;
@@ -677,11 +706,12 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
     const int warp = tid >> 5, lane = tid & 31;
     const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
     constexpr int RQ = 24;                      // dims per thread held in registers (128 threads x 24 = 3072)
-    constexpr int nth = NT;                     // 128, or 1024 when many shortlists have to be merged (few queries)
-    __shared__ double partial[32];
+    constexpr int nth = 128;                    // the canonical 128 lanes (see canon_d2); extra threads of the 1024-thread
+    const bool act = tid < nth;                 // flavour only help with the merge sort above
+    __shared__ double partial[4];
     double qreg[RQ];
     const bool fits = p.dim <= RQ * nth;
-    if (fits) {
+    if (fits && act) {
         // raw loads first, conversions after: a float->double conversion placed right behind its load would make the
         // in-order warp wait for that load before issuing the next one (24 serialized DRAM round trips)
         TQ qraw[RQ];
@@ -702,8 +732,13 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
             continue;
         }
         const TX *xr = x + static_cast<int64_t>(static_cast<uint32_t>(key)) * p.ld_x;
-        double a0 = 0.0, a1 = 0.0;
-        if (fits) {
+        if (!fits) {
+            const double tot = canon_d2(xr, qr, p.dim, tid, partial);
+            if (tid == 0) d2s[c] = tot;
+            continue;
+        }
+        if (act) {                               // same order as canon_d2, query slice already in registers
+            double a0 = 0.0, a1 = 0.0;
             TX xraw[RQ];
 #pragma unroll
             for (int i = 0; i < RQ; i++) {
@@ -718,27 +753,11 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
                 a0 = fma(d0, d0, a0);
                 a1 = fma(d1, d1, a1);
             }
-        } else {
-            int e = tid;
-            for (; e + nth < p.dim; e += 2 * nth) {
-                const double d0 = static_cast<double>(qr[e]) - static_cast<double>(xr[e]);
-                const double d1 = static_cast<double>(qr[e + nth]) - static_cast<double>(xr[e + nth]);
-                a0 = fma(d0, d0, a0);
-                a1 = fma(d1, d1, a1);
-            }
-            if (e < p.dim) {
-                const double d0 = static_cast<double>(qr[e]) - static_cast<double>(xr[e]);
-                a0 = fma(d0, d0, a0);
-            }
+            const double w = warp_sum(a0 + a1);
+            if (lane == 0) partial[warp] = w;
         }
-        const double w = warp_sum(a0 + a1);
-        if (lane == 0) partial[warp] = w;
         __syncthreads();
-        if (tid == 0) {
-            double tot = 0.0;
-            for (int i = 0; i < (nth >> 5); i++) tot += partial[i];
-            d2s[c] = tot;
-        }
+        if (tid == 0) d2s[c] = ((partial[0] + partial[1]) + partial[2]) + partial[3];
         __syncthreads();
     }
     __syncthreads();
@@ -843,16 +862,11 @@ rerank_collect_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, con
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
-    for (int c = warp; c < cnt; c += 8) {
+    __shared__ double partial[4];
+    for (int c = 0; c < cnt; c++) {
         const int j = p.coll_idx[static_cast<int64_t>(slot) * COLLECT_CAP + c];
-        const TX *xr = x + static_cast<int64_t>(j) * p.ld_x;
-        double a0 = 0.0;
-        for (int e = lane; e < p.dim; e += 32) {
-            const double d0 = static_cast<double>(qr[e]) - static_cast<double>(xr[e]);
-            a0 = fma(d0, d0, a0);
-        }
-        a0 = warp_sum(a0);
-        if (lane == 0) { d2[c] = a0; idx[c] = j; }
+        const double a0 = canon_d2(x + static_cast<int64_t>(j) * p.ld_x, qr, p.dim, threadIdx.x, partial);
+        if (threadIdx.x == 0) { d2[c] = a0; idx[c] = j; }
     }
     if (threadIdx.x == 0) { last_d_s = -1.0; last_i_s = -1; }
     __syncthreads();
@@ -1091,23 +1105,8 @@ ball_member_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const 
     const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
     for (int c = 0; c < cnt; c++) {
         const int j = p.coll_idx[static_cast<int64_t>(q) * p.cap + c];
-        const TX *xr = x + static_cast<int64_t>(j) * p.ld_x;
-        double a0 = 0.0, a1 = 0.0;
-        int e = tid;
-        for (; e + 128 < p.dim; e += 256) {
-            const double d0 = static_cast<double>(qr[e]) - static_cast<double>(xr[e]);
-            const double d1 = static_cast<double>(qr[e + 128]) - static_cast<double>(xr[e + 128]);
-            a0 = fma(d0, d0, a0);
-            a1 = fma(d1, d1, a1);
-        }
-        if (e < p.dim) {
-            const double d0 = static_cast<double>(qr[e]) - static_cast<double>(xr[e]);
-            a0 = fma(d0, d0, a0);
-        }
-        const double w = warp_sum(a0 + a1);
-        if (lane == 0) partial[warp] = w;
-        __syncthreads();
-        if (tid == 0 && (partial[0] + partial[1]) + (partial[2] + partial[3]) <= p.radius2[j]) found_s = 1;
+        const double dd = canon_d2(x + static_cast<int64_t>(j) * p.ld_x, qr, p.dim, tid, partial);
+        if (tid == 0 && dd <= p.radius2[j]) found_s = 1;
         __syncthreads();
         if (found_s) break;
     }
