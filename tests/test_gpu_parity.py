@@ -440,15 +440,15 @@ def test_results_do_not_depend_on_batching_or_path(lib):
     one big call, in 24-row calls (different kernel flavour, 1024-thread re-rank), or via the second pass gives
     bit-identical distances and indices."""
     from inclusivegan_b200 import DCI
-    x, y = make("gauss", 30000, 600, 1024, seed=90)         # enough uncertified rows to exercise the second pass
-    db = DCI(1024)
+    x, y = make("gauss", 4000, 600, 4096, seed=90)          # high-d i.i.d.: a good share of rows needs the second pass
+    db = DCI(4096)
     db.add(x)
-    i_all, d_all = db.query_arrays(y, 3)
+    i_all, d_all = db.query_arrays(y, 10)
     assert db.stats()["uncertified"] > 0
-    i_parts = np.concatenate([db.query_arrays(y[s:s + 24], 3)[0] for s in range(0, 600, 24)])
-    d_parts = np.concatenate([db.query_arrays(y[s:s + 24], 3)[1] for s in range(0, 600, 24)])
+    i_parts = np.concatenate([db.query_arrays(y[s:s + 24], 10)[0] for s in range(0, 600, 24)])
+    d_parts = np.concatenate([db.query_arrays(y[s:s + 24], 10)[1] for s in range(0, 600, 24)])
     assert np.array_equal(i_all, i_parts) and np.array_equal(d_all, d_parts)
-    i_nc, d_nc = db.query_arrays(y, 3, flags=FLAG_NO_CERTIFY)
+    i_nc, d_nc = db.query_arrays(y, 10, flags=FLAG_NO_CERTIFY)
     certified_rows = np.all(i_nc == i_all, axis=1)
-    assert certified_rows.mean() > 0.5
+    assert certified_rows.mean() > 0.2
     assert np.array_equal(d_nc[certified_rows], d_all[certified_rows])
