@@ -49,16 +49,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// non-blocking probe (try_wait may suspend the thread for a hardware time slice when the phase is not complete)
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
 // Bounded wait: a pipeline bug traps (the launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ uint64_t global_timer_ns() {
     uint64_t t;
