@@ -95,6 +95,12 @@ int b200knn_add(b200knn_index *index, const void *data, int dtype, int64_t n, in
 int b200knn_query(b200knn_index *index, const void *query, int dtype, int64_t nq, int64_t ld, int k,
                   unsigned flags, int32_t *out_idx, double *out_dist, int *out_kk);
 
+/* Self-kNN: every pool row queried against the pool it belongs to (row i's own entry, distance 0, comes first unless
+ * duplicates tie).  The reference's precision/recall metric does exactly this to get the k-th neighbour radii
+ * (metrics/precision_recall.py:74-90); the rows, their BF16 copies and norms are already on the device from add(), so
+ * nothing is uploaded or converted.  out_idx / out_dist: HOST, num_points x kk.  Single-device handles. */
+int b200knn_query_self(b200knn_index *index, int k, unsigned flags, int32_t *out_idx, double *out_dist, int *out_kk);
+
 /* Ball membership for the k-NN precision/recall metric (reference metrics/precision_recall.py:96-134, the
  * `np.any(distance_batch[..., None] <= self.D, axis=1)` test): out_member[i] = 1 iff query row i lies inside at least
  * one ball B(x_j, sqrt(radius2[j])) around a pool row (squared Euclidean distance <= radius2[j]; the reference works on

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <utility>
@@ -106,6 +107,21 @@ struct DevBuf {   // grow-only device buffer
     }
 };
 
+// Pinned staging ring for pageable host sources, one per device for the whole process: page-locking 96 MB costs
+// 30-100 ms, too much to repeat for every handle (the precision/recall metric builds two indexes per evaluation).
+struct PinnedRing {
+    static constexpr int RING = 3;
+    static constexpr size_t BYTES = 32u << 20;
+    unsigned char *buf[RING] = {nullptr, nullptr, nullptr};
+    cudaEvent_t done[RING] = {nullptr, nullptr, nullptr};
+    bool used[RING] = {false, false, false};
+    int next = 0;
+    std::mutex mu;
+};
+PinnedRing g_rings[64];
+
+struct QuerySide { const __nv_bfloat16 *bf; const float *norm; const float *err; };
+
 enum Kind { K_CONVERT = 0, K_DISTANCE = 1, K_RERANK = 2, K_SCAN = 3, K_NKINDS = 4 };
 
 struct Shard {
@@ -157,18 +173,12 @@ struct Shard {
     DevBuf<unsigned char> q_stage;   // host API: device copy of the caller's query rows
     DevBuf<unsigned char> q_stage2;  // second buffer: the upload of chunk i+1 overlaps the compute of chunk i
     cudaStream_t copy_stream = nullptr;
-    // pageable host sources are staged through a ring of pinned buffers filled by several host threads
-    static constexpr int RING = 3;
-    static constexpr size_t RING_BYTES = 32u << 20;
-    unsigned char *ring[RING] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ring_done[RING] = {nullptr, nullptr, nullptr};
-    bool ring_used[RING] = {false, false, false};
-    int ring_next = 0;
     int copy_threads = 8;            // $B200KNN_COPY_THREADS
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     DevBuf<int32_t> out_idx;
     DevBuf<double> out_dist;
     int *h_count = nullptr;          // pinned
+    const __nv_bfloat16 *cur_q_bf = nullptr;   // BF16 query rows of the tensor pass in flight (second pass gathers from them)
     int64_t last_nq = 0;             // geometry of the last tensor pass (b200knn_debug_shortlists)
     int last_slots = 0, last_c = 0;
 
@@ -295,12 +305,6 @@ struct Shard {
         if (h_count) cudaFreeHost(h_count);
         if (own_stream) cudaStreamDestroy(own_stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
-        for (int i = 0; i < RING; i++) {
-            if (ring[i]) cudaFreeHost(ring[i]);
-            if (ring_done[i]) cudaEventDestroy(ring_done[i]);
-            ring[i] = nullptr;
-            ring_done[i] = nullptr;
-        }
         for (int i = 0; i < 2; i++) {
             if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
             if (ev_consumed[i]) cudaEventDestroy(ev_consumed[i]);
@@ -324,12 +328,15 @@ struct Shard {
             else CU_TRY(cudaMemcpy2DAsync(dst, row_bytes, src, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, st));
             return B200KNN_OK;
         }
-        for (int i = 0; i < RING; i++) {
-            if (!ring[i]) {
-                CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&ring[i]), RING_BYTES));
-                CU_TRY(cudaEventCreateWithFlags(&ring_done[i], cudaEventDisableTiming));
+        PinnedRing &rg = g_rings[device & 63];
+        std::lock_guard<std::mutex> lock(rg.mu);     // one upload at a time per device
+        for (int i = 0; i < PinnedRing::RING; i++) {
+            if (!rg.buf[i]) {
+                CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&rg.buf[i]), PinnedRing::BYTES));
+                CU_TRY(cudaEventCreateWithFlags(&rg.done[i], cudaEventDisableTiming));
             }
         }
+        const size_t RING_BYTES = PinnedRing::BYTES;
         const int64_t piece_rows = std::max<int64_t>(1, static_cast<int64_t>(RING_BYTES / row_bytes));
         if (row_bytes > RING_BYTES) {   // absurdly wide rows: let the driver stage them
             CU_TRY(cudaMemcpy2DAsync(dst, row_bytes, src, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, st));
@@ -337,10 +344,10 @@ struct Shard {
         }
         for (int64_t r0 = 0; r0 < rows; r0 += piece_rows) {
             const int64_t pr = std::min(piece_rows, rows - r0);
-            const int slot = ring_next;
-            ring_next = (ring_next + 1) % RING;
-            if (ring_used[slot]) CU_TRY(cudaEventSynchronize(ring_done[slot]));   // its previous DMA has drained
-            unsigned char *buf = ring[slot];
+            const int slot = rg.next;
+            rg.next = (rg.next + 1) % PinnedRing::RING;
+            if (rg.used[slot]) CU_TRY(cudaEventSynchronize(rg.done[slot]));   // its previous DMA has drained
+            unsigned char *buf = rg.buf[slot];
             const char *sp = src + static_cast<size_t>(r0) * src_pitch;
             const int nt = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(copy_threads, pr), static_cast<int64_t>(pr * row_bytes) >> 21)));
             auto work = [&](int t) {
@@ -362,8 +369,8 @@ struct Shard {
             }
             CU_TRY(cudaMemcpyAsync(static_cast<char *>(dst) + static_cast<size_t>(r0) * row_bytes, buf, static_cast<size_t>(pr) * row_bytes,
                                    cudaMemcpyHostToDevice, st));
-            CU_TRY(cudaEventRecord(ring_done[slot], st));
-            ring_used[slot] = true;
+            CU_TRY(cudaEventRecord(rg.done[slot], st));
+            rg.used[slot] = true;
         }
         return B200KNN_OK;
     }
@@ -650,7 +657,7 @@ struct Shard {
         TRY(overflow_list.ensure(nun));
         prof_begin(K_SCAN);
         gather_rows_kernel<<<std::min<int64_t>(num_sms * 4, (static_cast<int64_t>(nun) * (kp / 8) + 255) / 256), 256, 0, stream>>>(
-            q_bf.p, uncert_list.p, nun, kp, q_bf2.p);
+            cur_q_bf, uncert_list.p, nun, kp, q_bf2.p);
         prof_end();
         CU_TRY(cudaGetLastError());
         CU_TRY(cudaMemsetAsync(coll_count.p, 0, static_cast<size_t>(nun) * sizeof(int), stream));
@@ -706,13 +713,22 @@ struct Shard {
 
     template <int C>
     int tensor_pass(const void *d_query, int q_dtype, int64_t nq, int64_t ld_q, int dim, int kp, int kk, unsigned flags,
-                    int32_t *d_out_idx, double *d_out_dist) {
-        TRY(q_bf.ensure(static_cast<size_t>(nq) * kp));
-        TRY(qnorm_bf.ensure(nq));
-        TRY(q_err.ensure(nq));
-        TRY(launch_convert(d_query, q_dtype, nq, ld_q, dim, kp, q_bf.p, qnorm_bf.p, q_err.p, scalars.p + 2));
+                    int32_t *d_out_idx, double *d_out_dist, const QuerySide *pre = nullptr) {
+        // query side: BF16 rows + norms, either converted now or (self-kNN) the pool's own, already converted by add()
+        const __nv_bfloat16 *qb;
+        const float *qn, *qe;
+        if (pre) {
+            qb = pre->bf; qn = pre->norm; qe = pre->err;
+        } else {
+            TRY(q_bf.ensure(static_cast<size_t>(nq) * kp));
+            TRY(qnorm_bf.ensure(nq));
+            TRY(q_err.ensure(nq));
+            TRY(launch_convert(d_query, q_dtype, nq, ld_q, dim, kp, q_bf.p, qnorm_bf.p, q_err.p, scalars.p + 2));
+            qb = q_bf.p; qn = qnorm_bf.p; qe = q_err.p;
+        }
+        cur_q_bf = qb;
         CUtensorMap tmap_q;
-        TRY(make_tmap(&tmap_q, q_bf.p, nq, kp, BM));
+        TRY(make_tmap(&tmap_q, qb, nq, kp, BM));
         const bool cached = sched1.matches(nq, n, kp, MAX_KEYS / C);
         if (!cached) TRY(plan(sched1, nq, kp, MAX_KEYS / C));
         const Sched &s = sched1;
@@ -745,8 +761,8 @@ struct Shard {
         rp.kk = kk;
         rp.index_base = index_base;
         rp.flags = flags;
-        rp.qnorm_bf = qnorm_bf.p;
-        rp.q_err = q_err.p;
+        rp.qnorm_bf = qn;
+        rp.q_err = qe;
         rp.max_xnorm_bf_bits = scalars.p;
         rp.max_x_err_bits = scalars.p + 1;
         rp.kp = kp;
@@ -873,16 +889,16 @@ struct Shard {
 
     // queries and outputs on this device; nq bounded by the caller's chunking
     int query_device(const void *d_query, int q_dtype, int64_t nq, int64_t ld_q, int dim, int kp, int k, unsigned flags,
-                     int32_t *d_out_idx, double *d_out_dist) {
+                     int32_t *d_out_idx, double *d_out_dist, const QuerySide *pre = nullptr) {
         if (nq <= 0) return B200KNN_OK;
         CU_TRY(cudaSetDevice(device));
         const int kk = static_cast<int>(std::min<int64_t>(k, n));
         stats.queries += nq;
         if (kk > 32 || (flags & B200KNN_FLAG_FORCE_SCAN))
             return scan(d_query, q_dtype, ld_q, nullptr, static_cast<int>(nq), dim, kk, flags, d_out_idx, d_out_dist);
-        if (kk <= 4) return tensor_pass<16>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist);
-        if (kk <= 16) return tensor_pass<32>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist);
-        return tensor_pass<64>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist);
+        if (kk <= 4) return tensor_pass<16>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist, pre);
+        if (kk <= 16) return tensor_pass<32>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist, pre);
+        return tensor_pass<64>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist, pre);
     }
 };
 
@@ -1277,6 +1293,32 @@ int b200knn_query_device(b200knn_index *ix, const void *d_query, int dtype, int6
         TRY(s.query_device(static_cast<const char *>(d_query) + static_cast<size_t>(q0) * ld * esz, dtype, cq, ld, ix->dim, ix->kp, k, flags,
                            d_out_idx + q0 * kk, d_out_dist + q0 * kk));
     }
+    return B200KNN_OK;
+}
+
+int b200knn_query_self(b200knn_index *ix, int k, unsigned flags, int32_t *out_idx, double *out_dist, int *out_kk) {
+    if (!ix) return fail(B200KNN_EINVAL, "index is NULL");
+    if (k <= 0) return fail(B200KNN_EINVAL, "k must be positive (got %d)", k);
+    if (ix->n_total <= 0) return fail(B200KNN_ESTATE, "query on an empty index");
+    if (ix->shards.size() != 1) return fail(B200KNN_EINVAL, "query_self is only valid for single-device handles");
+    if (!out_idx || !out_dist) return fail(B200KNN_EINVAL, "output buffer is NULL");
+    Shard &s = ix->shards[0];
+    const int kk = static_cast<int>(std::min<int64_t>(k, s.n));
+    if (out_kk) *out_kk = kk;
+    CU_TRY(cudaSetDevice(s.device));
+    TRY(s.out_idx.ensure(static_cast<size_t>(s.n) * kk));
+    TRY(s.out_dist.ensure(static_cast<size_t>(s.n) * kk));
+    const size_t esz = s.x_dtype == B200KNN_F64 ? 8 : 4;
+    for (int64_t q0 = 0; q0 < s.n; q0 += QUERY_CHUNK) {
+        const int64_t cq = std::min(QUERY_CHUNK, s.n - q0);
+        const QuerySide pre{s.x_bf.p + static_cast<size_t>(q0) * ix->kp, s.xnorm_bf.p + q0, s.x_err.p + q0};
+        TRY(s.query_device(static_cast<const char *>(s.x_raw) + static_cast<size_t>(q0) * s.ld_x * esz, s.x_dtype, cq, s.ld_x, ix->dim, ix->kp, k,
+                           flags, s.out_idx.p + q0 * kk, s.out_dist.p + q0 * kk, &pre));
+    }
+    CU_TRY(cudaMemcpyAsync(out_idx, s.out_idx.p, static_cast<size_t>(s.n) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+    CU_TRY(cudaMemcpyAsync(out_dist, s.out_dist.p, static_cast<size_t>(s.n) * kk * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CU_TRY(cudaStreamSynchronize(s.stream));
+    if (s.index_base != 0) { /* indices already carry index_base */ }
     return B200KNN_OK;
 }
 

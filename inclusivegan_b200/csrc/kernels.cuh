@@ -597,6 +597,30 @@ __device__ __forceinline__ double canon_d2(const TX *__restrict__ xr, const TQ *
     return tot;
 }
 
+// The same canonical sum computed by ONE warp (each lane plays the virtual lanes lane, lane+32, lane+64, lane+96):
+// bit-identical to canon_d2, no block barrier — lets the warps of a block work on different candidates.
+template <typename TX, typename TQ>
+__device__ __forceinline__ double canon_d2_warp(const TX *__restrict__ xr, const TQ *__restrict__ qr, int dim, int lane) {
+    double a[4][2] = {};
+    for (int base = 0; base < dim; base += 256) {
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const int e0 = base + lane + 32 * g, e1 = e0 + 128;
+            if (e0 < dim) {
+                const double d0 = static_cast<double>(qr[e0]) - static_cast<double>(xr[e0]);
+                a[g][0] = fma(d0, d0, a[g][0]);
+            }
+            if (e1 < dim) {
+                const double d1 = static_cast<double>(qr[e1]) - static_cast<double>(xr[e1]);
+                a[g][1] = fma(d1, d1, a[g][1]);
+            }
+        }
+    }
+    const double w0 = warp_sum(a[0][0] + a[0][1]), w1 = warp_sum(a[1][0] + a[1][1]);
+    const double w2 = warp_sum(a[2][0] + a[2][1]), w3 = warp_sum(a[3][0] + a[3][1]);
+    return ((w0 + w1) + w2) + w3;
+}
+
 struct RerankParams {
     const float *cand_s;
     const int *cand_i;
@@ -862,11 +886,10 @@ rerank_collect_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, con
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
-    __shared__ double partial[4];
-    for (int c = 0; c < cnt; c++) {
+    for (int c = warp; c < cnt; c += 8) {       // one candidate per warp, canonical summation order
         const int j = p.coll_idx[static_cast<int64_t>(slot) * COLLECT_CAP + c];
-        const double a0 = canon_d2(x + static_cast<int64_t>(j) * p.ld_x, qr, p.dim, threadIdx.x, partial);
-        if (threadIdx.x == 0) { d2[c] = a0; idx[c] = j; }
+        const double a0 = canon_d2_warp(x + static_cast<int64_t>(j) * p.ld_x, qr, p.dim, lane);
+        if (lane == 0) { d2[c] = a0; idx[c] = j; }
     }
     if (threadIdx.x == 0) { last_d_s = -1.0; last_i_s = -1; }
     __syncthreads();
@@ -1094,7 +1117,6 @@ struct MemberParams {
 template <typename TX, typename TQ>
 __global__ void __launch_bounds__(128)
 ball_member_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const MemberParams p) {
-    __shared__ double partial[4];
     __shared__ int found_s;
     const int q = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1103,10 +1125,14 @@ ball_member_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const 
     if (tid == 0) found_s = 0;
     __syncthreads();
     const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
-    for (int c = 0; c < cnt; c++) {
-        const int j = p.coll_idx[static_cast<int64_t>(q) * p.cap + c];
-        const double dd = canon_d2(x + static_cast<int64_t>(j) * p.ld_x, qr, p.dim, tid, partial);
-        if (tid == 0 && dd <= p.radius2[j]) found_s = 1;
+    // four candidates at a time (one per warp, canonical summation order), stop at the first witness
+    for (int c0 = 0; c0 < cnt; c0 += 4) {
+        const int c = c0 + warp;
+        if (c < cnt) {
+            const int j = p.coll_idx[static_cast<int64_t>(q) * p.cap + c];
+            const double dd = canon_d2_warp(x + static_cast<int64_t>(j) * p.ld_x, qr, p.dim, lane);
+            if (lane == 0 && dd <= p.radius2[j]) found_s = 1;
+        }
         __syncthreads();
         if (found_s) break;
     }

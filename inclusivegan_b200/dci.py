@@ -92,6 +92,8 @@ def load_library(path=None):
     lib.b200knn_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.b200knn_reset_stats.restype = i32
     lib.b200knn_reset_stats.argtypes = [vp]
+    lib.b200knn_query_self.restype = i32
+    lib.b200knn_query_self.argtypes = [vp, i32, u32, vp, vp, ctypes.POINTER(i32)]
     lib.b200knn_exchange_create.restype = i32
     lib.b200knn_exchange_create.argtypes = [i32, i32, i32, i64, i32, ctypes.POINTER(vp)]
     lib.b200knn_exchange_handle.restype = i32
@@ -434,6 +436,23 @@ class DCI(object):
             idx = self._orig_indices[idx].astype(np.int32, copy=False)
         elif self._offset:
             idx += np.int32(self._offset)
+        return idx, dist
+
+    def query_self_arrays(self, num_neighbours, squared=False):
+        """Extension: kNN of every indexed row among the indexed rows (itself first), without re-uploading them
+        (b200knn_query_self).  Falls back to a plain query of the original array on multi-device handles."""
+        _require_positive_int(num_neighbours)
+        n = self.num_points
+        kk = min(num_neighbours, n)
+        if self._orig_indices is not None or self._offset:
+            raise ValueError("query_self_arrays needs an index built from a whole array (indices=None)")
+        idx = np.empty((n, kk), dtype=np.int32)
+        dist = np.empty((n, kk), dtype=np.float64)
+        rc = self._lib.b200knn_query_self(self._handle, int(num_neighbours), FLAG_SQUARED if squared else 0, idx.ctypes.data,
+                                          dist.ctypes.data, None)
+        if rc == -1 and b"single-device" in self._lib.b200knn_last_error():
+            return self.query_arrays(self._array, num_neighbours, squared=squared)
+        _check(rc)
         return idx, dist
 
     def ball_membership(self, query, radius2):

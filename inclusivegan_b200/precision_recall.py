@@ -44,7 +44,7 @@ class ManifoldEstimator(object):
         # k-th nearest neighbour of each sample among the samples themselves: index 0 is the sample itself
         # (precision_recall.py:73-90, `np.partition(..., seq)[:, nhood_sizes]` with seq = 0..max(k))
         kmax = max(self.nhood_sizes) + 1
-        _, d2 = self._index.query_arrays(features, min(kmax, features.shape[0]), squared=True)
+        _, d2 = self._index.query_self_arrays(min(kmax, features.shape[0]), squared=True)   # rows are already on the device
         cols = [min(k, d2.shape[1] - 1) for k in self.nhood_sizes]
         self.D = np.ascontiguousarray(d2[:, cols])                       # float64 (reference: float16)
         if clamp_to_percentile is not None:                              # precision_recall.py:92-94

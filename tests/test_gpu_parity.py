@@ -120,6 +120,18 @@ def test_squared_distances(lib):
     check(db, x, y, 4, squared=True)
 
 
+def test_query_self_equals_querying_the_pool_rows(lib):
+    """b200knn_query_self (pool rows as queries, nothing re-uploaded or re-converted) == query(pool) bit for bit."""
+    from inclusivegan_b200 import DCI
+    x, _ = make("relu", 40000, 1, 384, seed=18, dtype=np.float32)         # > one device pass (32768 rows)
+    db = DCI(384)
+    db.add(x)
+    i1, d1 = db.query_self_arrays(4, squared=True)
+    i2, d2 = db.query_arrays(x, 4, squared=True)
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    assert np.array_equal(i1[:, 0], np.arange(40000)) and np.all(d1[:, 0] == 0.0)
+
+
 def test_self_knn_radius(lib):
     """precision_recall.py:74-90 pattern: k+1 smallest incl. self; self must be rank 0 at distance 0."""
     from inclusivegan_b200 import DCI
