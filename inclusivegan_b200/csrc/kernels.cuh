@@ -603,17 +603,25 @@ template <typename TX, typename TQ>
 __device__ __forceinline__ double canon_d2_warp(const TX *__restrict__ xr, const TQ *__restrict__ qr, int dim, int lane) {
     double a[4][2] = {};
     for (int base = 0; base < dim; base += 256) {
+        // all sixteen loads of the step first (see keep()), then the arithmetic
+        TQ qv[8];
+        TX xv[8];
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             const int e0 = base + lane + 32 * g, e1 = e0 + 128;
-            if (e0 < dim) {
-                const double d0 = static_cast<double>(qr[e0]) - static_cast<double>(xr[e0]);
-                a[g][0] = fma(d0, d0, a[g][0]);
-            }
-            if (e1 < dim) {
-                const double d1 = static_cast<double>(qr[e1]) - static_cast<double>(xr[e1]);
-                a[g][1] = fma(d1, d1, a[g][1]);
-            }
+            qv[2 * g] = (e0 < dim) ? qr[e0] : TQ(0);
+            xv[2 * g] = (e0 < dim) ? xr[e0] : TX(0);
+            qv[2 * g + 1] = (e1 < dim) ? qr[e1] : TQ(0);
+            xv[2 * g + 1] = (e1 < dim) ? xr[e1] : TX(0);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) { keep(qv[i]); keep(xv[i]); }
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const double d0 = static_cast<double>(qv[2 * g]) - static_cast<double>(xv[2 * g]);
+            const double d1 = static_cast<double>(qv[2 * g + 1]) - static_cast<double>(xv[2 * g + 1]);
+            a[g][0] = fma(d0, d0, a[g][0]);      // out-of-range elements are 0 - 0: they add nothing
+            a[g][1] = fma(d1, d1, a[g][1]);
         }
     }
     const double w0 = warp_sum(a[0][0] + a[0][1]), w1 = warp_sum(a[1][0] + a[1][1]);
@@ -670,6 +678,71 @@ __device__ __forceinline__ ErrModel make_err_model(const RerankParams &p, int q)
     m.eps_acc = (K + 8.0) * 2.4e-7 * sqrt(m.qn_bf * xn_bf) * 1.001 + (K / 16.0 + 8.0) * 1.2e-7 * (xn_bf + m.qn_bf);
     m.eta = (static_cast<double>(p.q_err[q]) + static_cast<double>(__uint_as_float(*p.max_x_err_bits))) * (1.0 + 1e-6) + 1e-30;
     return m;
+}
+
+// Final step of a re-rank, executed by ONE full warp: rank the C exact squared distances by (d2, row), emit the best kk,
+// and certify the answer (or queue the query for the second pass).  keysC: the C best-scored shortlist entries,
+// ascending by (score, row); d2s: their exact squared distances (DBL_MAX = pruned / empty).
+template <int C>
+__device__ __forceinline__ void rerank_finish(const RerankParams &p, int q, const unsigned long long *keys, const double *d2s, int lane) {
+    // rank the exact distances by (d2, index); each lane owns candidates lane, lane + 32 (C <= 64)
+    constexpr int H = (C + 31) / 32;
+    double myd[H];
+    uint32_t myi[H];
+    int rank[H];
+#pragma unroll
+    for (int h = 0; h < H; h++) {
+        const int c = lane + 32 * h;
+        myd[h] = (c < C) ? d2s[c] : DBL_MAX;
+        myi[h] = (c < C) ? static_cast<uint32_t>(keys[c]) : 0xffffffffu;
+        rank[h] = 0;
+    }
+#pragma unroll
+    for (int g = 0; g < H; g++) {
+#pragma unroll
+        for (int o = 0; o < 32; o++) {
+            const double od = __shfl_sync(0xffffffffu, myd[g], o);
+            const uint32_t oi = __shfl_sync(0xffffffffu, myi[g], o);
+#pragma unroll
+            for (int h = 0; h < H; h++) rank[h] += (od < myd[h] || (od == myd[h] && oi < myi[h])) ? 1 : 0;
+        }
+    }
+    double dk2 = DBL_MAX;
+    unsigned mk = 0;
+#pragma unroll
+    for (int h = 0; h < H; h++) {
+        const bool valid = (lane + 32 * h) < C;
+        if (valid && rank[h] < p.kk) {
+            p.out_idx[static_cast<int64_t>(q) * p.kk + rank[h]] = static_cast<int32_t>(p.index_base + myi[h]);
+            p.out_dist[static_cast<int64_t>(q) * p.kk + rank[h]] = (p.flags & 1u) ? myd[h] : sqrt(myd[h]);
+        }
+        // k-th exact distance (rank kk-1), broadcast
+        const unsigned mh = __ballot_sync(0xffffffffu, valid && rank[h] == p.kk - 1);
+        const double dh = __shfl_sync(0xffffffffu, myd[h], mh ? (__ffs(mh) - 1) : 0);
+        if (mh) { dk2 = dh; mk = mh; }
+    }
+    if (lane == 0 && !(p.flags & 2u)) {
+        // ---- certificate: every pool row NOT among the C kept has score >= tau (the C-th kept score), hence
+        // true distance >= lower(tau).  The answer is exact when the kk-th exact distance is below that.
+        bool certified = true;
+        const unsigned long long kc = keys[C - 1];
+        const ErrModel em = make_err_model(p, q);
+        const double dk = sqrt(dk2);
+        if (p.n > C && kc != ~0ull && mk != 0) {
+            const double lb = em.lower(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(kc >> 32))));
+            certified = (lb > 0.0) && (dk < lb);
+        } else if (mk == 0) {
+            certified = (p.n <= C);
+        }
+        if (!certified) {
+            // second pass collects every row with score <= thr: any x with d(q,x) <= dk has
+            // ||q~ - x~|| <= dk + eta, i.e. s~ <= (dk + eta)^2 - ||q~||^2 + eps_acc.
+            const double t = (dk + em.eta) * (dk + em.eta) - em.qn_bf + em.eps_acc;
+            const int slot = atomicAdd(p.uncert_count, 1);
+            p.uncert_list[slot] = q;
+            p.uncert_thr[slot] = __double2float_ru(t + 1e-6 * fabs(t));
+        }
+    }
 }
 
 template <typename TX, typename TQ, int C, int NT>
@@ -785,66 +858,7 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
         __syncthreads();
     }
     __syncthreads();
-    if (warp == 0) {
-        // rank the exact distances by (d2, index); each lane owns candidates lane, lane + 32 (C <= 64)
-        constexpr int H = (C + 31) / 32;
-        double myd[H];
-        uint32_t myi[H];
-        int rank[H];
-#pragma unroll
-        for (int h = 0; h < H; h++) {
-            const int c = lane + 32 * h;
-            myd[h] = (c < C) ? d2s[c] : DBL_MAX;
-            myi[h] = (c < C) ? static_cast<uint32_t>(keys[c]) : 0xffffffffu;
-            rank[h] = 0;
-        }
-#pragma unroll
-        for (int g = 0; g < H; g++) {
-#pragma unroll
-            for (int o = 0; o < 32; o++) {
-                const double od = __shfl_sync(0xffffffffu, myd[g], o);
-                const uint32_t oi = __shfl_sync(0xffffffffu, myi[g], o);
-#pragma unroll
-                for (int h = 0; h < H; h++) rank[h] += (od < myd[h] || (od == myd[h] && oi < myi[h])) ? 1 : 0;
-            }
-        }
-        double dk2 = DBL_MAX;
-        unsigned mk = 0;
-#pragma unroll
-        for (int h = 0; h < H; h++) {
-            const bool valid = (lane + 32 * h) < C;
-            if (valid && rank[h] < p.kk) {
-                p.out_idx[static_cast<int64_t>(q) * p.kk + rank[h]] = static_cast<int32_t>(p.index_base + myi[h]);
-                p.out_dist[static_cast<int64_t>(q) * p.kk + rank[h]] = (p.flags & 1u) ? myd[h] : sqrt(myd[h]);
-            }
-            // k-th exact distance (rank kk-1), broadcast
-            const unsigned mh = __ballot_sync(0xffffffffu, valid && rank[h] == p.kk - 1);
-            const double dh = __shfl_sync(0xffffffffu, myd[h], mh ? (__ffs(mh) - 1) : 0);
-            if (mh) { dk2 = dh; mk = mh; }
-        }
-        if (lane == 0 && !(p.flags & 2u)) {
-            // ---- certificate: every pool row NOT among the C kept has score >= tau (the C-th kept score), hence
-            // true distance >= lower(tau).  The answer is exact when the kk-th exact distance is below that.
-            bool certified = true;
-            const unsigned long long kc = keys[C - 1];
-            const ErrModel em = make_err_model(p, q);
-            const double dk = sqrt(dk2);
-            if (p.n > C && kc != ~0ull && mk != 0) {
-                const double lb = em.lower(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(kc >> 32))));
-                certified = (lb > 0.0) && (dk < lb);
-            } else if (mk == 0) {
-                certified = (p.n <= C);
-            }
-            if (!certified) {
-                // second pass collects every row with score <= thr: any x with d(q,x) <= dk has
-                // ||q~ - x~|| <= dk + eta, i.e. s~ <= (dk + eta)^2 - ||q~||^2 + eps_acc.
-                const double t = (dk + em.eta) * (dk + em.eta) - em.qn_bf + em.eps_acc;
-                const int slot = atomicAdd(p.uncert_count, 1);
-                p.uncert_list[slot] = q;
-                p.uncert_thr[slot] = __double2float_ru(t + 1e-6 * fabs(t));
-            }
-        }
-    }
+    if (warp == 0) rerank_finish<C>(p, q, keys, d2s, lane);
 }
 
 // Second pass, part 2: exact re-rank of the collected lists.  One block per uncertified query (list slot).
