@@ -40,7 +40,38 @@ WORKLOADS = {
     "c4": (50000, 50000, 2048, 4, "precision/recall self-kNN: 50k vs 50k, d=2048, k=3(+self) (configs[3])"),
     "c1": (10000, 100, 5000, 10, "dci_code/example.py shape: 10k pool, 100 queries, d=5000, k=10 (configs[0])"),
     "small": (20000, 2048, 512, 1, "smoke-sized"),
+    # configs[4]: 98 GB of BF16 pool + 197 GB of float32 originals -> needs >= 2 GPUs (>= 4 recommended); "c5s" is the
+    # 125k-row share one rank holds in the 8-GPU run, for single-GPU measurements
+    "c5": (1000000, 30000, 49152, 10, "scale sweep: 1M pool, d=49152 (128x128x3 raw pixels), 30k queries, k=10 (configs[4])"),
+    "c5s": (125000, 30000, 49152, 10, "one rank's 1/8 share (125k rows) of the configs[4] scale sweep: d=49152, 30k queries, k=10"),
 }
+IMAGE_LIKE = ("c5", "c5s")       # float32 image-like features; the others: float64 N(0,1)
+IMAGE_LATENT = 16
+
+
+def synth_rows(workload, a, b, d, dev, seed_base):
+    """Rows [a, b) of a workload's synthetic feature matrix, generated on the device; a row's values depend only on
+    (seed_base, global row block), so every sharding sees the same matrix."""
+    import torch
+    if workload not in IMAGE_LIKE:
+        raise ValueError(workload)
+    # image-like: a 16-dimensional latent through a fixed random basis + pixel noise, clipped to [-1, 1] (the
+    # trainer's pixel range, training_loop.py:362-365), float32 like the generator's output
+    gb = torch.Generator(device=dev)
+    gb.manual_seed(77)
+    basis = torch.randn(IMAGE_LATENT, d, device=dev, dtype=torch.float32, generator=gb) * 0.125
+    out = torch.empty(b - a, d, device=dev, dtype=torch.float32)
+    SB = 4096
+    for sb in range(a // SB, (b + SB - 1) // SB):
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed_base + sb)
+        lat = torch.randn(SB, IMAGE_LATENT, device=dev, dtype=torch.float32, generator=g)
+        x = lat @ basis
+        x += 0.05 * torch.randn(SB, d, device=dev, dtype=torch.float32, generator=g)
+        x.clamp_(-1.0, 1.0)
+        lo, hi = max(a, sb * SB), min(b, (sb + 1) * SB)
+        out[lo - a:hi - a] = x[lo - sb * SB:hi - sb * SB]
+    return out
 
 
 def load_peaks():
@@ -135,7 +166,7 @@ def reference_sample(workload, steps, warmup, budget_s=25.0):
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     if not ref_dci.available():
         return None
-    ns = int(min(n, 120000))
+    ns = int(min(n, 120000, max(2048, int(3.5e9) // (8 * d))))        # pool subsample bounded to 3.5 GB of float64
     qs = int(min(q, max(64, 16 * cores)))
     rng = np.random.default_rng(0)
     pool = rng.standard_normal((ns, d))
@@ -193,7 +224,7 @@ def run_reference(args):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from inclusivegan_b200.dci import DeviceKNN, F64, load_library
+    from inclusivegan_b200.dci import DeviceKNN, F32, F64, load_library
     import ctypes
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,29 +238,39 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     n, q, d, k, desc = WORKLOADS[args.workload]
-    # ---- synthetic features (float64, the dtype of the reference's interface), identical on every rank ----
+    image_like = args.workload in IMAGE_LIKE
+    fdt, FT, fbytes = (torch.float32, F32, 4) if image_like else (torch.float64, F64, 8)
     per = (n + world - 1) // world
     r0, r1 = min(n, per * rank), min(n, per * (rank + 1))
-    # the pool is generated in 8 fixed row blocks, each seeded by its block id, so 1/2/4/8-GPU runs see the same rows
-    pool = torch.empty(r1 - r0, d, device=dev, dtype=torch.float64)
-    blk = (n + 7) // 8
-    for b in range(8):
-        b0, b1 = max(r0, b * blk), min(r1, (b + 1) * blk, n)
-        if b1 <= b0:
-            continue
-        g = torch.Generator(device=dev)
-        g.manual_seed(1000 + b)
-        full = torch.randn(min((b + 1) * blk, n) - b * blk, d, device=dev, dtype=torch.float64, generator=g)
-        pool[b0 - r0:b1 - r0] = full[b0 - b * blk:b1 - b * blk]
-        del full
-    gq = torch.Generator(device=dev)
-    gq.manual_seed(1)
-    queries = torch.randn(q, d, device=dev, dtype=torch.float64, generator=gq)
+    need_gb = (r1 - r0) * d * (fbytes + 2) / 1e9 + q * d * (fbytes + 2) / 1e9
+    if need_gb > 150.0:
+        raise RuntimeError("workload %s needs %.0f GB per GPU at %d GPU(s): use more GPUs (pool rows are sharded)" % (args.workload, need_gb, world))
+    if image_like:
+        # ---- image-like float32 features generated on the device per row block (configs[4]) ----
+        pool = synth_rows(args.workload, r0, r1, d, dev, 1000)
+        queries = synth_rows(args.workload, 0, q, d, dev, 500000)
+    else:
+        # ---- synthetic features (float64, the dtype of the reference's interface), identical on every rank ----
+        # the pool is generated in 8 fixed row blocks, each seeded by its block id, so 1/2/4/8-GPU runs see the same rows
+        pool = torch.empty(r1 - r0, d, device=dev, dtype=torch.float64)
+        blk = (n + 7) // 8
+        for b in range(8):
+            b0, b1 = max(r0, b * blk), min(r1, (b + 1) * blk, n)
+            if b1 <= b0:
+                continue
+            g = torch.Generator(device=dev)
+            g.manual_seed(1000 + b)
+            full = torch.randn(min((b + 1) * blk, n) - b * blk, d, device=dev, dtype=torch.float64, generator=g)
+            pool[b0 - r0:b1 - r0] = full[b0 - b * blk:b1 - b * blk]
+            del full
+        gq = torch.Generator(device=dev)
+        gq.manual_seed(1)
+        queries = torch.randn(q, d, device=dev, dtype=torch.float64, generator=gq)
 
     stream = torch.cuda.current_stream()
     ix = DeviceKNN(d, local_rank)
     ix.set_stream(stream.cuda_stream)
-    ix.add(pool.data_ptr(), F64, r1 - r0, index_base=r0)
+    ix.add(pool.data_ptr(), FT, r1 - r0, index_base=r0)
     torch.cuda.synchronize()
     kk = min(k, n)
     loc_i = torch.empty(q, kk, device=dev, dtype=torch.int32)
@@ -278,7 +319,7 @@ def run_b200(args):
         ix.merge(all_i.data_ptr(), all_d.data_ptr(), world, q, kk, out_i.data_ptr(), out_d.data_ptr(), stream.cuda_stream)
 
     def step_device():
-        ix.query(queries.data_ptr(), F64, q, k, loc_i.data_ptr(), loc_d.data_ptr())
+        ix.query(queries.data_ptr(), FT, q, k, loc_i.data_ptr(), loc_d.data_ptr())
         if world > 1:
             exchange_and_merge()
 
@@ -318,14 +359,14 @@ def run_b200(args):
 
     # ---- end-to-end arm: host-buffer C-ABI call (what DCI.query makes), pinned host queries ----------
     lib = load_library()
-    hq = torch.empty(q, d, dtype=torch.float64).pin_memory()
+    hq = torch.empty(q, d, dtype=fdt).pin_memory()
     hq.copy_(queries)
     torch.cuda.synchronize()
     hx = ctypes.c_void_p()
     ids = (ctypes.c_int * 1)(local_rank)
     assert lib.b200knn_create(d, 1, ids, ctypes.byref(hx)) == 0
     assert lib.b200knn_set_stream(hx, ctypes.c_void_p(stream.cuda_stream)) == 0
-    assert lib.b200knn_add_device(hx, ctypes.c_void_p(pool.data_ptr()), F64, r1 - r0, d, r0) == 0, lib.b200knn_last_error()
+    assert lib.b200knn_add_device(hx, ctypes.c_void_p(pool.data_ptr()), FT, r1 - r0, d, r0) == 0, lib.b200knn_last_error()
     h_i = torch.empty(q, kk, dtype=torch.int32).pin_memory()
     h_d = torch.empty(q, kk, dtype=torch.float64).pin_memory()
     res_i = torch.empty(q, kk, dtype=torch.int32).pin_memory()
@@ -338,16 +379,16 @@ def run_b200(args):
     q_per = q_pad // world
     if world > 1:
         qa, qb = min(q, rank * q_per), min(q, (rank + 1) * q_per)
-        hq_slice = torch.zeros(q_per, d, dtype=torch.float64).pin_memory()
+        hq_slice = torch.zeros(q_per, d, dtype=fdt).pin_memory()
         hq_slice[:qb - qa].copy_(queries[qa:qb])
-        dq_full = torch.empty(q_pad, d, device=dev, dtype=torch.float64)
+        dq_full = torch.empty(q_pad, d, device=dev, dtype=fdt)
         torch.cuda.synchronize()
 
     sliced = world >= 4          # N <= 2: every rank runs the pipelined host-buffer call (upload hidden behind compute)
 
     def step_e2e():
         if not sliced:
-            rc = lib.b200knn_query(hx, ctypes.c_void_p(hq.data_ptr()), F64, q, d, k, 0, ctypes.c_void_p(h_i.data_ptr()),
+            rc = lib.b200knn_query(hx, ctypes.c_void_p(hq.data_ptr()), FT, q, d, k, 0, ctypes.c_void_p(h_i.data_ptr()),
                                    ctypes.c_void_p(h_d.data_ptr()), None)
             if rc != 0:
                 raise RuntimeError(lib.b200knn_last_error().decode())
@@ -362,7 +403,7 @@ def run_b200(args):
         dq_full[rank * q_per:(rank + 1) * q_per].copy_(hq_slice, non_blocking=True)          # H2D of this rank's slice
         dist.all_gather_into_tensor(dq_full, dq_full[rank * q_per:(rank + 1) * q_per])       # NVLink broadcast of the slices
         torch.cuda.synchronize()       # keep NCCL's kernels off the SMs the persistent distance kernel wants
-        ix.query(dq_full.data_ptr(), F64, q, k, loc_i.data_ptr(), loc_d.data_ptr())
+        ix.query(dq_full.data_ptr(), FT, q, k, loc_i.data_ptr(), loc_d.data_ptr())
         exchange_and_merge()
         res_i.copy_(out_i, non_blocking=True)                                                 # D2H of the merged result
         res_d.copy_(out_d, non_blocking=True)
@@ -376,8 +417,12 @@ def run_b200(args):
 
     # ---- self-check of the last device result against a float64 torch brute force on a query subsample ----
     nchk = min(q, 64)
-    sub = queries[:nchk]
-    d2 = (sub * sub).sum(1, keepdim=True) + (pool * pool).sum(1)[None, :] - 2.0 * sub @ pool.T
+    sub = queries[:nchk].double()
+    d2 = torch.empty(nchk, r1 - r0, device=dev, dtype=torch.float64)
+    for c0 in range(0, r1 - r0, 8192):                # float64 whatever the feature dtype
+        pc = pool[c0:c0 + 8192].double()
+        d2[:, c0:c0 + 8192] = (sub * sub).sum(1, keepdim=True) + (pc * pc).sum(1)[None, :] - 2.0 * sub @ pc.T
+    del pc
     tk = torch.topk(d2, min(kk, r1 - r0), dim=1, largest=False)
     if world == 1:
         check = bool((tk.indices.to(torch.int32) == loc_i[:nchk]).all().item()) if rank == 0 else None
@@ -418,7 +463,7 @@ def run_b200(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16 (tensor pass) + f64 (exact re-rank)", "data": "synthetic",
             "config": {"workload": "%s: %s" % (args.workload, desc), "pool": n, "queries": q, "dim": d, "k": k,
-                       "features": "float64 N(0,1), seeded", "parallelism": "pool row-sharded x%d, queries replicated, exchange=%s + k-way merge kernel" % (world, exchange_kind)
+                       "features": ("float32 image-like (16-d latent through a fixed basis + 0.05 pixel noise, clipped to [-1,1]), seeded per 4096-row block, generated on device" if image_like else "float64 N(0,1), seeded"), "parallelism": "pool row-sharded x%d, queries replicated, exchange=%s + k-way merge kernel" % (world, exchange_kind)
                        if world > 1 else "single GPU", "l2": "inputs exceed L2 (BF16 pool shard %.2f GB > 126 MB); no explicit flush" % ((r1 - r0) * d * 2 / 1e9),
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "tensor_peak_frac": 2.0 * q * n * d / (ms_step * 1e-3) / 1e12 / (peaks["bf16_tflops"] * world),
@@ -431,7 +476,7 @@ def run_b200(args):
                                    "rerank": st["ms_rerank"] / args.steps, "second_pass": st["ms_scan"] / args.steps},
             "uncertified_per_step": st["uncertified"] / args.steps,
             "e2e": {"value": q / (e2e_ms / e2e_steps * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                    "h2d_bytes_per_step": q * d * 8, "d2h_bytes_per_step": q * kk * 12,
+                    "h2d_bytes_per_step": q * d * fbytes, "d2h_bytes_per_step": q * kk * 12,
                     "api": ("b200knn_query (host buffers; the call inclusivegan_b200.dci.DCI.query makes)" + ("" if world == 1 else " per rank + peer exchange + D2H of the merged result")) if not sliced else
                            "per rank: H2D of a 1/N query slice from pinned host memory, NVLink all-gather of the slices, b200knn_query_device, peer exchange, D2H of the merged result"},
             "gpu_launches": int(launches),

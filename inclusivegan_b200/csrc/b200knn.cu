@@ -148,7 +148,8 @@ struct Shard {
     int forced_cg = 0;               // $B200KNN_CTA_GROUP=1|2 pins the kernel flavour (A/B measurements)
     unsigned opt_flags = 0;          // $B200KNN_OPT: kernel tuning switches (see DistParams::opt)
     int a_budget_mb = 64;            // $B200KNN_A_BUDGET_MB: L2 budget for the query tiles of one round
-    int sync_tiles = 16;             // $B200KNN_SYNC_TILES: lockstep interval of the workers sharing a pool-tile stream
+    int wide_mode = 1;               // $B200KNN_WIDE: 0 never, 1 when cheaper in HBM traffic, 2 always (A/B measurements)
+    int sync_tiles = -1;             // $B200KNN_SYNC_TILES: lockstep interval of the workers sharing a pool-tile stream (-1: by tile length)
     int max_pairs = 74;              // CTA pairs that can be co-resident (cudaOccupancyMaxActiveClusters)
 
     // ---- query workspace ----
@@ -223,6 +224,7 @@ struct Shard {
         if (const char *o = getenv("B200KNN_OPT")) opt_flags = static_cast<unsigned>(atoi(o));
         if (const char *o = getenv("B200KNN_A_BUDGET_MB")) a_budget_mb = std::max(1, atoi(o));
         if (const char *o = getenv("B200KNN_SYNC_TILES")) sync_tiles = std::max(0, atoi(o));
+        if (const char *o = getenv("B200KNN_WIDE")) wide_mode = atoi(o);
         if (const char *o = getenv("B200KNN_COPY_THREADS")) copy_threads = std::max(1, atoi(o));
         if (const char *o = getenv("B200KNN_CENTER")) use_centering = atoi(o) != 0;
         copy_threads = std::min<int>(copy_threads, std::max(1u, std::thread::hardware_concurrency()));
@@ -441,6 +443,7 @@ struct Shard {
     // in lockstep: HBM traffic per round is ~ one pass over the pool instead of one per worker.
     struct Sched {
         int cg, qt, nt, workers, nrounds, max_slots, grid, qg;
+        bool wide = false;                  // rounds run in round-wide lockstep (long K)
         int64_t key_nq = -1, key_n = -1;
         int key_kp = -1, key_slots = -1;
         bool matches(int64_t nq_, int64_t n_, int kp_, int slots_) const { return key_nq == nq_ && key_n == n_ && key_kp == kp_ && key_slots == slots_; }
@@ -470,6 +473,29 @@ struct Shard {
             const double util = static_cast<double>(g) * rc / W;
             if (util >= best_util - 1e-12) { best_util = util; qg = g; }   // ties -> larger group (fewer rounds)
         }
+        // Long K: only a few query tiles fit in L2 and each pool tile would be re-streamed from HBM for every small
+        // group.  Alternative: a gs x rc grid of (query tile, pool stream) workers that advance through K together
+        // (round-wide lockstep at every tile): a K block of a query tile is fetched once for its rc users and a K block
+        // of a pool tile once for its gs users, nothing has to stay resident.  HBM rows fetched per output tile:
+        // resident BN / gs, grid (gs * qrows + rc * BN) / (gs * rc); the cheaper one wins.
+        int wide_g = 0, wide_rc = 0;
+        (void)wide_rc;
+        if (wide_mode != 0) {
+            const int rc_res = std::max(1, std::min(std::min(W / qg, s.nt), max_slots_allowed));
+            const double res_cost = static_cast<double>(BN) / qg / std::min(1.0, static_cast<double>(qg) * rc_res / W);
+            double best_cost = 1e30;
+            int bg = 0, brc = 0;
+            for (int g = 2; g <= std::min(s.qt, 255); g++) {
+                const int rc = std::min(std::min(W / g, s.nt), max_slots_allowed);
+                if (rc < 2 || g * rc > 255) continue;
+                const double util = static_cast<double>(g) * rc / W;
+                const double cost = (static_cast<double>(g) * qrows + static_cast<double>(rc) * BN) / (static_cast<double>(g) * rc) / util;
+                if (cost < best_cost) { best_cost = cost; bg = g; brc = rc; }
+            }
+            if (bg && (wide_mode == 2 || best_cost < 0.85 * res_cost)) { wide_g = bg; wide_rc = brc; }
+            if (wide_g) qg = wide_g;
+        }
+        s.wide = wide_g != 0;
         s.qg = qg;
         s.items.clear();
         s.slots_per_qtile.assign(s.qt, 0);
@@ -477,7 +503,9 @@ struct Shard {
         s.max_slots = 1;
         for (int q0 = 0; q0 < s.qt; q0 += qg) {
             const int gs = std::min(qg, s.qt - q0);
-            const int rc = std::max(1, std::min(std::min(W / gs, s.nt), max_slots_allowed));
+            int rc = std::max(1, std::min(std::min(W / gs, s.nt), max_slots_allowed));
+            if (s.wide && gs * rc > 255) rc = 255 / gs;
+            const int wide_bits = (s.wide && gs > 1 && rc > 1) ? (gs * rc) << 24 : 0;
             s.max_slots = std::max(s.max_slots, rc);
             s.items.resize(static_cast<size_t>(s.nrounds + 1) * W, WorkItem{-1, 0, 0, 0});
             WorkItem *row = s.items.data() + static_cast<size_t>(s.nrounds) * W;
@@ -485,7 +513,7 @@ struct Shard {
             for (int c = 0; c < rc; c++) {
                 const int t0 = static_cast<int>(static_cast<int64_t>(c) * s.nt / rc);
                 const int t1 = static_cast<int>(static_cast<int64_t>(c + 1) * s.nt / rc);
-                for (int g = 0; g < gs; g++) row[c * gs + g] = WorkItem{q0 + g, t0, t1, c | (gs << 16)};
+                for (int g = 0; g < gs; g++) row[c * gs + g] = WorkItem{q0 + g, t0, t1, c | (gs << 16) | wide_bits};
             }
             for (int g = 0; g < gs; g++) s.slots_per_qtile[q0 + g] = rc;
             s.nrounds++;
@@ -621,8 +649,9 @@ struct Shard {
         int pk = 1;
         while (pk < rp.max_slots * C) pk <<= 1;
         const size_t sm = static_cast<size_t>(pk) * sizeof(unsigned long long);
-        // merging many shortlists (few queries, many pool streams) is a latency-bound sort: give it 32 warps
-        if (pk >= 1024) launch_rerank_nt<C, 1024>(d_query, q_dtype, g, sm, rp);
+        // merging many shortlists for few queries (many pool streams) is a latency-bound sort: give it 32 warps; with
+        // many queries the device is full anyway and the exact sweep (128 lanes per query) is what matters
+        if (pk >= 1024 && nq <= 4096) launch_rerank_nt<C, 1024>(d_query, q_dtype, g, sm, rp);
         else launch_rerank_nt<C, 128>(d_query, q_dtype, g, sm, rp);
         prof_end();
         CU_TRY(cudaGetLastError());
@@ -640,7 +669,9 @@ struct Shard {
         dp.workers = s.workers;
         dp.round_counter = scalars.p + 6;
         dp.stream_sync = stream_sync.p;
-        dp.sync_tiles = sync_tiles;
+        // sharers drift by time, not by tiles: about one re-alignment per 16 tiles of K = 3072
+        dp.sync_tiles = sync_tiles >= 0 ? sync_tiles : (s.wide ? 1 : std::max(1, 16 * 3072 / std::max(kp, 1)));
+        dp.sync_timeout_ns = 40000u * static_cast<unsigned>(std::max(1, kp / 3072));     // ~2 tile times
         dp.max_slots = s.max_slots;
         dp.opt = opt_flags;
         return dp;

@@ -227,8 +227,10 @@ convert_norm_kernel(const T *__restrict__ src, const double *__restrict__ mu, in
 // of pool tiles.  All items of a round have the same length (+-1 tile) and the query tiles of a round form a group
 // whose BF16 rows fit in L2 next to the pool tiles being streamed, so the workers that share pool tiles stay in
 // lockstep and each pool tile is fetched from HBM once per round; a grid barrier separates rounds.
-struct WorkItem { int qtile, t0, t1, slot; };   // qtile < 0: idle in this round; slot: low 16 bits = shortlist slot of the
-                                                // query rows (= pool-tile stream of the round), high 16 bits = workers sharing the stream
+struct WorkItem { int qtile, t0, t1, slot; };   // qtile < 0: idle in this round; slot: bits 0-15 = shortlist slot of the query
+                                                // rows (= pool-tile stream of the round), bits 16-23 = workers sharing the stream,
+                                                // bits 24-31 = 0, or the number of active workers of a round that runs in
+                                                // round-wide lockstep (long K: see Shard::plan)
 
 struct DistParams {
     const float *xnorm;      // [n] ||x~||^2
@@ -241,6 +243,7 @@ struct DistParams {
     unsigned int *round_counter;   // grid barrier between rounds (zeroed by the host before the launch)
     unsigned int *stream_sync;     // [nrounds][max_slots] lockstep counters of the workers sharing a pool-tile stream (zeroed)
     int sync_tiles;                // the sharers of a stream re-align every sync_tiles tiles (0 = never)
+    unsigned int sync_timeout_ns;  // bound on one lockstep wait (~2 tile times)
     int max_slots;           // shortlists per query row in cand_* (row stride)
     float *cand_s;           // [nq][max_slots][C] approximate scores, ascending
     int *cand_i;             // [nq][max_slots][C] shard-local row index (-1 = empty slot)
@@ -354,12 +357,16 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 const WorkItem w = load_item(p, round, worker);
                 if (w.qtile >= 0) {
                     const int q0 = w.qtile * (BM * CG) + static_cast<int>(cta_rank) * BM;
-                    const int sharers = w.slot >> 16;
-                    unsigned int *sync = p.stream_sync + static_cast<int64_t>(round) * p.max_slots + (w.slot & 0xffff);
+                    const unsigned int sw = static_cast<unsigned int>(w.slot);
+                    const int wide = static_cast<int>(sw >> 24), per_stream = static_cast<int>((sw >> 16) & 0xffu);
+                    const int sharers = wide ? wide : per_stream;
+                    // round-wide lockstep covers the tiles every stream of the round has (chunks differ by one tile)
+                    const int sync_lim = wide ? ((p.n + BN - 1) / BN) / (wide / per_stream) : 0x7fffffff;
+                    unsigned int *sync = p.stream_sync + static_cast<int64_t>(round) * p.max_slots + (wide ? 0u : (sw & 0xffffu));
                     for (int t = w.t0; t < w.t1; t++) {
                         // lockstep: the workers streaming the same pool tiles re-align every sync_tiles tiles, so a tile
                         // fetched from HBM by the first of them is still in L2 when the last one asks for it
-                        if (p.sync_tiles > 0 && sharers > 1 && (CG == 1 || leader) && t > w.t0 && (t - w.t0) % p.sync_tiles == 0) {
+                        if (p.sync_tiles > 0 && sharers > 1 && (CG == 1 || leader) && t > w.t0 && (t - w.t0) < sync_lim && (t - w.t0) % p.sync_tiles == 0) {
                             const unsigned int target = static_cast<unsigned int>((t - w.t0) / p.sync_tiles) * sharers;
                             atomicAdd(sync, 1u);
                             // bounded: if a sharer is not resident (a foreign kernel holds its SM) we go on alone after
@@ -367,7 +374,7 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             const uint64_t t_start = global_timer_ns();
                             while (*reinterpret_cast<volatile unsigned int *>(sync) < target) {
                                 __nanosleep(128);
-                                if (global_timer_ns() - t_start > 40000ull) break;
+                                if (global_timer_ns() - t_start > p.sync_timeout_ns) break;
                             }
                         }
                         const int n0 = t * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS;
@@ -577,16 +584,25 @@ template <typename TX, typename TQ>
 __device__ __forceinline__ double canon_d2(const TX *__restrict__ xr, const TQ *__restrict__ qr, int dim, int tid, double *partial4) {
     if (tid < 128) {
         double a0 = 0.0, a1 = 0.0;
-        int e = tid;
-        for (; e + 128 < dim; e += 256) {
-            const double d0 = static_cast<double>(qr[e]) - static_cast<double>(xr[e]);
-            const double d1 = static_cast<double>(qr[e + 128]) - static_cast<double>(xr[e + 128]);
-            a0 = fma(d0, d0, a0);
-            a1 = fma(d1, d1, a1);
-        }
-        if (e < dim) {
-            const double d0 = static_cast<double>(qr[e]) - static_cast<double>(xr[e]);
-            a0 = fma(d0, d0, a0);
+        constexpr int RB = 16;                   // elements per lane and step: 32 loads in flight before any arithmetic
+        for (int base = 0; base < dim; base += RB * 128) {
+            TQ qraw[RB];
+            TX xraw[RB];
+#pragma unroll
+            for (int i = 0; i < RB; i++) {
+                const int e = base + tid + i * 128;
+                qraw[i] = (e < dim) ? qr[e] : TQ(0);     // past the end: 0 - 0 adds nothing
+                xraw[i] = (e < dim) ? xr[e] : TX(0);
+            }
+#pragma unroll
+            for (int i = 0; i < RB; i++) { keep(qraw[i]); keep(xraw[i]); }
+#pragma unroll
+            for (int i = 0; i < RB; i += 2) {
+                const double d0 = static_cast<double>(qraw[i]) - static_cast<double>(xraw[i]);
+                const double d1 = static_cast<double>(qraw[i + 1]) - static_cast<double>(xraw[i + 1]);
+                a0 = fma(d0, d0, a0);
+                a1 = fma(d1, d1, a1);
+            }
         }
         const double w = warp_sum(a0 + a1);
         if ((tid & 31) == 0) partial4[tid >> 5] = w;
@@ -597,7 +613,6 @@ __device__ __forceinline__ double canon_d2(const TX *__restrict__ xr, const TQ *
     return tot;
 }
 
-// The same canonical sum computed by ONE warp (each lane plays the virtual lanes lane, lane+32, lane+64, lane+96):
 // bit-identical to canon_d2, no block barrier — lets the warps of a block work on different candidates.
 template <typename TX, typename TQ>
 __device__ __forceinline__ double canon_d2_warp(const TX *__restrict__ xr, const TQ *__restrict__ qr, int dim, int lane) {
@@ -796,7 +811,7 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
         m_s = m;
     }
     __syncthreads();
-    const int m = m_s;
+    int m = m_s;
     // exact float64 distances of the surviving candidates (the arithmetic of util.c:62-69, tree-summed).  The whole
     // block works on one candidate at a time: every thread owns a strided slice of the dimensions, keeps its slice
     // of the query row in registers across candidates, and issues its loads of the pool row back to back.
@@ -823,6 +838,30 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
         for (int i = 0; i < RQ; i++) qreg[i] = static_cast<double>(qraw[i]);
     }
     for (int c = 0; c < C; c++) {
+        if (c == p.kk && c < m) {               // uniform across the block
+            // kk exact distances are known: the kk-th true distance is at most their maximum, which is a far tighter
+            // pruning limit than the a-priori upper bound (the survivors stay a prefix: scores are sorted)
+            if (warp == 0) {
+                double mx = 0.0;
+                for (int i = lane; i < p.kk; i += 32) mx = fmax(mx, d2s[i]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                int cnt = 0;
+                if (mx < DBL_MAX) {
+                    const ErrModel em = make_err_model(p, q);
+                    const double dk = sqrt(mx);
+                    for (int i = p.kk + lane; i < m; i += 32)
+                        cnt += (keys[i] != ~0ull && em.lower(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(keys[i] >> 32)))) <= dk) ? 1 : 0;
+                } else {
+                    cnt = (lane == 0) ? m - p.kk : 0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                if (lane == 0) m_s = p.kk + cnt;
+            }
+            __syncthreads();
+            m = m_s;
+        }
         const unsigned long long key = keys[c];
         if (c >= m || key == ~0ull) {           // uniform across the block
             if (tid == 0) d2s[c] = DBL_MAX;

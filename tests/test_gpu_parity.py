@@ -464,3 +464,35 @@ def test_results_do_not_depend_on_batching_or_path(lib):
     certified_rows = np.all(i_nc == i_all, axis=1)
     assert certified_rows.mean() > 0.2
     assert np.array_equal(d_nc[certified_rows], d_all[certified_rows])
+
+
+@pytest.mark.parametrize("cg", ["1", "2"])
+def test_round_wide_lockstep_schedule(lib, cg, monkeypatch):
+    """Long-K schedule (Shard::plan: a grid of query tiles x pool streams advancing through K together) forced at a
+    size with several rounds and ragged chunks; answers must not depend on the schedule."""
+    from inclusivegan_b200 import DCI
+    x, y = make("cluster", 21000, 2900, 320, seed=33, dtype=np.float32)
+    ref = DCI(320)
+    ref.add(x)
+    i0, d0 = ref.query_arrays(y, 4)
+    monkeypatch.setenv("B200KNN_WIDE", "2")
+    monkeypatch.setenv("B200KNN_CTA_GROUP", cg)
+    db = DCI(320)
+    db.add(x)
+    i1, d1 = check(db, x, y, 4)
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+
+
+def test_long_rows_pick_the_wide_schedule_and_stay_exact(lib):
+    """d = 49152 (config 5's raw pixels) on image-like rows: first pass on the tensor path, exact answers."""
+    from inclusivegan_b200 import DCI
+    rng = np.random.default_rng(5)
+    d, n, q = 49152, 6000, 700
+    basis = (0.125 * rng.standard_normal((16, d))).astype(np.float32)
+    x = np.clip(rng.standard_normal((n, 16)).astype(np.float32) @ basis + 0.05 * rng.standard_normal((n, d)).astype(np.float32), -1, 1)
+    y = np.clip(rng.standard_normal((q, 16)).astype(np.float32) @ basis + 0.05 * rng.standard_normal((q, d)).astype(np.float32), -1, 1)
+    db = DCI(d)
+    db.add(x)
+    check(db, x, y, 10)
+    st = db.stats()
+    assert st["exact_scanned"] == 0, st
