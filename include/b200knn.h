@@ -109,6 +109,22 @@ int b200knn_query_self(b200knn_index *index, int k, unsigned flags, int32_t *out
 int b200knn_ball_membership(b200knn_index *index, const void *query, int dtype, int64_t nq, int64_t ld, const double *radius2,
                             unsigned char *out_member);
 
+/* ---- random projection on the device (single-device handles) ----
+ * The trainer's optional `--init-proj-dim` path multiplies every 256-row chunk of generated images and every 24-row
+ * chunk of real images by a fixed Gaussian matrix in NumPy float64 on the host before handing them to DCI
+ * (training/training_loop.py:205-212 builds `projector`, :362-365 and :379-381 do `np.matmul(rows.astype(float64),
+ * projector)`).  These entry points take the UNPROJECTED rows (float32 as the generator emits them, or float64) and
+ * do that product on the device in float64 (one sequential FMA chain per output element: independent of chunking),
+ * so neither the float64 blow-up of the images nor the projected matrix crosses PCIe.
+ * projector: HOST float64 [in_dim][dim] row-major (leading dimension ld), dim = the handle's dim; may be replaced at
+ * any time, applies to later calls.  rows: HOST [n][in_dim].  Results exactly as add() / query() on the projected rows. */
+int b200knn_set_projector(b200knn_index *index, const double *projector, int64_t in_dim, int64_t ld);
+int b200knn_add_projected(b200knn_index *index, const void *rows, int dtype, int64_t n, int64_t ld);
+int b200knn_query_projected(b200knn_index *index, const void *rows, int dtype, int64_t nq, int64_t ld, int k, unsigned flags,
+                            int32_t *out_idx, double *out_dist, int *out_kk);
+/* Debug / parity: the projected rows themselves.  out: HOST float64 [n][dim]. */
+int b200knn_project_rows(b200knn_index *index, const void *rows, int dtype, int64_t n, int64_t ld, double *out);
+
 /* ---- device-buffer entry points (inputs already resident in HBM; single-device handles) ---- */
 
 /* Launch all work of this handle on `stream` (a cudaStream_t passed as void*, NULL = the

@@ -949,6 +949,11 @@ struct b200knn_index {
     // multi-device gather buffers on shard 0
     DevBuf<int32_t> g_idx;
     DevBuf<double> g_dist;
+    // random projection (single-device handles): projector [proj_in_dim][dim], staging for unprojected rows, projected queries
+    DevBuf<double> projector;
+    int64_t proj_in_dim = 0;
+    DevBuf<unsigned char> proj_stage;
+    DevBuf<double> proj_rows;
 
     int ensure_devices() {
         if (devices_ready) return B200KNN_OK;
@@ -1030,6 +1035,9 @@ int b200knn_destroy(b200knn_index *ix) {
         cudaSetDevice(ix->shards[0].device);
         ix->g_idx.release();
         ix->g_dist.release();
+        ix->projector.release();
+        ix->proj_stage.release();
+        ix->proj_rows.release();
     }
     delete ix;
     return B200KNN_OK;
@@ -1350,6 +1358,129 @@ int b200knn_query_self(b200knn_index *ix, int k, unsigned flags, int32_t *out_id
     CU_TRY(cudaMemcpyAsync(out_dist, s.out_dist.p, static_cast<size_t>(s.n) * kk * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     CU_TRY(cudaStreamSynchronize(s.stream));
     if (s.index_base != 0) { /* indices already carry index_base */ }
+    return B200KNN_OK;
+}
+
+// ---- random projection on the device ----
+static int check_projected_args(b200knn_index *ix, const void *p, int dtype, int64_t rows, int64_t ld, const char *what) {
+    if (!ix) return fail(B200KNN_EINVAL, "index is NULL");
+    if (ix->device_ids.size() > 1) return fail(B200KNN_EINVAL, "the projected entry points are only valid for single-device handles");
+    if (ix->proj_in_dim <= 0) return fail(B200KNN_ESTATE, "no projector set (b200knn_set_projector)");
+    if (!p && rows > 0) return fail(B200KNN_EINVAL, "%s pointer is NULL", what);
+    if (dtype != B200KNN_F64 && dtype != B200KNN_F32) return fail(B200KNN_EINVAL, "%s dtype %d is not B200KNN_F64/F32", what, dtype);
+    if (rows < 0) return fail(B200KNN_EINVAL, "%s row count is negative", what);
+    if (ld < ix->proj_in_dim) return fail(B200KNN_EINVAL, "%s leading dimension %lld < projector input dim %lld", what, (long long)ld, (long long)ix->proj_in_dim);
+    if (rows > 0x7fffffffll - 512) return fail(B200KNN_EINVAL, "%s has too many rows (%lld)", what, (long long)rows);
+    return B200KNN_OK;
+}
+
+// rows [n][in_dim] on the HOST -> d_out [n][dim] float64 on the device, in row chunks through the staging buffer
+static int project_host_rows(b200knn_index *ix, Shard &s, const void *rows, int dtype, int64_t n, int64_t ld, double *d_out) {
+    const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
+    const int64_t in_dim = ix->proj_in_dim;
+    const int64_t chunk = std::max<int64_t>(PJ_T, std::min<int64_t>((n + PJ_T - 1) / PJ_T * PJ_T, (512ll << 20) / (in_dim * static_cast<int64_t>(esz)) / PJ_T * PJ_T));
+    TRY(ix->proj_stage.ensure(static_cast<size_t>(std::min(chunk, n)) * in_dim * esz));
+    for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+        const int64_t cr = std::min(chunk, n - r0);
+        TRY(s.upload_rows(ix->proj_stage.p, static_cast<const char *>(rows) + static_cast<size_t>(r0) * ld * esz, cr, static_cast<size_t>(in_dim) * esz,
+                          static_cast<size_t>(ld) * esz, s.stream));
+        const dim3 grid(static_cast<unsigned>((ix->dim + PJ_T - 1) / PJ_T), static_cast<unsigned>((cr + PJ_T - 1) / PJ_T));
+        s.stats.kernel_launches++;
+        if (dtype == B200KNN_F64)
+            project_kernel<double><<<grid, 256, 0, s.stream>>>(reinterpret_cast<const double *>(ix->proj_stage.p), in_dim, static_cast<int>(cr), ix->projector.p,
+                                                               static_cast<int>(in_dim), ix->dim, d_out + r0 * ix->dim, ix->dim);
+        else
+            project_kernel<float><<<grid, 256, 0, s.stream>>>(reinterpret_cast<const float *>(ix->proj_stage.p), in_dim, static_cast<int>(cr), ix->projector.p,
+                                                              static_cast<int>(in_dim), ix->dim, d_out + r0 * ix->dim, ix->dim);
+        CU_TRY(cudaGetLastError());
+        // the staging buffer is reused by the next chunk's upload, which is ordered behind this kernel on the stream
+        // only for DMA copies; the pinned-ring path fills host slots first, so ordering on the stream is sufficient
+    }
+    return B200KNN_OK;
+}
+
+int b200knn_set_projector(b200knn_index *ix, const double *projector, int64_t in_dim, int64_t ld) {
+    if (!ix) return fail(B200KNN_EINVAL, "index is NULL");
+    if (ix->device_ids.size() > 1) return fail(B200KNN_EINVAL, "the projected entry points are only valid for single-device handles");
+    if (!projector) return fail(B200KNN_EINVAL, "projector pointer is NULL");
+    if (in_dim <= 0 || in_dim > 0x7fffffffll) return fail(B200KNN_EINVAL, "projector input dim %lld out of range", (long long)in_dim);
+    if (ld < ix->dim) return fail(B200KNN_EINVAL, "projector leading dimension %lld < dim %d", (long long)ld, ix->dim);
+    TRY(ix->ensure_devices());
+    Shard &s = ix->shards[0];
+    CU_TRY(cudaSetDevice(s.device));
+    CU_TRY(cudaStreamSynchronize(s.stream));          // nothing in flight may still read the previous projector
+    TRY(ix->projector.ensure(static_cast<size_t>(in_dim) * ix->dim));
+    TRY(s.upload_rows(ix->projector.p, reinterpret_cast<const char *>(projector), in_dim, static_cast<size_t>(ix->dim) * 8, static_cast<size_t>(ld) * 8, s.stream));
+    CU_TRY(cudaStreamSynchronize(s.stream));
+    ix->proj_in_dim = in_dim;
+    return B200KNN_OK;
+}
+
+int b200knn_project_rows(b200knn_index *ix, const void *rows, int dtype, int64_t n, int64_t ld, double *out) {
+    TRY(check_projected_args(ix, rows, dtype, n, ld, "rows"));
+    if (n == 0) return B200KNN_OK;
+    if (!out) return fail(B200KNN_EINVAL, "output buffer is NULL");
+    Shard &s = ix->shards[0];
+    CU_TRY(cudaSetDevice(s.device));
+    TRY(ix->proj_rows.ensure(static_cast<size_t>(n) * ix->dim));
+    TRY(project_host_rows(ix, s, rows, dtype, n, ld, ix->proj_rows.p));
+    CU_TRY(cudaMemcpyAsync(out, ix->proj_rows.p, static_cast<size_t>(n) * ix->dim * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CU_TRY(cudaStreamSynchronize(s.stream));
+    return B200KNN_OK;
+}
+
+static int add_projected_impl(b200knn_index *ix, const void *rows, int dtype, int64_t n, int64_t ld) {
+    TRY(check_projected_args(ix, rows, dtype, n, ld, "rows"));
+    if (ix->n_total > 0) return fail(B200KNN_ESTATE, "index already holds %lld points; clear() it first", (long long)ix->n_total);
+    if (n == 0) return B200KNN_OK;
+    Shard &s = ix->shards[0];
+    CU_TRY(cudaSetDevice(s.device));
+    void *d_pool = nullptr;
+    CU_TRY(cudaMalloc(&d_pool, static_cast<size_t>(n) * ix->dim * sizeof(double)));
+    int r = s.attach_pool(d_pool, true, B200KNN_F64, n, ix->dim, ix->dim, ix->kp, 0);   // the shard owns d_pool from here
+    if (r != B200KNN_OK) return r;
+    TRY(project_host_rows(ix, s, rows, dtype, n, ld, static_cast<double *>(d_pool)));
+    TRY(s.compute_mean(d_pool, B200KNN_F64, n, ix->dim, ix->dim));
+    TRY(s.launch_convert(d_pool, B200KNN_F64, n, ix->dim, ix->dim, ix->kp, s.x_bf.p, s.xnorm_bf.p, s.x_err.p, s.scalars.p));
+    CU_TRY(cudaStreamSynchronize(s.stream));          // the caller may free / overwrite `rows` after return
+    ix->n_total = n;
+    return B200KNN_OK;
+}
+
+int b200knn_add_projected(b200knn_index *ix, const void *rows, int dtype, int64_t n, int64_t ld) {
+    const int rc = add_projected_impl(ix, rows, dtype, n, ld);
+    if (rc != B200KNN_OK && rc != B200KNN_ESTATE && ix && ix->n_total == 0) {
+        const std::string msg = g_last_error;
+        for (auto &s : ix->shards) s.clear_pool();
+        cudaGetLastError();
+        g_last_error = msg;
+    }
+    return rc;
+}
+
+int b200knn_query_projected(b200knn_index *ix, const void *rows, int dtype, int64_t nq, int64_t ld, int k, unsigned flags,
+                            int32_t *out_idx, double *out_dist, int *out_kk) {
+    TRY(check_projected_args(ix, rows, dtype, nq, ld, "query"));
+    if (k <= 0) return fail(B200KNN_EINVAL, "k must be positive (got %d)", k);
+    if (ix->n_total <= 0) return fail(B200KNN_ESTATE, "query on an empty index");
+    if (nq > 0 && (!out_idx || !out_dist)) return fail(B200KNN_EINVAL, "output buffer is NULL");
+    Shard &s = ix->shards[0];
+    const int kk = static_cast<int>(std::min<int64_t>(k, s.n));
+    if (out_kk) *out_kk = kk;
+    if (nq == 0) return B200KNN_OK;
+    CU_TRY(cudaSetDevice(s.device));
+    TRY(s.out_idx.ensure(static_cast<size_t>(std::min(nq, QUERY_CHUNK)) * kk));
+    TRY(s.out_dist.ensure(static_cast<size_t>(std::min(nq, QUERY_CHUNK)) * kk));
+    TRY(ix->proj_rows.ensure(static_cast<size_t>(std::min(nq, QUERY_CHUNK)) * ix->dim));
+    const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
+    for (int64_t q0 = 0; q0 < nq; q0 += QUERY_CHUNK) {
+        const int64_t cq = std::min(QUERY_CHUNK, nq - q0);
+        TRY(project_host_rows(ix, s, static_cast<const char *>(rows) + static_cast<size_t>(q0) * ld * esz, dtype, cq, ld, ix->proj_rows.p));
+        TRY(s.query_device(ix->proj_rows.p, B200KNN_F64, cq, ix->dim, ix->dim, ix->kp, k, flags, s.out_idx.p, s.out_dist.p));
+        CU_TRY(cudaMemcpyAsync(out_idx + q0 * kk, s.out_idx.p, static_cast<size_t>(cq) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        CU_TRY(cudaMemcpyAsync(out_dist + q0 * kk, s.out_dist.p, static_cast<size_t>(cq) * kk * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        CU_TRY(cudaStreamSynchronize(s.stream));
+    }
     return B200KNN_OK;
 }
 

@@ -106,6 +106,14 @@ def load_library(path=None):
     lib.b200knn_exchange_destroy.argtypes = [vp]
     lib.b200knn_ball_membership.restype = i32
     lib.b200knn_ball_membership.argtypes = [vp, vp, i32, i64, i64, vp, vp]
+    lib.b200knn_set_projector.restype = i32
+    lib.b200knn_set_projector.argtypes = [vp, vp, i64, i64]
+    lib.b200knn_add_projected.restype = i32
+    lib.b200knn_add_projected.argtypes = [vp, vp, i32, i64, i64]
+    lib.b200knn_query_projected.restype = i32
+    lib.b200knn_query_projected.argtypes = [vp, vp, i32, i64, i64, i32, u32, vp, vp, ctypes.POINTER(i32)]
+    lib.b200knn_project_rows.restype = i32
+    lib.b200knn_project_rows.argtypes = [vp, vp, i32, i64, i64, vp]
     lib.b200knn_debug_shortlists.restype = i32
     lib.b200knn_debug_shortlists.argtypes = [vp, vp, vp, i64, ctypes.POINTER(i64), ctypes.POINTER(i32), ctypes.POINTER(i32)]
     lib.b200knn_last_error.restype = ctypes.c_char_p
@@ -468,6 +476,72 @@ class DCI(object):
         _check(self._lib.b200knn_ball_membership(self._handle, q.ctypes.data, self._dtype_code(q), q.shape[0], self._dim,
                                                  r2.ctypes.data, out.ctypes.data))
         return out
+
+    # ---- random projection on the device (training_loop.py:205-212,362-365,379-381) ------------------
+    def set_projector(self, projector):
+        """Extension: register the trainer's random projector (in_dim x dim, float64).  add_projected() /
+        query_projected() then take UNPROJECTED rows (in_dim wide, float32 or float64) and compute
+        `rows.astype(float64) @ projector` on the device, in float64, before indexing / searching."""
+        p = np.ascontiguousarray(projector, dtype=np.float64)
+        if p.ndim != 2 or p.shape[1] != self.dim or p.shape[0] < 1:
+            raise ValueError("projector must have shape (in_dim, %d), got %r" % (self.dim, p.shape))
+        _check(self._lib.b200knn_set_projector(self._handle, p.ctypes.data, p.shape[0], p.shape[1]))
+        self._proj_in_dim = int(p.shape[0])
+
+    def _fix_unprojected(self, rows):
+        in_dim = getattr(self, "_proj_in_dim", 0)
+        if not in_dim:
+            raise RuntimeError("no projector set: call set_projector() first")
+        rows = np.asarray(rows)
+        if rows.ndim > 2:                                   # images: flatten like np.reshape(x, (-1, prod(shape[1:])))
+            rows = rows.reshape(rows.shape[0], -1)
+        if rows.ndim != 2 or rows.shape[1] != in_dim:
+            raise ValueError("mismatch between row width (%d) and the projector's input dimension (%d)"
+                             % (rows.shape[1] if rows.ndim == 2 else -1, in_dim))
+        if rows.dtype not in (np.float32, np.float64):
+            rows = rows.astype(np.float64)
+        return np.ascontiguousarray(rows)
+
+    def project_rows(self, rows):
+        """Extension (parity checks): the float64 projected rows the device computes."""
+        r = self._fix_unprojected(rows)
+        out = np.empty((r.shape[0], self.dim), dtype=np.float64)
+        _check(self._lib.b200knn_project_rows(self._handle, r.ctypes.data, F64 if r.dtype == np.float64 else F32, r.shape[0],
+                                              r.shape[1], out.ctypes.data))
+        return out
+
+    def add_projected(self, rows, num_levels=2, field_of_view=10, **_ignored):
+        """Extension: add(rows.astype(float64) @ projector) without the host matmul (one array per index, like add)."""
+        if self.num_points > 0:
+            raise RuntimeError("DCI class does not support insertion of more than one array. "
+                               "Must combine all arrays into one array before inserting")
+        r = self._fix_unprojected(rows)
+        if r.shape[0] > 0:
+            _check(self._lib.b200knn_add_projected(self._handle, r.ctypes.data, F64 if r.dtype == np.float64 else F32,
+                                                   r.shape[0], r.shape[1]))
+        self._orig_indices = None
+        self._offset = 0
+        self._array = None
+        self._num_levels = int(num_levels) if r.shape[0] > 0 else 0
+
+    def query_projected_arrays(self, rows, num_neighbours, squared=False, flags=0):
+        """Extension: query_arrays(rows.astype(float64) @ projector) without the host matmul."""
+        r = self._fix_unprojected(rows)
+        _require_positive_int(num_neighbours)
+        kk = min(num_neighbours, self.num_points)
+        idx = np.empty((r.shape[0], kk), dtype=np.int32)
+        dist = np.empty((r.shape[0], kk), dtype=np.float64)
+        _check(self._lib.b200knn_query_projected(self._handle, r.ctypes.data, F64 if r.dtype == np.float64 else F32, r.shape[0],
+                                                 r.shape[1], int(num_neighbours), int(flags) | (FLAG_SQUARED if squared else 0),
+                                                 idx.ctypes.data, dist.ctypes.data, None))
+        return idx, dist
+
+    def query_projected(self, rows, num_neighbours=-1, **_ignored):
+        """Extension: query(rows.astype(float64) @ projector); same return convention as query()."""
+        if num_neighbours < 0:
+            num_neighbours = self.num_points
+        idx, dist = self.query_projected_arrays(rows, num_neighbours)
+        return list(idx), list(dist)
 
     def clear(self):
         """Drop the pool (dci.py:332-335)."""
