@@ -34,6 +34,11 @@ print("\n".join(lines))
 num = lambda k: float(d[k][0].replace(',', ''))
 scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1, 'Tbyte': 1e12}
 traffic = num('dram__bytes_read.sum') * scale[d['dram__bytes_read.sum'][1]] + num('dram__bytes_write.sum') * scale[d['dram__bytes_write.sum'][1]]
-json.dump({"c3": {"dram_bytes_per_launch": traffic, "source": "profiles/dist_kernel_ncu_r1_c3.txt (ncu --set full, one launch)",
-                  "algorithmic_operand_floor_bytes": 2 * (300000 + 30000) * 3072}}, open('profiles/dist_kernel_ncu.json', 'w'), indent=1)
+try:
+    allw = json.load(open('profiles/dist_kernel_ncu.json'))       # other workloads' entries are kept
+except Exception:
+    allw = {}
+allw["c3"] = {"dram_bytes_per_launch": traffic, "source": "profiles/dist_kernel_ncu_r1_c3.txt (ncu --set full, one launch)",
+              "algorithmic_operand_floor_bytes": 2 * (300000 + 30000) * 3072}
+json.dump(allw, open('profiles/dist_kernel_ncu.json', 'w'), indent=1)
 print(traffic / 1e9, "GB")
