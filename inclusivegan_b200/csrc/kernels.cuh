@@ -841,6 +841,7 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
         if (c == p.kk && c < m) {               // uniform across the block
             // kk exact distances are known: the kk-th true distance is at most their maximum, which is a far tighter
             // pruning limit than the a-priori upper bound (the survivors stay a prefix: scores are sorted)
+            __syncthreads();                    // d2s[0..kk) were written by thread 0, possibly without a barrier since
             if (warp == 0) {
                 double mx = 0.0;
                 for (int i = lane; i < p.kk; i += 32) mx = fmax(mx, d2s[i]);

@@ -13,3 +13,15 @@ db2 = DCI(64); db2.add(np.ascontiguousarray(xx)); db2.query_arrays(np.ascontiguo
 r2 = np.full(3000, 150.0); db.ball_membership(y, r2)
 xf = rng.standard_normal((1500, 129)).astype(np.float32); dbf = DCI(129); dbf.add(xf); dbf.query_arrays(xf[:100], 4, squared=True)
 print("sanitize target done", db.stats()["kernel_launches"], db2.stats())
+# later additions: self-kNN, long rows (batched canonical sums), forced grid schedule (round-wide lockstep), random projection
+db.query_self_arrays(4)
+xl = rng.standard_normal((600, 3300)).astype(np.float32); dbl = DCI(3300); dbl.add(xl); dbl.query_arrays(xl[:70], 10)
+os.environ["B200KNN_WIDE"] = "2"
+for cg in ("1", "2"):
+    os.environ["B200KNN_CTA_GROUP"] = cg
+    dbw = DCI(200); dbw.add(x); dbw.query_arrays(y, 4); dbw.query_arrays(np.vstack([y] * 3), 1)
+del os.environ["B200KNN_WIDE"], os.environ["B200KNN_CTA_GROUP"]
+P = rng.normal(0, 0.01, size=(777, 129)); dbp = DCI(129); dbp.set_projector(P)
+rows = rng.standard_normal((300, 777)).astype(np.float32)
+dbp.add_projected(rows); dbp.query_projected_arrays(rows[:50], 3); dbp.project_rows(rows[:33].astype(np.float64))
+print("sanitize target (additions) done")
