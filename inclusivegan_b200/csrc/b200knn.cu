@@ -478,21 +478,20 @@ struct Shard {
         // (round-wide lockstep at every tile): a K block of a query tile is fetched once for its rc users and a K block
         // of a pool tile once for its gs users, nothing has to stay resident.  HBM rows fetched per output tile:
         // resident BN / gs, grid (gs * qrows + rc * BN) / (gs * rc); the cheaper one wins.
-        int wide_g = 0, wide_rc = 0;
-        (void)wide_rc;
+        int wide_g = 0;
         if (wide_mode != 0) {
             const int rc_res = std::max(1, std::min(std::min(W / qg, s.nt), max_slots_allowed));
             const double res_cost = static_cast<double>(BN) / qg / std::min(1.0, static_cast<double>(qg) * rc_res / W);
             double best_cost = 1e30;
-            int bg = 0, brc = 0;
+            int bg = 0;
             for (int g = 2; g <= std::min(s.qt, 255); g++) {
                 const int rc = std::min(std::min(W / g, s.nt), max_slots_allowed);
                 if (rc < 2 || g * rc > 255) continue;
                 const double util = static_cast<double>(g) * rc / W;
                 const double cost = (static_cast<double>(g) * qrows + static_cast<double>(rc) * BN) / (static_cast<double>(g) * rc) / util;
-                if (cost < best_cost) { best_cost = cost; bg = g; brc = rc; }
+                if (cost < best_cost) { best_cost = cost; bg = g; }
             }
-            if (bg && (wide_mode == 2 || best_cost < 0.85 * res_cost)) { wide_g = bg; wide_rc = brc; }
+            if (bg && (wide_mode == 2 || best_cost < 0.85 * res_cost)) wide_g = bg;
             if (wide_g) qg = wide_g;
         }
         s.wide = wide_g != 0;
@@ -505,7 +504,7 @@ struct Shard {
             const int gs = std::min(qg, s.qt - q0);
             int rc = std::max(1, std::min(std::min(W / gs, s.nt), max_slots_allowed));
             if (s.wide && gs * rc > 255) rc = 255 / gs;
-            const int wide_bits = (s.wide && gs > 1 && rc > 1) ? (gs * rc) << 24 : 0;
+            const int wide_bits = (s.wide && gs > 1 && rc > 1) ? static_cast<int>(static_cast<unsigned int>(gs * rc) << 24) : 0;
             s.max_slots = std::max(s.max_slots, rc);
             s.items.resize(static_cast<size_t>(s.nrounds + 1) * W, WorkItem{-1, 0, 0, 0});
             WorkItem *row = s.items.data() + static_cast<size_t>(s.nrounds) * W;
@@ -1393,8 +1392,7 @@ static int project_host_rows(b200knn_index *ix, Shard &s, const void *rows, int 
             project_kernel<float><<<grid, 256, 0, s.stream>>>(reinterpret_cast<const float *>(ix->proj_stage.p), in_dim, static_cast<int>(cr), ix->projector.p,
                                                               static_cast<int>(in_dim), ix->dim, d_out + r0 * ix->dim, ix->dim);
         CU_TRY(cudaGetLastError());
-        // the staging buffer is reused by the next chunk's upload, which is ordered behind this kernel on the stream
-        // only for DMA copies; the pinned-ring path fills host slots first, so ordering on the stream is sufficient
+        // the next chunk's upload reuses the staging buffer: its DMA is enqueued on the same stream, behind this kernel
     }
     return B200KNN_OK;
 }
