@@ -15,7 +15,8 @@ _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libb200knn.so")
 _STAMP = os.path.join(_HERE, ".libb200knn.stamp")
 SOURCES = ["b200knn.cu"]
-HEADERS = ["kernels.cuh", "ptx.cuh", os.path.join(_ROOT, "include", "b200knn.h")]
+HEADERS = ["kernels.cuh", "common.cuh", "convert.cuh", "dist.cuh", "rerank.cuh", "scan.cuh", "member.cuh", "exchange.cuh", "project.cuh", "ptx.cuh",
+           os.path.join(_ROOT, "include", "b200knn.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

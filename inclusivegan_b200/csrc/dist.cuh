@@ -1,0 +1,351 @@
+// Kernel 2 — BF16 distance GEMM on tcgen05/TMEM fed by TMA, fused top-C / threshold-collect epilogue (tensor-bound).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+// ------------------------------------------------------------------------------------------------
+// Kernel 2: BF16 distance GEMM on tcgen05 with fused top-C epilogue.
+// ------------------------------------------------------------------------------------------------
+// Work schedule (built on the host, Shard::plan): `nrounds` rounds of `workers` items; worker w (a CTA, or a CTA pair
+// for cta_group::2) takes items[r * workers + w] in round r.  An item is one query tile swept over a contiguous range
+// of pool tiles.  All items of a round have the same length (+-1 tile) and the query tiles of a round form a group
+// whose BF16 rows fit in L2 next to the pool tiles being streamed, so the workers that share pool tiles stay in
+// lockstep and each pool tile is fetched from HBM once per round; a grid barrier separates rounds.
+struct WorkItem { int qtile, t0, t1, slot; };   // qtile < 0: idle in this round; slot: bits 0-15 = shortlist slot of the query
+                                                // rows (= pool-tile stream of the round), bits 16-23 = workers sharing the stream,
+                                                // bits 24-31 = 0, or the number of active workers of a round that runs in
+                                                // round-wide lockstep (long K: see Shard::plan)
+
+struct DistParams {
+    const float *xnorm;      // [n] ||x~||^2
+    int n;                   // pool rows in this shard
+    int nq;                  // query rows
+    int num_kb;              // ceil(kp / BK)
+    const WorkItem *items;   // [nrounds][workers]
+    int nrounds;
+    int workers;
+    unsigned int *round_counter;   // grid barrier between rounds (zeroed by the host before the launch)
+    unsigned int *stream_sync;     // [nrounds][max_slots] lockstep counters of the workers sharing a pool-tile stream (zeroed)
+    int sync_tiles;                // the sharers of a stream re-align every sync_tiles tiles (0 = never)
+    unsigned int sync_timeout_ns;  // bound on one lockstep wait (~2 tile times)
+    int max_slots;           // shortlists per query row in cand_* (row stride)
+    float *cand_s;           // [nq][max_slots][C] approximate scores, ascending
+    int *cand_i;             // [nq][max_slots][C] shard-local row index (-1 = empty slot)
+    // collect mode (second pass): every pool row whose score is <= thr[row] is appended to the row's list
+    const float *thr;        // [nq]
+    int *coll_count;         // [nq] running count (may exceed coll_cap: overflow)
+    int *coll_idx;           // [nq][coll_cap]
+    int coll_cap;
+    unsigned opt;            // tuning switches (A/B measurements): bit2 grid barrier between rounds
+};
+
+__device__ __forceinline__ WorkItem load_item(const DistParams &p, int round, int worker) {
+    const int4 v = __ldg(reinterpret_cast<const int4 *>(p.items) + static_cast<int64_t>(round) * p.workers + worker);
+    WorkItem w;
+    w.qtile = v.x; w.t0 = v.y; w.t1 = v.z; w.slot = v.w;
+    return w;
+}
+
+// sorted-ascending register list; precondition for insert: s < v[C-1]
+template <int C>
+__device__ __forceinline__ void topc_insert(float (&v)[C], int (&id)[C], float s, int idx) {
+    v[C - 1] = s;
+    id[C - 1] = idx;
+#pragma unroll
+    for (int i = C - 1; i > 0; --i) {
+        const bool sw = v[i] < v[i - 1];
+        const float a = v[i], b = v[i - 1];
+        const int ia = id[i], ib = id[i - 1];
+        v[i] = sw ? b : a;
+        v[i - 1] = sw ? a : b;
+        id[i] = sw ? ib : ia;
+        id[i - 1] = sw ? ia : ib;
+    }
+}
+
+// COLLECT == false: per-(query row, chunk) top-C shortlist.   COLLECT == true: threshold collection (second pass).
+// CG == 1: one CTA computes a 128(query) x 256(pool) tile per step.
+// CG == 2: a cluster of two CTAs (one SM pair) computes a 256 x 256 tile with tcgen05.mma.cta_group::2: each CTA
+//          stages its own 128 query rows (A half) and 128 of the 256 pool rows (B half), so per SM the operand
+//          traffic into and out of shared memory drops by a third; CTA rank 0 issues every MMA, both CTAs run
+//          the TMA producer and the epilogue for their own 128 query rows (their own TMEM lanes).
+template <int CG>
+struct DistCfg {
+    static constexpr int STAGES = (CG == 1) ? 4 : 6;
+    static constexpr int B_ROWS = BN / CG;                       // pool rows staged per CTA
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = B_ROWS * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SCRATCH_BYTES = 32 * 128 * 4;            // epilogue: one 32-score slab per thread (rare path)
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2 * BN * 4 + 256 + SCRATCH_BYTES;
+};
+
+template <int C, bool COLLECT, int CG>
+__global__ void __launch_bounds__(DIST_THREADS, 1)
+dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x, const DistParams p) {
+    using Cfg = DistCfg<CG>;
+    constexpr int NSTAGE = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles must sit on 1024-byte boundaries (identical carve-up in both CTAs of a pair)
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t smem_a = base;
+    const uint32_t smem_b = base + NSTAGE * Cfg::A_BYTES;
+    float *xn_s = reinterpret_cast<float *>(gen + NSTAGE * Cfg::STAGE_BYTES);   // [2][BN]
+    const uint32_t bars = base + NSTAGE * Cfg::STAGE_BYTES + 2 * BN * 4;
+    const uint32_t bar_full = bars;                       // [NSTAGE]  TMA -> MMA      (the leader's copy is used)
+    const uint32_t bar_empty = bars + 8 * NSTAGE;         // [NSTAGE]  MMA -> TMA      (one per CTA)
+    const uint32_t bar_tfull = bars + 16 * NSTAGE;        // [2]       MMA -> epilogue (one per CTA)
+    const uint32_t bar_tempty = bars + 16 * NSTAGE + 16;  // [2]       epilogue -> MMA (the leader's copy is used)
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + NSTAGE * Cfg::STAGE_BYTES + 2 * BN * 4 + 16 * NSTAGE + 32);
+    float *scratch = reinterpret_cast<float *>(gen + NSTAGE * Cfg::STAGE_BYTES + 2 * BN * 4 + 256);   // [32][128]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int worker = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;          // cluster (or CTA) index
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_x);
+        for (int s = 0; s < NSTAGE; s++) {
+            mbar_init(bar_full + 8 * s, 1);       // the leader's arrive.expect_tx covers the bytes of BOTH CTAs' loads
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 4 * CG);   // one arrival per epilogue warp of every CTA
+        }
+        fence_mbar_init();
+    }
+    if (CG == 2) cluster_sync_all();   // barriers of both CTAs initialised before anyone allocates / arrives remotely
+    if (warp == 1) {
+        tmem_alloc<CG>(smem_u32(const_cast<uint32_t *>(tmem_slot)), TMEM_COLS);
+        tmem_relinquish<CG>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one lane per CTA) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t full_remote = 0;   // cluster address of the leader's full barriers
+            if (CG == 2) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(full_remote) : "r"(bar_full), "r"(0));
+            for (int round = 0; round < p.nrounds; round++) {
+                const WorkItem w = load_item(p, round, worker);
+                if (w.qtile >= 0) {
+                    const int q0 = w.qtile * (BM * CG) + static_cast<int>(cta_rank) * BM;
+                    const unsigned int sw = static_cast<unsigned int>(w.slot);
+                    const int wide = static_cast<int>(sw >> 24), per_stream = static_cast<int>((sw >> 16) & 0xffu);
+                    const int sharers = wide ? wide : per_stream;
+                    // round-wide lockstep covers the tiles every stream of the round has (chunks differ by one tile)
+                    const int sync_lim = wide ? ((p.n + BN - 1) / BN) / (wide / per_stream) : 0x7fffffff;
+                    unsigned int *sync = p.stream_sync + static_cast<int64_t>(round) * p.max_slots + (wide ? 0u : (sw & 0xffffu));
+                    for (int t = w.t0; t < w.t1; t++) {
+                        // lockstep: the workers streaming the same pool tiles re-align every sync_tiles tiles, so a tile
+                        // fetched from HBM by the first of them is still in L2 when the last one asks for it
+                        if (p.sync_tiles > 0 && sharers > 1 && (CG == 1 || leader) && t > w.t0 && (t - w.t0) < sync_lim && (t - w.t0) % p.sync_tiles == 0) {
+                            const unsigned int target = static_cast<unsigned int>((t - w.t0) / p.sync_tiles) * sharers;
+                            atomicAdd(sync, 1u);
+                            // bounded: if a sharer is not resident (a foreign kernel holds its SM) we go on alone after
+                            // ~2 tile times — only L2 sharing is lost, never progress
+                            const uint64_t t_start = global_timer_ns();
+                            while (*reinterpret_cast<volatile unsigned int *>(sync) < target) {
+                                __nanosleep(128);
+                                if (global_timer_ns() - t_start > p.sync_timeout_ns) break;
+                            }
+                        }
+                        const int n0 = t * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS;
+                        for (int kb = 0; kb < p.num_kb; kb++) {
+                            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                            if (CG == 1) {
+                                mbar_expect_tx(bar_full + 8 * stage, Cfg::STAGE_BYTES);
+                                tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_q, bar_full + 8 * stage, kb * BK, q0);
+                                tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_x, bar_full + 8 * stage, kb * BK, n0);
+                            } else {
+                                // all four loads of the pair (2 x A half, 2 x B half) signal the LEADER's barrier; the
+                                // peer never arrives there: its loads only complete_tx (a remote arrive per K block
+                                // would cost a cluster-scope fence each time)
+                                if (leader) mbar_expect_tx(bar_full + 8 * stage, 2 * Cfg::STAGE_BYTES);
+                                const uint32_t fb = leader ? (bar_full + 8 * stage) : (full_remote + 8 * stage);
+                                tma_load_2d_cg2(smem_a + stage * Cfg::A_BYTES, &tmap_q, fb, kb * BK, q0);
+                                tma_load_2d_cg2(smem_b + stage * Cfg::B_BYTES, &tmap_x, fb, kb * BK, n0);
+                            }
+                            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+                // grid barrier: nobody starts streaming the next round's pool tiles before everyone is done issuing
+                // this round's loads (keeps the workers that share pool tiles in lockstep)
+                if ((p.opt & 4u) && round + 1 < p.nrounds) {
+                    __threadfence();
+                    atomicAdd(p.round_counter, 1u);
+                    const unsigned int target = static_cast<unsigned int>(round + 1) * gridDim.x;
+                    const uint64_t t_start = global_timer_ns();
+                    while (*reinterpret_cast<volatile unsigned int *>(p.round_counter) < target) {
+                        __nanosleep(256);
+                        if (global_timer_ns() - t_start > 2000000ull) break;   // bounded (2 ms): never a deadlock
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        // The whole warp runs the loop converged (uniform control flow, uniform registers); one elected lane issues.
+        // The issuing thread is on the critical path: per K block it must spend less than the 512 tensor cycles the
+        // four MMAs take.
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int round = 0; round < p.nrounds; round++) {
+                const WorkItem w = load_item(p, round, worker);
+                if (w.qtile < 0) continue;
+                for (int t = w.t0; t < w.t1; t++) {
+                    mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);     // epilogues have drained this accumulator
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + acc * BN;
+                    for (int kb = 0; kb < p.num_kb; kb++) {
+                        mbar_wait(bar_full + 8 * stage, phase);               // TMA bytes (of both CTAs) have landed
+                        tc_fence_after();
+                        const uint32_t cur = stage;
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        if (elect_one()) {
+                            const uint64_t da = make_smem_desc_sw128(smem_a + cur * Cfg::A_BYTES);
+                            const uint64_t db = make_smem_desc_sw128(smem_b + cur * Cfg::B_BYTES);
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; k++) {
+                                // +32 bytes per K slice inside the 128-byte swizzle row: +2 in the (>>4) address field
+                                umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            }
+                            // frees the smem slot (in both CTAs) when the MMAs retire
+                            if (CG == 1) umma_commit(bar_empty + 8 * cur);
+                            else umma_commit_cg2(bar_empty + 8 * cur, 0x3);
+                            if (kb == p.num_kb - 1) {                      // accumulator complete -> epilogue(s)
+                                if (CG == 1) umma_commit(bar_tfull + 8 * acc);
+                                else umma_commit_cg2(bar_tfull + 8 * acc, 0x3);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: 4 warps, thread <-> query row =====================
+        const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
+        const int row_in_tile = quarter * 32 + lane;
+        const int et = threadIdx.x - 64;               // 0..127
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int round = 0; round < p.nrounds; round++) {
+            const WorkItem w = load_item(p, round, worker);
+            if (w.qtile < 0) continue;
+            const int t0 = w.t0, t1 = w.t1;
+            float v[C];
+            int id[C];
+            const int q = w.qtile * (BM * CG) + static_cast<int>(cta_rank) * BM + row_in_tile;
+            float thr = -FLT_MAX;
+            int local_hits = 0;
+            if constexpr (COLLECT) {
+                if (q < p.nq) thr = __ldg(p.thr + q);
+            } else {
+#pragma unroll
+                for (int i = 0; i < C; i++) { v[i] = FLT_MAX; id[i] = -1; }
+            }
+            for (int t = t0; t < t1; t++) {
+                const int n0 = t * BN;
+                // stage ||x~||^2 of this tile; rows past the end of the pool can never be selected
+                float *xs = xn_s + acc * BN;
+                {
+                    const int c0 = n0 + et, c1 = n0 + et + 128;
+                    xs[et] = (c0 < p.n) ? __ldg(p.xnorm + c0) : FLT_MAX;
+                    xs[et + 128] = (c1 < p.n) ? __ldg(p.xnorm + c1) : FLT_MAX;
+                }
+                named_bar_sync(1, 128);
+                mbar_wait(bar_tfull + 8 * acc, acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+                // TMEM -> registers in 32-column slabs.  Hot path per score: FFMA + compare + predicated OR into a hit
+                // mask (no branches, compact code: the issuing warps share the SM's instruction cache with this loop).
+                // Slabs with hits park their 32 scores in shared memory and replay only the hit positions through ONE
+                // copy of the sorted-insert code.
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c++) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + c * 32, r);
+                    tmem_ld_wait();
+                    if constexpr (COLLECT) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float sc = fmaf(-2.f, __uint_as_float(r[j]), xs[c * 32 + j]);
+                            if (sc <= thr && local_hits <= p.coll_cap) {   // a row that filled its list from here stops counting
+                                local_hits++;
+                                const int pos = atomicAdd(p.coll_count + q, 1);
+                                if (pos < p.coll_cap) p.coll_idx[static_cast<int64_t>(q) * p.coll_cap + pos] = n0 + c * 32 + j;
+                            }
+                        }
+                    } else {
+                        const float worst = v[C - 1];
+                        uint32_t hits = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float sc = fmaf(-2.f, __uint_as_float(r[j]), xs[c * 32 + j]);
+                            r[j] = __float_as_uint(sc);
+                            hits |= (sc < worst) ? (1u << j) : 0u;
+                        }
+                        if (hits) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) scratch[j * 128 + et] = __uint_as_float(r[j]);
+                            do {
+                                const int j = __ffs(hits) - 1;
+                                hits &= hits - 1;
+                                const float sc = scratch[j * 128 + et];
+                                if (sc < v[C - 1]) topc_insert<C>(v, id, sc, n0 + c * 32 + j);
+                            } while (hits);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {                       // this warp is done with the accumulator
+                    if (CG == 1 || leader) mbar_arrive(bar_tempty + 8 * acc);
+                    else mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+            if constexpr (!COLLECT) {
+                if (q < p.nq) {
+                    float *cs = p.cand_s + (static_cast<int64_t>(q) * p.max_slots + (w.slot & 0xffff)) * C;
+                    int *ci = p.cand_i + (static_cast<int64_t>(q) * p.max_slots + (w.slot & 0xffff)) * C;
+#pragma unroll
+                    for (int i = 0; i < C; i += 4) {
+                        *reinterpret_cast<float4 *>(cs + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        *reinterpret_cast<int4 *>(ci + i) = make_int4(id[i], id[i + 1], id[i + 2], id[i + 3]);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();   // the peer's smem / TMEM stay alive until the leader's last MMA has retired
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace b200

@@ -1,0 +1,433 @@
+// Kernel 3 — shortlist merge, exact float64 re-rank in one canonical summation order, certificate; second-pass list re-rank.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+// ------------------------------------------------------------------------------------------------
+// Kernel 3: shortlist merge + exact re-rank + certificate.  One block (128 threads) per query.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_order_bits(float f) {   // monotone float -> uint
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_order_bits(uint32_t b) {
+    return __uint_as_float((b & 0x80000000u) ? (b & 0x7fffffffu) : ~b);
+}
+
+// Canonical exact squared distance: ONE summation order for every code path that emits a distance (first-pass re-rank,
+// second-pass list re-rank, ball membership), so a result does not depend on how the pool is sharded, on the batch
+// size, or on whether the query needed the second pass.  128 virtual lanes: lane v sums the elements e = v + 128 i,
+// even i into one accumulator and odd i into another; xor-shuffle tree inside each of the 4 warps; the 4 warp sums are
+// added in order.  Executed by threads 0..127 of the block; the value is returned to every thread.
+template <typename TX, typename TQ>
+__device__ __forceinline__ double canon_d2(const TX *__restrict__ xr, const TQ *__restrict__ qr, int dim, int tid, double *partial4) {
+    if (tid < 128) {
+        double a0 = 0.0, a1 = 0.0;
+        constexpr int RB = 16;                   // elements per lane and step: 32 loads in flight before any arithmetic
+        for (int base = 0; base < dim; base += RB * 128) {
+            TQ qraw[RB];
+            TX xraw[RB];
+#pragma unroll
+            for (int i = 0; i < RB; i++) {
+                const int e = base + tid + i * 128;
+                qraw[i] = (e < dim) ? qr[e] : TQ(0);     // past the end: 0 - 0 adds nothing
+                xraw[i] = (e < dim) ? xr[e] : TX(0);
+            }
+#pragma unroll
+            for (int i = 0; i < RB; i++) { keep(qraw[i]); keep(xraw[i]); }
+#pragma unroll
+            for (int i = 0; i < RB; i += 2) {
+                const double d0 = static_cast<double>(qraw[i]) - static_cast<double>(xraw[i]);
+                const double d1 = static_cast<double>(qraw[i + 1]) - static_cast<double>(xraw[i + 1]);
+                a0 = fma(d0, d0, a0);
+                a1 = fma(d1, d1, a1);
+            }
+        }
+        const double w = warp_sum(a0 + a1);
+        if ((tid & 31) == 0) partial4[tid >> 5] = w;
+    }
+    __syncthreads();
+    const double tot = ((partial4[0] + partial4[1]) + partial4[2]) + partial4[3];
+    __syncthreads();
+    return tot;
+}
+
+// bit-identical to canon_d2, no block barrier — lets the warps of a block work on different candidates.
+template <typename TX, typename TQ>
+__device__ __forceinline__ double canon_d2_warp(const TX *__restrict__ xr, const TQ *__restrict__ qr, int dim, int lane) {
+    double a[4][2] = {};
+    for (int base = 0; base < dim; base += 256) {
+        // all sixteen loads of the step first (see keep()), then the arithmetic
+        TQ qv[8];
+        TX xv[8];
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const int e0 = base + lane + 32 * g, e1 = e0 + 128;
+            qv[2 * g] = (e0 < dim) ? qr[e0] : TQ(0);
+            xv[2 * g] = (e0 < dim) ? xr[e0] : TX(0);
+            qv[2 * g + 1] = (e1 < dim) ? qr[e1] : TQ(0);
+            xv[2 * g + 1] = (e1 < dim) ? xr[e1] : TX(0);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) { keep(qv[i]); keep(xv[i]); }
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const double d0 = static_cast<double>(qv[2 * g]) - static_cast<double>(xv[2 * g]);
+            const double d1 = static_cast<double>(qv[2 * g + 1]) - static_cast<double>(xv[2 * g + 1]);
+            a[g][0] = fma(d0, d0, a[g][0]);      // out-of-range elements are 0 - 0: they add nothing
+            a[g][1] = fma(d1, d1, a[g][1]);
+        }
+    }
+    const double w0 = warp_sum(a[0][0] + a[0][1]), w1 = warp_sum(a[1][0] + a[1][1]);
+    const double w2 = warp_sum(a[2][0] + a[2][1]), w3 = warp_sum(a[3][0] + a[3][1]);
+    return ((w0 + w1) + w2) + w3;
+}
+
+struct RerankParams {
+    const float *cand_s;
+    const int *cand_i;
+    int max_slots;                 // row stride of cand_* in shortlists
+    const int *slots_per_qtile;    // [query tiles] shortlists actually written for the rows of that tile
+    int qtile_rows;                // query rows per tile (BM * CG)
+    int dim;
+    int64_t ld_x, ld_q;
+    int n;                         // pool rows in the shard
+    int kk;                        // neighbours to emit (<= C)
+    int64_t index_base;
+    unsigned flags;                // B200KNN_FLAG_*
+    const float *qnorm_bf;         // [nq] ||q~||^2 (fp32, of rounded values)
+    const float *q_err;            // [nq] ||q - q~|| rounded up
+    const unsigned int *max_xnorm_bf_bits;   // device scalars (pool): max ||x~||^2, max ||x - x~||
+    const unsigned int *max_x_err_bits;
+    int kp;                        // padded K of the BF16 operands (accumulation length)
+    int32_t *out_idx;              // [nq][kk]
+    double *out_dist;              // [nq][kk]
+    int *uncert_count;             // number of uncertified queries
+    int *uncert_list;              // their row numbers
+    float *uncert_thr;             // score threshold for the collection pass, per list slot
+};
+
+// Error model shared by the pruning rule, the certificate and the second-pass threshold.  With q~, x~ the BF16
+// roundings:  s~ + ||q~||^2 = ||q~ - x~||^2 up to fp32 accumulation error eps_acc, and
+// | ||q - x|| - ||q~ - x~|| | <= ||q - q~|| + ||x - x~|| =: eta   (triangle inequality; both norms are computed
+// exactly by convert_norm_kernel, the pool side as a maximum over rows).
+struct ErrModel {
+    double qn_bf, eps_acc, eta;
+    __device__ __forceinline__ double lower(double s) const {   // lower bound on the true distance, given score s
+        const double v = s + qn_bf - eps_acc;
+        return (v > 0.0 ? sqrt(v) : 0.0) - eta;
+    }
+    __device__ __forceinline__ double upper(double s) const {   // upper bound on the true distance
+        const double v = s + qn_bf + eps_acc;
+        return (v > 0.0 ? sqrt(v) : 0.0) + eta;
+    }
+};
+__device__ __forceinline__ ErrModel make_err_model(const RerankParams &p, int q) {
+    ErrModel m;
+    m.qn_bf = static_cast<double>(p.qnorm_bf[q]);
+    const double xn_bf = static_cast<double>(__uint_as_float(*p.max_xnorm_bf_bits));
+    const double K = static_cast<double>(p.kp);
+    // fp32 accumulation error of the MMA (K terms of magnitude <= ||q~|| ||x~||, x2 for the -2 factor, truncating
+    // adds assumed), of the fp32 norm sums, and of forming s~ in fp32
+    m.eps_acc = (K + 8.0) * 2.4e-7 * sqrt(m.qn_bf * xn_bf) * 1.001 + (K / 16.0 + 8.0) * 1.2e-7 * (xn_bf + m.qn_bf);
+    m.eta = (static_cast<double>(p.q_err[q]) + static_cast<double>(__uint_as_float(*p.max_x_err_bits))) * (1.0 + 1e-6) + 1e-30;
+    return m;
+}
+
+// Final step of a re-rank, executed by ONE full warp: rank the C exact squared distances by (d2, row), emit the best kk,
+// and certify the answer (or queue the query for the second pass).  keysC: the C best-scored shortlist entries,
+// ascending by (score, row); d2s: their exact squared distances (DBL_MAX = pruned / empty).
+template <int C>
+__device__ __forceinline__ void rerank_finish(const RerankParams &p, int q, const unsigned long long *keys, const double *d2s, int lane) {
+    // rank the exact distances by (d2, index); each lane owns candidates lane, lane + 32 (C <= 64)
+    constexpr int H = (C + 31) / 32;
+    double myd[H];
+    uint32_t myi[H];
+    int rank[H];
+#pragma unroll
+    for (int h = 0; h < H; h++) {
+        const int c = lane + 32 * h;
+        myd[h] = (c < C) ? d2s[c] : DBL_MAX;
+        myi[h] = (c < C) ? static_cast<uint32_t>(keys[c]) : 0xffffffffu;
+        rank[h] = 0;
+    }
+#pragma unroll
+    for (int g = 0; g < H; g++) {
+#pragma unroll
+        for (int o = 0; o < 32; o++) {
+            const double od = __shfl_sync(0xffffffffu, myd[g], o);
+            const uint32_t oi = __shfl_sync(0xffffffffu, myi[g], o);
+#pragma unroll
+            for (int h = 0; h < H; h++) rank[h] += (od < myd[h] || (od == myd[h] && oi < myi[h])) ? 1 : 0;
+        }
+    }
+    double dk2 = DBL_MAX;
+    unsigned mk = 0;
+#pragma unroll
+    for (int h = 0; h < H; h++) {
+        const bool valid = (lane + 32 * h) < C;
+        if (valid && rank[h] < p.kk) {
+            p.out_idx[static_cast<int64_t>(q) * p.kk + rank[h]] = static_cast<int32_t>(p.index_base + myi[h]);
+            p.out_dist[static_cast<int64_t>(q) * p.kk + rank[h]] = (p.flags & 1u) ? myd[h] : sqrt(myd[h]);
+        }
+        // k-th exact distance (rank kk-1), broadcast
+        const unsigned mh = __ballot_sync(0xffffffffu, valid && rank[h] == p.kk - 1);
+        const double dh = __shfl_sync(0xffffffffu, myd[h], mh ? (__ffs(mh) - 1) : 0);
+        if (mh) { dk2 = dh; mk = mh; }
+    }
+    if (lane == 0 && !(p.flags & 2u)) {
+        // ---- certificate: every pool row NOT among the C kept has score >= tau (the C-th kept score), hence
+        // true distance >= lower(tau).  The answer is exact when the kk-th exact distance is below that.
+        bool certified = true;
+        const unsigned long long kc = keys[C - 1];
+        const ErrModel em = make_err_model(p, q);
+        const double dk = sqrt(dk2);
+        if (p.n > C && kc != ~0ull && mk != 0) {
+            const double lb = em.lower(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(kc >> 32))));
+            certified = (lb > 0.0) && (dk < lb);
+        } else if (mk == 0) {
+            certified = (p.n <= C);
+        }
+        if (!certified) {
+            // second pass collects every row with score <= thr: any x with d(q,x) <= dk has
+            // ||q~ - x~|| <= dk + eta, i.e. s~ <= (dk + eta)^2 - ||q~||^2 + eps_acc.
+            const double t = (dk + em.eta) * (dk + em.eta) - em.qn_bf + em.eps_acc;
+            const int slot = atomicAdd(p.uncert_count, 1);
+            p.uncert_list[slot] = q;
+            p.uncert_thr[slot] = __double2float_ru(t + 1e-6 * fabs(t));
+        }
+    }
+}
+
+template <typename TX, typename TQ, int C, int NT>
+__global__ void __launch_bounds__(NT)
+rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const RerankParams p) {
+    extern __shared__ unsigned long long keys[];   // next_pow2(max_slots * C) entries (host-sized, <= MAX_KEYS)
+    __shared__ double d2s[C];
+    __shared__ int m_s;
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int total = __ldg(p.slots_per_qtile + q / p.qtile_rows) * C;
+    int P = 1;
+    while (P < total) P <<= 1;
+
+    for (int i = tid; i < P; i += blockDim.x) {
+        unsigned long long key = ~0ull;
+        if (i < total) {
+            const int64_t o = static_cast<int64_t>(q) * p.max_slots * C + i;
+            const int idx = p.cand_i[o];
+            if (idx >= 0) key = (static_cast<unsigned long long>(float_order_bits(p.cand_s[o])) << 32) | static_cast<uint32_t>(idx);
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    // bitonic sort, ascending by (score, index)
+    for (int k2 = 2; k2 <= P; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long a = keys[i], b = keys[l];
+                    const bool up = (i & k2) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // Pruning: candidate c (ascending score) can be among the true top-kk only if its distance lower bound does not
+    // exceed the kk-th smallest distance upper bound.  Scores are sorted, so the survivors are a prefix of length m.
+    if (tid == 0) {
+        int m = min(C, p.kk);
+        if (keys[p.kk - 1] != ~0ull) {
+            const ErrModel em = make_err_model(p, q);
+            const double u = em.upper(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(keys[p.kk - 1] >> 32))));
+            while (m < C && keys[m] != ~0ull &&
+                   em.lower(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(keys[m] >> 32)))) <= u) m++;
+        } else {
+            m = C;
+        }
+        m_s = m;
+    }
+    __syncthreads();
+    int m = m_s;
+    // exact float64 distances of the surviving candidates (the arithmetic of util.c:62-69, tree-summed).  The whole
+    // block works on one candidate at a time: every thread owns a strided slice of the dimensions, keeps its slice
+    // of the query row in registers across candidates, and issues its loads of the pool row back to back.
+    const int warp = tid >> 5, lane = tid & 31;
+    const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
+    constexpr int RQ = 24;                      // dims per thread held in registers (128 threads x 24 = 3072)
+    constexpr int nth = 128;                    // the canonical 128 lanes (see canon_d2); extra threads of the 1024-thread
+    const bool act = tid < nth;                 // flavour only help with the merge sort above
+    __shared__ double partial[4];
+    double qreg[RQ];
+    const bool fits = p.dim <= RQ * nth;
+    if (fits && act) {
+        // raw loads first, conversions after: a float->double conversion placed right behind its load would make the
+        // in-order warp wait for that load before issuing the next one (24 serialized DRAM round trips)
+        TQ qraw[RQ];
+#pragma unroll
+        for (int i = 0; i < RQ; i++) {
+            const int e = tid + i * nth;
+            qraw[i] = (e < p.dim) ? qr[e] : TQ(0);
+        }
+#pragma unroll
+        for (int i = 0; i < RQ; i++) keep(qraw[i]);
+#pragma unroll
+        for (int i = 0; i < RQ; i++) qreg[i] = static_cast<double>(qraw[i]);
+    }
+    for (int c = 0; c < C; c++) {
+        if (c == p.kk && c < m) {               // uniform across the block
+            // kk exact distances are known: the kk-th true distance is at most their maximum, which is a far tighter
+            // pruning limit than the a-priori upper bound (the survivors stay a prefix: scores are sorted)
+            __syncthreads();                    // d2s[0..kk) were written by thread 0, possibly without a barrier since
+            if (warp == 0) {
+                double mx = 0.0;
+                for (int i = lane; i < p.kk; i += 32) mx = fmax(mx, d2s[i]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                int cnt = 0;
+                if (mx < DBL_MAX) {
+                    const ErrModel em = make_err_model(p, q);
+                    const double dk = sqrt(mx);
+                    for (int i = p.kk + lane; i < m; i += 32)
+                        cnt += (keys[i] != ~0ull && em.lower(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(keys[i] >> 32)))) <= dk) ? 1 : 0;
+                } else {
+                    cnt = (lane == 0) ? m - p.kk : 0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                if (lane == 0) m_s = p.kk + cnt;
+            }
+            __syncthreads();
+            m = m_s;
+        }
+        const unsigned long long key = keys[c];
+        if (c >= m || key == ~0ull) {           // uniform across the block
+            if (tid == 0) d2s[c] = DBL_MAX;
+            continue;
+        }
+        const TX *xr = x + static_cast<int64_t>(static_cast<uint32_t>(key)) * p.ld_x;
+        if (!fits) {
+            const double tot = canon_d2(xr, qr, p.dim, tid, partial);
+            if (tid == 0) d2s[c] = tot;
+            continue;
+        }
+        if (act) {                               // same order as canon_d2, query slice already in registers
+            double a0 = 0.0, a1 = 0.0;
+            TX xraw[RQ];
+#pragma unroll
+            for (int i = 0; i < RQ; i++) {
+                const int e = tid + i * nth;
+                xraw[i] = (e < p.dim) ? xr[e] : TX(0);
+            }
+#pragma unroll
+            for (int i = 0; i < RQ; i++) keep(xraw[i]);
+#pragma unroll
+            for (int i = 0; i < RQ; i += 2) {
+                const double d0 = qreg[i] - static_cast<double>(xraw[i]), d1 = qreg[i + 1] - static_cast<double>(xraw[i + 1]);
+                a0 = fma(d0, d0, a0);
+                a1 = fma(d1, d1, a1);
+            }
+            const double w = warp_sum(a0 + a1);
+            if (lane == 0) partial[warp] = w;
+        }
+        __syncthreads();
+        if (tid == 0) d2s[c] = ((partial[0] + partial[1]) + partial[2]) + partial[3];
+        __syncthreads();
+    }
+    __syncthreads();
+    if (warp == 0) rerank_finish<C>(p, q, keys, d2s, lane);
+}
+
+// Second pass, part 2: exact re-rank of the collected lists.  One block per uncertified query (list slot).
+// Lists longer than the capacity (or shorter than kk) are handed to the exact scan via the overflow list.
+constexpr int COLLECT_CAP = 1024;
+struct CollectRerankParams {
+    const int *uncert_list;      // [nun] query rows
+    const int *coll_count;       // [nun]
+    const int *coll_idx;         // [nun][COLLECT_CAP]
+    int dim;
+    int64_t ld_x, ld_q;
+    int kk;
+    int64_t index_base;
+    unsigned flags;
+    int32_t *out_idx;
+    double *out_dist;
+    int *overflow_count;
+    int *overflow_list;          // query rows that need the exact scan
+};
+
+template <typename TX, typename TQ>
+__global__ void __launch_bounds__(256)
+rerank_collect_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const CollectRerankParams p) {
+    __shared__ double d2[COLLECT_CAP];
+    __shared__ int idx[COLLECT_CAP];
+    __shared__ double sd[8];
+    __shared__ int si[8];
+    __shared__ double last_d_s;
+    __shared__ int last_i_s;
+    const int slot = blockIdx.x;
+    const int q = p.uncert_list[slot];
+    const int cnt = p.coll_count[slot];
+    if (cnt > COLLECT_CAP || cnt < p.kk) {
+        if (threadIdx.x == 0) {
+            const int o = atomicAdd(p.overflow_count, 1);
+            p.overflow_list[o] = q;
+        }
+        return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
+    for (int c = warp; c < cnt; c += 8) {       // one candidate per warp, canonical summation order
+        const int j = p.coll_idx[static_cast<int64_t>(slot) * COLLECT_CAP + c];
+        const double a0 = canon_d2_warp(x + static_cast<int64_t>(j) * p.ld_x, qr, p.dim, lane);
+        if (lane == 0) { d2[c] = a0; idx[c] = j; }
+    }
+    if (threadIdx.x == 0) { last_d_s = -1.0; last_i_s = -1; }
+    __syncthreads();
+    for (int r = 0; r < p.kk; r++) {
+        const double ld = last_d_s;
+        const int li = last_i_s;
+        double bd = DBL_MAX;
+        int bi = 0x7fffffff;
+        for (int c = threadIdx.x; c < cnt; c += blockDim.x) {
+            const double d = d2[c];
+            const int j = idx[c];
+            const bool after = (d > ld) || (d == ld && j > li);
+            if (after && (d < bd || (d == bd && j < bi))) { bd = d; bi = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        __syncthreads();
+        if (lane == 0) { sd[warp] = bd; si[warp] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; w++)
+                if (sd[w] < bd || (sd[w] == bd && si[w] < bi)) { bd = sd[w]; bi = si[w]; }
+            last_d_s = bd;
+            last_i_s = bi;
+            p.out_idx[static_cast<int64_t>(q) * p.kk + r] = static_cast<int32_t>(p.index_base + bi);
+            p.out_dist[static_cast<int64_t>(q) * p.kk + r] = (p.flags & 1u) ? bd : sqrt(bd);
+        }
+        __syncthreads();
+    }
+}
+
+// gather BF16 query rows of the uncertified queries into a compact matrix for the collection pass
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const __nv_bfloat16 *__restrict__ src, const int *__restrict__ list, int nsel, int kp, __nv_bfloat16 *__restrict__ dst) {
+    const int vec_per_row = kp >> 3;   // kp is a multiple of 8: 16-byte chunks
+    const int64_t total = static_cast<int64_t>(nsel) * vec_per_row;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / vec_per_row), c = static_cast<int>(i % vec_per_row);
+        reinterpret_cast<uint4 *>(dst + static_cast<int64_t>(r) * kp)[c] =
+            reinterpret_cast<const uint4 *>(src + static_cast<int64_t>(list[r]) * kp)[c];
+    }
+}
+
+}  // namespace b200

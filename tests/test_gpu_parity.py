@@ -357,7 +357,7 @@ def _bf16_round(a):
 def test_tensor_scores_within_the_certified_error_model(lib, kind, n, q, d):
     """The certificate is only as good as its error model.  Pull the raw tensor-core scores of the shortlists and
     check them against float64 arithmetic on the BF16-rounded (mean-centred) inputs: |s~_gpu - (||x~||^2 - 2 q~.x~)| must stay
-    below the eps_acc the kernels assume (kernels.cuh make_err_model), and every kept score must bracket the true
+    below the eps_acc the kernels assume (csrc/rerank.cuh make_err_model), and every kept score must bracket the true
     distance through the exact perturbation norms ||q-q~||, ||x-x~||."""
     from inclusivegan_b200 import DCI
     x, y = make(kind, n, q, d, seed=d + n)
@@ -448,7 +448,7 @@ def test_extension_stand_in_functions(lib):
 
 
 def test_results_do_not_depend_on_batching_or_path(lib):
-    """Every emitting kernel sums a distance in one canonical order (kernels.cuh canon_d2): the same query answered in
+    """Every emitting kernel sums a distance in one canonical order (csrc/rerank.cuh canon_d2): the same query answered in
     one big call, in 24-row calls (different kernel flavour, 1024-thread re-rank), or via the second pass gives
     bit-identical distances and indices."""
     from inclusivegan_b200 import DCI
