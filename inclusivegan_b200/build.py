@@ -15,7 +15,7 @@ _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libb200knn.so")
 _STAMP = os.path.join(_HERE, ".libb200knn.stamp")
 SOURCES = ["b200knn.cu"]
-HEADERS = ["kernels.cuh", "common.cuh", "convert.cuh", "dist.cuh", "rerank.cuh", "scan.cuh", "member.cuh", "exchange.cuh", "project.cuh", "ptx.cuh",
+HEADERS = ["host_util.cuh", "shard.cuh", "kernels.cuh", "common.cuh", "convert.cuh", "dist.cuh", "rerank.cuh", "scan.cuh", "member.cuh", "exchange.cuh", "project.cuh", "ptx.cuh",
            os.path.join(_ROOT, "include", "b200knn.h")]
 
 NVCC_FLAGS = [

@@ -1,0 +1,820 @@
+// One GPU's share of an index: the pool shard (originals, BF16 rows, norms), the work schedule of the distance kernel
+// (Shard::plan), and the kernel sequence that answers a batch of device-resident queries (Shard::query_device).
+#pragma once
+#include "host_util.cuh"
+
+namespace {
+
+enum Kind { K_CONVERT = 0, K_DISTANCE = 1, K_RERANK = 2, K_SCAN = 3, K_NKINDS = 4 };
+
+struct Shard {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;   // the one work is launched on (own or user-provided)
+    bool ready = false;
+
+    // ---- pool ----
+    const void *x_raw = nullptr;     // original rows (f64 or f32), ld_x elements apart
+    void *x_owned = nullptr;         // set when the library owns the copy
+    int x_dtype = B200KNN_F64;
+    int64_t n = 0, ld_x = 0, index_base = 0;
+    DevBuf<__nv_bfloat16> x_bf;
+    DevBuf<float> xnorm_bf, x_err;
+    DevBuf<double> col_mean;         // pool column means (subtracted from pool and queries before BF16 rounding)
+    bool centered = false;
+    bool use_centering = true;       // $B200KNN_CENTER=0 disables
+    DevBuf<unsigned int> scalars;    // [0] max ||x~||^2 bits, [1] max ||x - x~|| bits, [2],[3] same for queries (unused), [4] uncertified count,
+                                     // [5] overflow count, [6] grid-barrier counter of the distance kernel, [7] max (r_j + e_j) bits (ball membership)
+    CUtensorMap tmap_x;              // pool, 256-row box (1-CTA kernel)
+    CUtensorMap tmap_x128;           // pool, 128-row box (each CTA of a pair stages half of the 256-row tile)
+    int forced_cg = 0;               // $B200KNN_CTA_GROUP=1|2 pins the kernel flavour (A/B measurements)
+    unsigned opt_flags = 0;          // $B200KNN_OPT: kernel tuning switches (see DistParams::opt)
+    int a_budget_mb = 64;            // $B200KNN_A_BUDGET_MB: L2 budget for the query tiles of one round
+    int wide_mode = 1;               // $B200KNN_WIDE: 0 never, 1 when cheaper in HBM traffic, 2 always (A/B measurements)
+    int sync_tiles = -1;             // $B200KNN_SYNC_TILES: lockstep interval of the workers sharing a pool-tile stream (-1: by tile length)
+    int max_pairs = 74;              // CTA pairs that can be co-resident (cudaOccupancyMaxActiveClusters)
+
+    // ---- query workspace ----
+    DevBuf<__nv_bfloat16> q_bf;
+    DevBuf<float> qnorm_bf, q_err;
+    DevBuf<__nv_bfloat16> q_bf2;     // second pass: BF16 rows of the uncertified queries
+    DevBuf<float> uncert_thr;
+    DevBuf<int> coll_count, coll_idx, overflow_list;
+    DevBuf<WorkItem> sched_items;    // first-pass schedule (cached across calls of the same shape: the trainer's 24-row loop)
+    DevBuf<WorkItem> sched_items2;   // second pass / membership schedules
+    DevBuf<double> radius2;          // ball membership: squared radii of this shard's rows
+    DevBuf<float> colterm, rowthr;
+    DevBuf<unsigned char> member;
+    DevBuf<unsigned int> stream_sync;
+    DevBuf<int> sched_slots;
+    DevBuf<float> cand_s;
+    DevBuf<int> cand_i;
+    DevBuf<int> uncert_list;
+    DevBuf<double> scan_d2, scan_d2_sorted;
+    DevBuf<int> scan_iota, scan_vals_sorted, scan_offsets;
+    DevBuf<unsigned char> cub_tmp;
+    DevBuf<unsigned char> q_stage;   // host API: device copy of the caller's query rows
+    DevBuf<unsigned char> q_stage2;  // second buffer: the upload of chunk i+1 overlaps the compute of chunk i
+    cudaStream_t copy_stream = nullptr;
+    int copy_threads = 8;            // $B200KNN_COPY_THREADS
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    DevBuf<int32_t> out_idx;
+    DevBuf<double> out_dist;
+    int *h_count = nullptr;          // pinned
+    const __nv_bfloat16 *cur_q_bf = nullptr;   // BF16 query rows of the tensor pass in flight (second pass gathers from them)
+    int64_t last_nq = 0;             // geometry of the last tensor pass (b200knn_debug_shortlists)
+    int last_slots = 0, last_c = 0;
+
+    // ---- stats ----
+    b200knn_stats stats{};
+    bool profiling = false;
+    struct Ev { cudaEvent_t a, b; int kind; double flops; };
+    std::vector<Ev> events;
+
+    int init(int dev) {
+        device = dev;
+        CU_TRY(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CU_TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            return fail(B200KNN_ENODEVICE, "device %d (%s, sm_%d%d) is not an sm_100 (B200) GPU; libb200knn has no other code path",
+                        device, prop.name, prop.major, prop.minor);
+        num_sms = prop.multiProcessorCount;
+        CU_TRY(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+        stream = own_stream;
+        CU_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU_TRY(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&ev_consumed[i], cudaEventDisableTiming));
+        }
+        TRY(scalars.ensure(8));
+        CU_TRY(cudaMemsetAsync(scalars.p, 0, 8 * sizeof(unsigned int), stream));
+        CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&h_count), sizeof(int)));
+        TRY(set_kernel_attrs());
+        ready = true;
+        return B200KNN_OK;
+    }
+    int set_kernel_attrs() {
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<16, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<1>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<32, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<1>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<16, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<1>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<16, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<32, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<16, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<64, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<1>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<64, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
+        if (const char *o = getenv("B200KNN_OPT")) opt_flags = static_cast<unsigned>(atoi(o));
+        if (const char *o = getenv("B200KNN_A_BUDGET_MB")) a_budget_mb = std::max(1, atoi(o));
+        if (const char *o = getenv("B200KNN_SYNC_TILES")) sync_tiles = std::max(0, atoi(o));
+        if (const char *o = getenv("B200KNN_WIDE")) wide_mode = atoi(o);
+        if (const char *o = getenv("B200KNN_COPY_THREADS")) copy_threads = std::max(1, atoi(o));
+        if (const char *o = getenv("B200KNN_CENTER")) use_centering = atoi(o) != 0;
+        copy_threads = std::min<int>(copy_threads, std::max(1u, std::thread::hardware_concurrency()));
+        const char *e = getenv("B200KNN_CTA_GROUP");
+        if (e && (e[0] == '1' || e[0] == '2')) forced_cg = e[0] - '0';
+        // a persistent, statically-strided grid must be fully co-resident: ask how many CTA pairs fit at once
+        {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(num_sms / 2 * 2);
+            cfg.blockDim = dim3(DIST_THREADS);
+            cfg.dynamicSmemBytes = DistCfg<2>::SMEM_BYTES;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, dist_topc_kernel<16, false, 2>, &cfg) == cudaSuccess && nc > 0) max_pairs = std::min(nc, num_sms / 2);
+            else { cudaGetLastError(); max_pairs = num_sms / 2; }
+            const char *g = getenv("B200KNN_MAX_PAIRS");
+            if (g && atoi(g) > 0) max_pairs = atoi(g);
+            if (getenv("B200KNN_VERBOSE")) fprintf(stderr, "[b200knn] device %d: %d SMs, %d co-resident CTA pairs (occupancy query %d)\n", device, num_sms, max_pairs, nc);
+        }
+        return B200KNN_OK;
+    }
+    void prof_begin(int kind, double flops = 0.0) {
+        stats.kernel_launches++;
+        if (!profiling) return;
+        Ev e;
+        cudaEventCreate(&e.a);
+        cudaEventCreate(&e.b);
+        e.kind = kind;
+        e.flops = flops;
+        cudaEventRecord(e.a, stream);
+        events.push_back(e);
+    }
+    void prof_end() {
+        if (!profiling) return;
+        cudaEventRecord(events.back().b, stream);
+    }
+    void drain_events() {
+        for (auto &e : events) {
+            cudaEventSynchronize(e.b);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e.a, e.b);
+            switch (e.kind) {
+                case K_CONVERT: stats.ms_convert += ms; break;
+                case K_DISTANCE: stats.ms_distance += ms; stats.distance_launches++; stats.distance_flops += e.flops; break;
+                case K_RERANK: stats.ms_rerank += ms; break;
+                default: stats.ms_scan += ms; break;
+            }
+            cudaEventDestroy(e.a);
+            cudaEventDestroy(e.b);
+        }
+        events.clear();
+    }
+    void clear_pool() {
+        if (!ready) return;
+        cudaSetDevice(device);
+        cudaStreamSynchronize(stream);
+        if (x_owned) cudaFree(x_owned);
+        x_owned = nullptr;
+        x_raw = nullptr;
+        n = 0;
+        sched1.key_nq = -1;
+        x_bf.release();
+        xnorm_bf.release();
+        x_err.release();
+        centered = false;
+    }
+    void destroy() {
+        if (!ready) return;
+        clear_pool();
+        drain_events();
+        q_bf.release(); qnorm_bf.release(); q_err.release(); q_bf2.release(); uncert_thr.release(); coll_count.release(); coll_idx.release(); overflow_list.release(); sched_items.release(); sched_items2.release(); sched_slots.release(); stream_sync.release(); radius2.release(); colterm.release(); rowthr.release(); member.release(); cand_s.release(); cand_i.release(); uncert_list.release();
+        scan_d2.release(); scan_d2_sorted.release(); scan_iota.release(); scan_vals_sorted.release(); scan_offsets.release();
+        cub_tmp.release(); q_stage.release(); q_stage2.release(); out_idx.release(); out_dist.release(); scalars.release();
+        if (h_count) cudaFreeHost(h_count);
+        if (own_stream) cudaStreamDestroy(own_stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        for (int i = 0; i < 2; i++) {
+            if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
+            if (ev_consumed[i]) cudaEventDestroy(ev_consumed[i]);
+        }
+        ready = false;
+    }
+
+    // ------------------------------------------------------------------ host -> device rows
+    // rows x row_bytes, source pitch src_pitch, destination packed.  Pinned / registered sources are DMA'd directly.
+    // Pageable sources (what NumPy hands over) go through the pinned ring: several host threads memcpy a 32 MB piece
+    // into a ring slot, the slot is DMA'd asynchronously, and the next piece is being filled meanwhile.
+    int upload_rows(void *dst, const char *src, int64_t rows, size_t row_bytes, size_t src_pitch, cudaStream_t st) {
+        if (rows <= 0) return B200KNN_OK;
+        cudaPointerAttributes attr;
+        bool pinned = false;
+        if (cudaPointerGetAttributes(&attr, src) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+        else cudaGetLastError();
+        const size_t total = static_cast<size_t>(rows) * row_bytes;
+        if (pinned || total <= (8u << 20)) {   // small pageable copies: the driver's own staging is faster than spawning threads
+            if (src_pitch == row_bytes) CU_TRY(cudaMemcpyAsync(dst, src, total, cudaMemcpyHostToDevice, st));
+            else CU_TRY(cudaMemcpy2DAsync(dst, row_bytes, src, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, st));
+            return B200KNN_OK;
+        }
+        PinnedRing &rg = g_rings[device & 63];
+        std::lock_guard<std::mutex> lock(rg.mu);     // one upload at a time per device
+        for (int i = 0; i < PinnedRing::RING; i++) {
+            if (!rg.buf[i]) {
+                CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&rg.buf[i]), PinnedRing::BYTES));
+                CU_TRY(cudaEventCreateWithFlags(&rg.done[i], cudaEventDisableTiming));
+            }
+        }
+        const size_t RING_BYTES = PinnedRing::BYTES;
+        const int64_t piece_rows = std::max<int64_t>(1, static_cast<int64_t>(RING_BYTES / row_bytes));
+        if (row_bytes > RING_BYTES) {   // absurdly wide rows: let the driver stage them
+            CU_TRY(cudaMemcpy2DAsync(dst, row_bytes, src, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, st));
+            return B200KNN_OK;
+        }
+        for (int64_t r0 = 0; r0 < rows; r0 += piece_rows) {
+            const int64_t pr = std::min(piece_rows, rows - r0);
+            const int slot = rg.next;
+            rg.next = (rg.next + 1) % PinnedRing::RING;
+            if (rg.used[slot]) CU_TRY(cudaEventSynchronize(rg.done[slot]));   // its previous DMA has drained
+            unsigned char *buf = rg.buf[slot];
+            const char *sp = src + static_cast<size_t>(r0) * src_pitch;
+            const int nt = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(copy_threads, pr), static_cast<int64_t>(pr * row_bytes) >> 21)));
+            auto work = [&](int t) {
+                const int64_t a = pr * t / nt, b = pr * (t + 1) / nt;
+                if (src_pitch == row_bytes) {
+                    std::memcpy(buf + static_cast<size_t>(a) * row_bytes, sp + static_cast<size_t>(a) * src_pitch, static_cast<size_t>(b - a) * row_bytes);
+                } else {
+                    for (int64_t r = a; r < b; r++) std::memcpy(buf + static_cast<size_t>(r) * row_bytes, sp + static_cast<size_t>(r) * src_pitch, row_bytes);
+                }
+            };
+            if (nt == 1) {
+                work(0);
+            } else {
+                std::vector<std::thread> th;
+                th.reserve(nt - 1);
+                for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+                work(0);
+                for (auto &x : th) x.join();
+            }
+            CU_TRY(cudaMemcpyAsync(static_cast<char *>(dst) + static_cast<size_t>(r0) * row_bytes, buf, static_cast<size_t>(pr) * row_bytes,
+                                   cudaMemcpyHostToDevice, st));
+            CU_TRY(cudaEventRecord(rg.done[slot], st));
+            rg.used[slot] = true;
+        }
+        return B200KNN_OK;
+    }
+
+    // ------------------------------------------------------------------ pool mean (centering)
+    int compute_mean(const void *d_rows, int dtype, int64_t rows, int64_t ld, int dim) {
+        centered = false;
+        if (!use_centering || rows <= 0) return B200KNN_OK;
+        TRY(col_mean.ensure(dim));
+        CU_TRY(cudaMemsetAsync(col_mean.p, 0, static_cast<size_t>(dim) * sizeof(double), stream));
+        dim3 grid(static_cast<unsigned>((dim + 255) / 256), static_cast<unsigned>((rows + 255) / 256));
+        prof_begin(K_CONVERT);
+        if (dtype == B200KNN_F64) colsum_kernel<double><<<grid, 256, 0, stream>>>(static_cast<const double *>(d_rows), rows, ld, dim, col_mean.p);
+        else colsum_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(d_rows), rows, ld, dim, col_mean.p);
+        prof_end();
+        prof_begin(K_CONVERT);
+        scale_kernel<<<(dim + 255) / 256, 256, 0, stream>>>(col_mean.p, dim, 1.0 / static_cast<double>(rows));
+        prof_end();
+        CU_TRY(cudaGetLastError());
+        centered = true;
+        return B200KNN_OK;
+    }
+
+    // ------------------------------------------------------------------ kernels: convert
+    int launch_convert(const void *src, int dtype, int64_t rows, int64_t ld, int dim, int kp, __nv_bfloat16 *dst, float *nbf,
+                       float *nex, unsigned int *maxbits /* [2] */) {
+        const double *mu = centered ? col_mean.p : nullptr;
+        if (rows <= 0) return B200KNN_OK;
+        const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
+        const int vec = (dim % 8 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0) && ((ld * esz) % 16 == 0);
+        const int warps_per_block = 8;
+        int64_t blocks = (rows + warps_per_block - 1) / warps_per_block;
+        blocks = std::min<int64_t>(blocks, static_cast<int64_t>(num_sms) * 8);
+        prof_begin(K_CONVERT);
+        if (dtype == B200KNN_F64)
+            convert_norm_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+                static_cast<const double *>(src), mu, rows, ld, dim, kp, vec, dst, nbf, nex, maxbits, maxbits + 1);
+        else
+            convert_norm_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+                static_cast<const float *>(src), mu, rows, ld, dim, kp, vec, dst, nbf, nex, maxbits, maxbits + 1);
+        prof_end();
+        CU_TRY(cudaGetLastError());
+        return B200KNN_OK;
+    }
+
+    // ------------------------------------------------------------------ pool
+    int attach_pool(const void *d_rows, bool owned, int dtype, int64_t rows, int64_t ld, int dim, int kp, int64_t base) {
+        x_raw = d_rows;
+        x_owned = owned ? const_cast<void *>(d_rows) : nullptr;
+        x_dtype = dtype;
+        n = rows;
+        ld_x = ld;
+        index_base = base;
+        TRY(x_bf.ensure(static_cast<size_t>(rows) * kp));
+        TRY(xnorm_bf.ensure(rows));
+        TRY(x_err.ensure(rows));
+        CU_TRY(cudaMemsetAsync(scalars.p, 0, 2 * sizeof(unsigned int), stream));
+        TRY(make_tmap(&tmap_x, x_bf.p, rows, kp, BN));
+        TRY(make_tmap(&tmap_x128, x_bf.p, rows, kp, BN / 2));
+        return B200KNN_OK;
+    }
+
+    // ------------------------------------------------------------------ schedule
+    // ------------------------------------------------------------------ schedule
+    // One round per group of query tiles: the group's `gs` tiles x `rc` chunks of the pool are processed side by side
+    // (gs * rc <= workers), every worker sweeping NT/rc pool tiles (+-1).  The group's BF16 query rows (gs tiles) stay
+    // in L2 for the whole round while `rc` pool-tile streams pass through once, each shared by `gs` workers that run
+    // in lockstep: HBM traffic per round is ~ one pass over the pool instead of one per worker.
+    struct Sched {
+        int cg, qt, nt, workers, nrounds, max_slots, grid, qg;
+        bool wide = false;                  // rounds run in round-wide lockstep (long K)
+        int64_t key_nq = -1, key_n = -1;
+        int key_kp = -1, key_slots = -1;
+        bool matches(int64_t nq_, int64_t n_, int kp_, int slots_) const { return key_nq == nq_ && key_n == n_ && key_kp == kp_ && key_slots == slots_; }
+        std::vector<WorkItem> items;        // [nrounds][workers]
+        std::vector<int> slots_per_qtile;   // [qt]
+    };
+    Sched sched1;   // cached first-pass schedule
+    int plan(Sched &s, int64_t nq, int kp, int max_slots_allowed) const {
+        s.key_nq = nq;
+        s.key_n = n;
+        s.key_kp = kp;
+        s.key_slots = max_slots_allowed;
+        s.cg = forced_cg ? forced_cg : (nq > BM ? 2 : 1);
+        s.workers = std::max(1, s.cg == 2 ? max_pairs : num_sms);
+        const int W = s.workers;
+        const int qrows = BM * s.cg;
+        s.qt = static_cast<int>((nq + qrows - 1) / qrows);
+        s.nt = static_cast<int>((n + BN - 1) / BN);
+        // group size: as many query tiles as the L2 budget for the A operand allows, preferring sizes that tile the
+        // worker count exactly
+        const int64_t a_tile_bytes = static_cast<int64_t>(qrows) * kp * 2;
+        const int g_cap = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(W, (static_cast<int64_t>(a_budget_mb) << 20) / std::max<int64_t>(a_tile_bytes, 1))));
+        int qg = 1;
+        double best_util = -1.0;
+        for (int g = 1; g <= std::min(g_cap, s.qt); g++) {
+            const int rc = std::min(std::min(W / g, s.nt), max_slots_allowed);
+            const double util = static_cast<double>(g) * rc / W;
+            if (util >= best_util - 1e-12) { best_util = util; qg = g; }   // ties -> larger group (fewer rounds)
+        }
+        // Long K: only a few query tiles fit in L2 and each pool tile would be re-streamed from HBM for every small
+        // group.  Alternative: a gs x rc grid of (query tile, pool stream) workers that advance through K together
+        // (round-wide lockstep at every tile): a K block of a query tile is fetched once for its rc users and a K block
+        // of a pool tile once for its gs users, nothing has to stay resident.  HBM rows fetched per output tile:
+        // resident BN / gs, grid (gs * qrows + rc * BN) / (gs * rc); the cheaper one wins.
+        int wide_g = 0;
+        if (wide_mode != 0) {
+            const int rc_res = std::max(1, std::min(std::min(W / qg, s.nt), max_slots_allowed));
+            const double res_cost = static_cast<double>(BN) / qg / std::min(1.0, static_cast<double>(qg) * rc_res / W);
+            double best_cost = 1e30;
+            int bg = 0;
+            for (int g = 2; g <= std::min(s.qt, 255); g++) {
+                const int rc = std::min(std::min(W / g, s.nt), max_slots_allowed);
+                if (rc < 2 || g * rc > 255) continue;
+                const double util = static_cast<double>(g) * rc / W;
+                const double cost = (static_cast<double>(g) * qrows + static_cast<double>(rc) * BN) / (static_cast<double>(g) * rc) / util;
+                if (cost < best_cost) { best_cost = cost; bg = g; }
+            }
+            if (bg && (wide_mode == 2 || best_cost < 0.85 * res_cost)) wide_g = bg;
+            if (wide_g) qg = wide_g;
+        }
+        s.wide = wide_g != 0;
+        s.qg = qg;
+        s.items.clear();
+        s.slots_per_qtile.assign(s.qt, 0);
+        s.nrounds = 0;
+        s.max_slots = 1;
+        for (int q0 = 0; q0 < s.qt; q0 += qg) {
+            const int gs = std::min(qg, s.qt - q0);
+            int rc = std::max(1, std::min(std::min(W / gs, s.nt), max_slots_allowed));
+            if (s.wide && gs * rc > 255) rc = 255 / gs;
+            const int wide_bits = (s.wide && gs > 1 && rc > 1) ? static_cast<int>(static_cast<unsigned int>(gs * rc) << 24) : 0;
+            s.max_slots = std::max(s.max_slots, rc);
+            s.items.resize(static_cast<size_t>(s.nrounds + 1) * W, WorkItem{-1, 0, 0, 0});
+            WorkItem *row = s.items.data() + static_cast<size_t>(s.nrounds) * W;
+            // chunk-major: workers sharing a pool-tile stream are neighbours
+            for (int c = 0; c < rc; c++) {
+                const int t0 = static_cast<int>(static_cast<int64_t>(c) * s.nt / rc);
+                const int t1 = static_cast<int>(static_cast<int64_t>(c + 1) * s.nt / rc);
+                for (int g = 0; g < gs; g++) row[c * gs + g] = WorkItem{q0 + g, t0, t1, c | (gs << 16) | wide_bits};
+            }
+            for (int g = 0; g < gs; g++) s.slots_per_qtile[q0 + g] = rc;
+            s.nrounds++;
+        }
+        s.grid = s.cg * W;
+        return B200KNN_OK;
+    }
+    // upload the schedule (small: a few KB) and reset the round barrier / lockstep counters
+    int upload_schedule(const Sched &s, DevBuf<WorkItem> &items_dst, bool with_slots, bool cached) {
+        if (!cached) {
+            TRY(items_dst.ensure(s.items.size()));
+            // (copies from pageable host memory are staged before cudaMemcpyAsync returns: no synchronisation needed)
+            CU_TRY(cudaMemcpyAsync(items_dst.p, s.items.data(), s.items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, stream));
+            if (with_slots) {
+                TRY(sched_slots.ensure(s.slots_per_qtile.size()));
+                CU_TRY(cudaMemcpyAsync(sched_slots.p, s.slots_per_qtile.data(), s.slots_per_qtile.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+            }
+        }
+        CU_TRY(cudaMemsetAsync(scalars.p + 6, 0, sizeof(unsigned int), stream));
+        TRY(stream_sync.ensure(static_cast<size_t>(s.nrounds) * s.max_slots));
+        CU_TRY(cudaMemsetAsync(stream_sync.p, 0, static_cast<size_t>(s.nrounds) * s.max_slots * sizeof(unsigned int), stream));
+        return B200KNN_OK;
+    }
+
+    template <int C, bool COLLECT>
+    int launch_dist(const Sched &s, const CUtensorMap &tmap_q, const DistParams &dp) {
+        if (s.cg == 2) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(s.grid);
+            cfg.blockDim = dim3(DIST_THREADS);
+            cfg.dynamicSmemBytes = DistCfg<2>::SMEM_BYTES;
+            cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            CU_TRY(cudaLaunchKernelEx(&cfg, dist_topc_kernel<C, COLLECT, 2>, tmap_q, tmap_x128, dp));
+        } else {
+            dist_topc_kernel<C, COLLECT, 1><<<s.grid, DIST_THREADS, DistCfg<1>::SMEM_BYTES, stream>>>(tmap_q, tmap_x, dp);
+        }
+        CU_TRY(cudaGetLastError());
+        return B200KNN_OK;
+    }
+
+    // ------------------------------------------------------------------ exact scan of a query subset
+    template <typename TX, typename TQ>
+    int scan_typed(const TQ *d_query, int64_t ld_q, const int *d_qlist, int nsub, int dim, int kk, unsigned flags,
+                   int32_t *d_out_idx, double *d_out_dist) {
+        const TX *x = static_cast<const TX *>(x_raw);
+        // sub-batches bounded to ~1.5 GB of scratch
+        int64_t per_q = n * (kk > 32 ? 24 : 8);
+        int batch = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nsub, (1536ll << 20) / std::max<int64_t>(per_q, 1))));
+        batch = std::max(1, std::min(batch, 4096));
+        TRY(scan_d2.ensure(static_cast<size_t>(batch) * n));
+        for (int s0 = 0; s0 < nsub; s0 += batch) {
+            const int ns = std::min(batch, nsub - s0);
+            // qlist == nullptr means rows s0..s0+ns of the query matrix
+            const TQ *qbase = d_qlist ? d_query : d_query + static_cast<int64_t>(s0) * ld_q;
+            const int *ql = d_qlist ? d_qlist + s0 : nullptr;
+            dim3 grid(static_cast<unsigned>((n + SCAN_TX - 1) / SCAN_TX), static_cast<unsigned>((ns + SCAN_TQ - 1) / SCAN_TQ));
+            prof_begin(K_SCAN);
+            scan_dist_kernel<TX, TQ><<<grid, 256, 0, stream>>>(x, ld_x, static_cast<int>(n), qbase, ld_q, ql, ns, dim, scan_d2.p);
+            prof_end();
+            CU_TRY(cudaGetLastError());
+            int32_t *oi = d_qlist ? d_out_idx : d_out_idx + static_cast<int64_t>(s0) * kk;
+            double *od = d_qlist ? d_out_dist : d_out_dist + static_cast<int64_t>(s0) * kk;
+            if (kk <= 32) {
+                prof_begin(K_SCAN);
+                scan_select_kernel<<<ns, 256, 0, stream>>>(scan_d2.p, static_cast<int>(n), ql, kk, index_base, flags, oi, od);
+                prof_end();
+                CU_TRY(cudaGetLastError());
+            } else {
+                const int64_t total = static_cast<int64_t>(ns) * n;
+                TRY(scan_d2_sorted.ensure(total));
+                TRY(scan_iota.ensure(total));
+                TRY(scan_vals_sorted.ensure(total));
+                TRY(scan_offsets.ensure(ns + 1));
+                std::vector<int> off(ns + 1);
+                for (int i = 0; i <= ns; i++) off[i] = static_cast<int>(static_cast<int64_t>(i) * n);
+                if (total > 0x7fffffffll) return fail(B200KNN_EINVAL, "scan batch too large");
+                CU_TRY(cudaMemcpyAsync(scan_offsets.p, off.data(), (ns + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+                CU_TRY(cudaStreamSynchronize(stream));   // `off` is a stack-lifetime host buffer
+                prof_begin(K_SCAN);
+                iota_kernel<<<num_sms * 4, 256, 0, stream>>>(scan_iota.p, total, static_cast<int>(n));
+                prof_end();
+                size_t tmp_bytes = 0;
+                cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp_bytes, scan_d2.p, scan_d2_sorted.p, scan_iota.p, scan_vals_sorted.p,
+                                                         static_cast<int>(total), ns, scan_offsets.p, scan_offsets.p + 1, 0, 64, stream);
+                TRY(cub_tmp.ensure(tmp_bytes));
+                stats.kernel_launches++;
+                CU_TRY(cub::DeviceSegmentedRadixSort::SortPairs(cub_tmp.p, tmp_bytes, scan_d2.p, scan_d2_sorted.p, scan_iota.p,
+                                                                scan_vals_sorted.p, static_cast<int>(total), ns, scan_offsets.p,
+                                                                scan_offsets.p + 1, 0, 64, stream));
+                prof_begin(K_SCAN);
+                scatter_sorted_kernel<<<num_sms * 4, 256, 0, stream>>>(scan_d2_sorted.p, scan_vals_sorted.p, static_cast<int>(n), ql, ns, kk,
+                                                                      index_base, flags, oi, od);
+                prof_end();
+                CU_TRY(cudaGetLastError());
+            }
+        }
+        return B200KNN_OK;
+    }
+    int scan(const void *d_query, int q_dtype, int64_t ld_q, const int *d_qlist, int nsub, int dim, int kk, unsigned flags,
+             int32_t *d_out_idx, double *d_out_dist) {
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
+            return scan_typed<double, double>(static_cast<const double *>(d_query), ld_q, d_qlist, nsub, dim, kk, flags, d_out_idx, d_out_dist);
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
+            return scan_typed<double, float>(static_cast<const float *>(d_query), ld_q, d_qlist, nsub, dim, kk, flags, d_out_idx, d_out_dist);
+        if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
+            return scan_typed<float, double>(static_cast<const double *>(d_query), ld_q, d_qlist, nsub, dim, kk, flags, d_out_idx, d_out_dist);
+        return scan_typed<float, float>(static_cast<const float *>(d_query), ld_q, d_qlist, nsub, dim, kk, flags, d_out_idx, d_out_dist);
+    }
+
+    // ------------------------------------------------------------------ rerank dispatch
+    template <int C, int NT>
+    void launch_rerank_nt(const void *d_query, int q_dtype, unsigned g, size_t sm, const RerankParams &rp) {
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
+            rerank_kernel<double, double, C, NT><<<g, NT, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), rp);
+        else if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
+            rerank_kernel<double, float, C, NT><<<g, NT, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), rp);
+        else if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
+            rerank_kernel<float, double, C, NT><<<g, NT, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), rp);
+        else
+            rerank_kernel<float, float, C, NT><<<g, NT, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), rp);
+    }
+    template <int C>
+    int launch_rerank(const void *d_query, int q_dtype, int64_t nq, const RerankParams &rp) {
+        prof_begin(K_RERANK);
+        const unsigned g = static_cast<unsigned>(nq);
+        int pk = 1;
+        while (pk < rp.max_slots * C) pk <<= 1;
+        const size_t sm = static_cast<size_t>(pk) * sizeof(unsigned long long);
+        // merging many shortlists for few queries (many pool streams) is a latency-bound sort: give it 32 warps; with
+        // many queries the device is full anyway and the exact sweep (128 lanes per query) is what matters
+        if (pk >= 1024 && nq <= 4096) launch_rerank_nt<C, 1024>(d_query, q_dtype, g, sm, rp);
+        else launch_rerank_nt<C, 128>(d_query, q_dtype, g, sm, rp);
+        prof_end();
+        CU_TRY(cudaGetLastError());
+        return B200KNN_OK;
+    }
+
+    DistParams base_dist_params(int64_t nq, int kp, const Sched &s, const WorkItem *items) const {
+        DistParams dp{};
+        dp.xnorm = xnorm_bf.p;
+        dp.n = static_cast<int>(n);
+        dp.nq = static_cast<int>(nq);
+        dp.num_kb = (kp + BK - 1) / BK;
+        dp.items = items;
+        dp.nrounds = s.nrounds;
+        dp.workers = s.workers;
+        dp.round_counter = scalars.p + 6;
+        dp.stream_sync = stream_sync.p;
+        // sharers drift by time, not by tiles: about one re-alignment per 16 tiles of K = 3072
+        dp.sync_tiles = sync_tiles >= 0 ? sync_tiles : (s.wide ? 1 : std::max(1, 16 * 3072 / std::max(kp, 1)));
+        dp.sync_timeout_ns = 40000u * static_cast<unsigned>(std::max(1, kp / 3072));     // ~2 tile times
+        dp.max_slots = s.max_slots;
+        dp.opt = opt_flags;
+        return dp;
+    }
+
+    // Second pass for the `nun` queries the certificate rejected: the same tcgen05 GEMM, but the epilogue collects
+    // every pool row whose score is within the query's error margin; those short lists are re-ranked exactly.
+    // Lists that overflow go to the exact CUDA-core scan.
+    int second_pass(const void *d_query, int q_dtype, int64_t ld_q, int nun, int dim, int kp, int kk, unsigned flags,
+                    int32_t *d_out_idx, double *d_out_dist) {
+        TRY(q_bf2.ensure(static_cast<size_t>(nun) * kp));
+        TRY(coll_count.ensure(nun));
+        TRY(coll_idx.ensure(static_cast<size_t>(nun) * COLLECT_CAP));
+        TRY(overflow_list.ensure(nun));
+        prof_begin(K_SCAN);
+        gather_rows_kernel<<<std::min<int64_t>(num_sms * 4, (static_cast<int64_t>(nun) * (kp / 8) + 255) / 256), 256, 0, stream>>>(
+            cur_q_bf, uncert_list.p, nun, kp, q_bf2.p);
+        prof_end();
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemsetAsync(coll_count.p, 0, static_cast<size_t>(nun) * sizeof(int), stream));
+        CU_TRY(cudaMemsetAsync(scalars.p + 5, 0, sizeof(unsigned int), stream));
+        CUtensorMap tmap_q2;
+        TRY(make_tmap(&tmap_q2, q_bf2.p, nun, kp, BM));
+        Sched s;
+        TRY(plan(s, nun, kp, 1 << 20));
+        TRY(upload_schedule(s, sched_items2, false, false));
+        DistParams dp = base_dist_params(nun, kp, s, sched_items2.p);
+        dp.thr = uncert_thr.p;
+        dp.coll_count = coll_count.p;
+        dp.coll_idx = coll_idx.p;
+        dp.coll_cap = COLLECT_CAP;
+        prof_begin(K_SCAN);
+        const int rc2 = launch_dist<16, true>(s, tmap_q2, dp);
+        prof_end();
+        TRY(rc2);
+        CollectRerankParams cp{};
+        cp.uncert_list = uncert_list.p;
+        cp.coll_count = coll_count.p;
+        cp.coll_idx = coll_idx.p;
+        cp.dim = dim;
+        cp.ld_x = ld_x;
+        cp.ld_q = ld_q;
+        cp.kk = kk;
+        cp.index_base = index_base;
+        cp.flags = flags;
+        cp.out_idx = d_out_idx;
+        cp.out_dist = d_out_dist;
+        cp.overflow_count = reinterpret_cast<int *>(scalars.p + 5);
+        cp.overflow_list = overflow_list.p;
+        prof_begin(K_SCAN);
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
+            rerank_collect_kernel<double, double><<<nun, 256, 0, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), cp);
+        else if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
+            rerank_collect_kernel<double, float><<<nun, 256, 0, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), cp);
+        else if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
+            rerank_collect_kernel<float, double><<<nun, 256, 0, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), cp);
+        else
+            rerank_collect_kernel<float, float><<<nun, 256, 0, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), cp);
+        prof_end();
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(h_count, scalars.p + 5, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        const int nov = *h_count;
+        if (nov > 0) {
+            stats.exact_scanned += nov;
+            TRY(scan(d_query, q_dtype, ld_q, overflow_list.p, nov, dim, kk, flags, d_out_idx, d_out_dist));
+        }
+        return B200KNN_OK;
+    }
+
+    template <int C>
+    int tensor_pass(const void *d_query, int q_dtype, int64_t nq, int64_t ld_q, int dim, int kp, int kk, unsigned flags,
+                    int32_t *d_out_idx, double *d_out_dist, const QuerySide *pre = nullptr) {
+        // query side: BF16 rows + norms, either converted now or (self-kNN) the pool's own, already converted by add()
+        const __nv_bfloat16 *qb;
+        const float *qn, *qe;
+        if (pre) {
+            qb = pre->bf; qn = pre->norm; qe = pre->err;
+        } else {
+            TRY(q_bf.ensure(static_cast<size_t>(nq) * kp));
+            TRY(qnorm_bf.ensure(nq));
+            TRY(q_err.ensure(nq));
+            TRY(launch_convert(d_query, q_dtype, nq, ld_q, dim, kp, q_bf.p, qnorm_bf.p, q_err.p, scalars.p + 2));
+            qb = q_bf.p; qn = qnorm_bf.p; qe = q_err.p;
+        }
+        cur_q_bf = qb;
+        CUtensorMap tmap_q;
+        TRY(make_tmap(&tmap_q, qb, nq, kp, BM));
+        const bool cached = sched1.matches(nq, n, kp, MAX_KEYS / C);
+        if (!cached) TRY(plan(sched1, nq, kp, MAX_KEYS / C));
+        const Sched &s = sched1;
+        TRY(upload_schedule(s, sched_items, true, cached));
+        TRY(cand_s.ensure(static_cast<size_t>(nq) * s.max_slots * C));
+        TRY(cand_i.ensure(static_cast<size_t>(nq) * s.max_slots * C));
+        DistParams dp = base_dist_params(nq, kp, s, sched_items.p);
+        dp.cand_s = cand_s.p;
+        dp.cand_i = cand_i.p;
+        prof_begin(K_DISTANCE, 2.0 * static_cast<double>(nq) * static_cast<double>(n) * dim);
+        const int rc1 = launch_dist<C, false>(s, tmap_q, dp);
+        prof_end();
+        TRY(rc1);
+
+        last_nq = nq;
+        last_slots = s.max_slots;
+        last_c = C;
+        TRY(uncert_list.ensure(nq));
+        TRY(uncert_thr.ensure(nq));
+        RerankParams rp{};
+        rp.cand_s = cand_s.p;
+        rp.cand_i = cand_i.p;
+        rp.max_slots = s.max_slots;
+        rp.slots_per_qtile = sched_slots.p;
+        rp.qtile_rows = BM * s.cg;
+        rp.dim = dim;
+        rp.ld_x = ld_x;
+        rp.ld_q = ld_q;
+        rp.n = static_cast<int>(n);
+        rp.kk = kk;
+        rp.index_base = index_base;
+        rp.flags = flags;
+        rp.qnorm_bf = qn;
+        rp.q_err = qe;
+        rp.max_xnorm_bf_bits = scalars.p;
+        rp.max_x_err_bits = scalars.p + 1;
+        rp.kp = kp;
+        rp.out_idx = d_out_idx;
+        rp.out_dist = d_out_dist;
+        rp.uncert_count = reinterpret_cast<int *>(scalars.p + 4);
+        rp.uncert_list = uncert_list.p;
+        rp.uncert_thr = uncert_thr.p;
+        CU_TRY(cudaMemsetAsync(scalars.p + 4, 0, sizeof(unsigned int), stream));
+        TRY(launch_rerank<C>(d_query, q_dtype, nq, rp));
+        if (!(flags & B200KNN_FLAG_NO_CERTIFY)) {
+            CU_TRY(cudaMemcpyAsync(h_count, scalars.p + 4, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CU_TRY(cudaStreamSynchronize(stream));
+            const int nun = *h_count;
+            if (nun > 0) {
+                stats.uncertified += nun;
+                TRY(second_pass(d_query, q_dtype, ld_q, nun, dim, kp, kk, flags, d_out_idx, d_out_dist));
+            }
+        }
+        return B200KNN_OK;
+    }
+
+    // ------------------------------------------------------------------ ball membership (precision/recall metric)
+    // d_out[i] |= 1 when query i lies inside any ball B(x_j, sqrt(radius2[j])) of this shard.  radius2 is already in
+    // `radius2` (device).  Tensor-core filter in collect mode + exact float64 decision; overflowed lists without a
+    // witness go to the exact scan.
+    static constexpr int MEMBER_CAP = 256;
+    int ball_membership(const void *d_query, int q_dtype, int64_t nq, int64_t ld_q, int dim, int kp, unsigned char *d_out) {
+        if (nq <= 0 || n <= 0) return B200KNN_OK;
+        CU_TRY(cudaSetDevice(device));
+        stats.queries += nq;
+        TRY(q_bf.ensure(static_cast<size_t>(nq) * kp));
+        TRY(qnorm_bf.ensure(nq));
+        TRY(q_err.ensure(nq));
+        TRY(launch_convert(d_query, q_dtype, nq, ld_q, dim, kp, q_bf.p, qnorm_bf.p, q_err.p, scalars.p + 2));
+        TRY(colterm.ensure(n));
+        TRY(rowthr.ensure(nq));
+        CU_TRY(cudaMemsetAsync(scalars.p + 7, 0, sizeof(unsigned int), stream));
+        prof_begin(K_SCAN);
+        ball_colterm_kernel<<<std::min<int64_t>(num_sms * 4, (n + 255) / 256), 256, 0, stream>>>(xnorm_bf.p, x_err.p, radius2.p, static_cast<int>(n),
+                                                                                          colterm.p, scalars.p + 7);
+        prof_end();
+        prof_begin(K_SCAN);
+        ball_rowthr_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, stream>>>(qnorm_bf.p, q_err.p, scalars.p, scalars.p + 7, kp,
+                                                                                        static_cast<int>(nq), rowthr.p);
+        prof_end();
+        CU_TRY(cudaGetLastError());
+        TRY(coll_count.ensure(nq));
+        TRY(coll_idx.ensure(static_cast<size_t>(nq) * MEMBER_CAP));
+        TRY(overflow_list.ensure(nq));
+        CU_TRY(cudaMemsetAsync(coll_count.p, 0, static_cast<size_t>(nq) * sizeof(int), stream));
+        CU_TRY(cudaMemsetAsync(scalars.p + 5, 0, sizeof(unsigned int), stream));
+        CUtensorMap tmap_q;
+        TRY(make_tmap(&tmap_q, q_bf.p, nq, kp, BM));
+        Sched s;
+        TRY(plan(s, nq, kp, 1 << 20));
+        TRY(upload_schedule(s, sched_items2, false, false));
+        DistParams dp = base_dist_params(nq, kp, s, sched_items2.p);
+        dp.xnorm = colterm.p;
+        dp.thr = rowthr.p;
+        dp.coll_count = coll_count.p;
+        dp.coll_idx = coll_idx.p;
+        dp.coll_cap = MEMBER_CAP;
+        prof_begin(K_DISTANCE, 2.0 * static_cast<double>(nq) * static_cast<double>(n) * dim);
+        const int rc = launch_dist<16, true>(s, tmap_q, dp);
+        prof_end();
+        TRY(rc);
+        MemberParams mp{};
+        mp.coll_count = coll_count.p;
+        mp.coll_idx = coll_idx.p;
+        mp.cap = MEMBER_CAP;
+        mp.radius2 = radius2.p;
+        mp.dim = dim;
+        mp.ld_x = ld_x;
+        mp.ld_q = ld_q;
+        mp.out_member = d_out;
+        mp.overflow_count = reinterpret_cast<int *>(scalars.p + 5);
+        mp.overflow_list = overflow_list.p;
+        prof_begin(K_RERANK);
+        const unsigned g = static_cast<unsigned>(nq);
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
+            ball_member_kernel<double, double><<<g, 128, 0, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), mp);
+        else if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
+            ball_member_kernel<double, float><<<g, 128, 0, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), mp);
+        else if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
+            ball_member_kernel<float, double><<<g, 128, 0, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), mp);
+        else
+            ball_member_kernel<float, float><<<g, 128, 0, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), mp);
+        prof_end();
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(h_count, scalars.p + 5, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        const int nov = *h_count;
+        if (nov > 0) {
+            stats.exact_scanned += nov;
+            TRY(scan_members(d_query, q_dtype, ld_q, nov, dim, d_out));
+        }
+        return B200KNN_OK;
+    }
+    template <typename TX, typename TQ>
+    int scan_members_typed(const TQ *d_query, int64_t ld_q, int nsub, int dim, unsigned char *d_out) {
+        const int batch = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min(nsub, 4096), (1536ll << 20) / std::max<int64_t>(n * 8, 1))));
+        TRY(scan_d2.ensure(static_cast<size_t>(batch) * n));
+        for (int s0 = 0; s0 < nsub; s0 += batch) {
+            const int ns = std::min(batch, nsub - s0);
+            dim3 grid(static_cast<unsigned>((n + SCAN_TX - 1) / SCAN_TX), static_cast<unsigned>((ns + SCAN_TQ - 1) / SCAN_TQ));
+            prof_begin(K_SCAN);
+            scan_dist_kernel<TX, TQ><<<grid, 256, 0, stream>>>(static_cast<const TX *>(x_raw), ld_x, static_cast<int>(n), d_query, ld_q,
+                                                               overflow_list.p + s0, ns, dim, scan_d2.p);
+            prof_end();
+            prof_begin(K_SCAN);
+            scan_member_kernel<<<ns, 256, 0, stream>>>(scan_d2.p, static_cast<int>(n), overflow_list.p + s0, radius2.p, d_out);
+            prof_end();
+            CU_TRY(cudaGetLastError());
+        }
+        return B200KNN_OK;
+    }
+    int scan_members(const void *d_query, int q_dtype, int64_t ld_q, int nsub, int dim, unsigned char *d_out) {
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64) return scan_members_typed<double, double>(static_cast<const double *>(d_query), ld_q, nsub, dim, d_out);
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32) return scan_members_typed<double, float>(static_cast<const float *>(d_query), ld_q, nsub, dim, d_out);
+        if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64) return scan_members_typed<float, double>(static_cast<const double *>(d_query), ld_q, nsub, dim, d_out);
+        return scan_members_typed<float, float>(static_cast<const float *>(d_query), ld_q, nsub, dim, d_out);
+    }
+
+    // queries and outputs on this device; nq bounded by the caller's chunking
+    int query_device(const void *d_query, int q_dtype, int64_t nq, int64_t ld_q, int dim, int kp, int k, unsigned flags,
+                     int32_t *d_out_idx, double *d_out_dist, const QuerySide *pre = nullptr) {
+        if (nq <= 0) return B200KNN_OK;
+        CU_TRY(cudaSetDevice(device));
+        const int kk = static_cast<int>(std::min<int64_t>(k, n));
+        stats.queries += nq;
+        if (kk > 32 || (flags & B200KNN_FLAG_FORCE_SCAN))
+            return scan(d_query, q_dtype, ld_q, nullptr, static_cast<int>(nq), dim, kk, flags, d_out_idx, d_out_dist);
+        if (kk <= 4) return tensor_pass<16>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist, pre);
+        if (kk <= 16) return tensor_pass<32>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist, pre);
+        return tensor_pass<64>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist, pre);
+    }
+};
+
+constexpr int64_t QUERY_CHUNK = 32768;   // query rows per device pass (bounds workspace; 256 query tiles)
+
+}  // namespace
