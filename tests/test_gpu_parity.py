@@ -481,6 +481,15 @@ def test_round_wide_lockstep_schedule(lib, cg, monkeypatch):
     db.add(x)
     i1, d1 = check(db, x, y, 4)
     assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+    # the second pass (collect mode) and the ball-membership filter run on the same schedule
+    xg, yg = make("gauss", 4000, 600, 4096, seed=90)
+    dg = DCI(4096)
+    dg.add(xg)
+    check(dg, xg, yg, 10)
+    assert dg.stats()["uncertified"] > 0
+    r2 = np.full(21000, 0.9 * float(np.median(d1[:, 0])) ** 2)
+    member = db.ball_membership(y, r2)
+    assert np.array_equal(member.astype(bool), d1[:, 0] ** 2 <= r2[0])
 
 
 def test_long_rows_pick_the_wide_schedule_and_stay_exact(lib):
