@@ -19,30 +19,33 @@ __device__ __forceinline__ float float_from_order_bits(uint32_t b) {
 // size, or on whether the query needed the second pass.  128 virtual lanes: lane v sums the elements e = v + 128 i,
 // even i into one accumulator and odd i into another; xor-shuffle tree inside each of the 4 warps; the 4 warp sums are
 // added in order.  Executed by threads 0..127 of the block; the value is returned to every thread.
+template <int RB = 16, typename TX, typename TQ>    // RB (even) elements per lane and step: 2 RB loads in flight before any arithmetic
+__device__ __forceinline__ void canon_d2_lanes(const TX *__restrict__ xr, const TQ *__restrict__ qr, int dim, int v, double &a0, double &a1) {
+    for (int base = 0; base < dim; base += RB * 128) {
+        TQ qraw[RB];
+        TX xraw[RB];
+#pragma unroll
+        for (int i = 0; i < RB; i++) {
+            const int e = base + v + i * 128;
+            qraw[i] = (e < dim) ? qr[e] : TQ(0);     // past the end: 0 - 0 adds nothing
+            xraw[i] = (e < dim) ? xr[e] : TX(0);
+        }
+#pragma unroll
+        for (int i = 0; i < RB; i++) { keep(qraw[i]); keep(xraw[i]); }
+#pragma unroll
+        for (int i = 0; i < RB; i += 2) {
+            const double d0 = static_cast<double>(qraw[i]) - static_cast<double>(xraw[i]);
+            const double d1 = static_cast<double>(qraw[i + 1]) - static_cast<double>(xraw[i + 1]);
+            a0 = fma(d0, d0, a0);
+            a1 = fma(d1, d1, a1);
+        }
+    }
+}
 template <typename TX, typename TQ>
 __device__ __forceinline__ double canon_d2(const TX *__restrict__ xr, const TQ *__restrict__ qr, int dim, int tid, double *partial4) {
     if (tid < 128) {
         double a0 = 0.0, a1 = 0.0;
-        constexpr int RB = 16;                   // elements per lane and step: 32 loads in flight before any arithmetic
-        for (int base = 0; base < dim; base += RB * 128) {
-            TQ qraw[RB];
-            TX xraw[RB];
-#pragma unroll
-            for (int i = 0; i < RB; i++) {
-                const int e = base + tid + i * 128;
-                qraw[i] = (e < dim) ? qr[e] : TQ(0);     // past the end: 0 - 0 adds nothing
-                xraw[i] = (e < dim) ? xr[e] : TX(0);
-            }
-#pragma unroll
-            for (int i = 0; i < RB; i++) { keep(qraw[i]); keep(xraw[i]); }
-#pragma unroll
-            for (int i = 0; i < RB; i += 2) {
-                const double d0 = static_cast<double>(qraw[i]) - static_cast<double>(xraw[i]);
-                const double d1 = static_cast<double>(qraw[i + 1]) - static_cast<double>(xraw[i + 1]);
-                a0 = fma(d0, d0, a0);
-                a1 = fma(d1, d1, a1);
-            }
-        }
+        canon_d2_lanes(xr, qr, dim, tid, a0, a1);
         const double w = warp_sum(a0 + a1);
         if ((tid & 31) == 0) partial4[tid >> 5] = w;
     }
@@ -199,6 +202,34 @@ __device__ __forceinline__ void rerank_finish(const RerankParams &p, int q, cons
     }
 }
 
+// Progressive pruning (executed by the whole block, uniform call): kk exact distances are known, the kk-th true distance
+// is at most their maximum — a far tighter limit than the a-priori upper bound.  Scores are sorted, so the survivors
+// stay a prefix; returns its new length.
+__device__ __forceinline__ int tighten_survivors(const RerankParams &p, int q, const unsigned long long *keys, const double *d2s, int m,
+                                                 int *m_s, int warp, int lane) {
+    __syncthreads();                    // d2s[0..kk) were written by single threads, possibly without a barrier since
+    if (warp == 0) {
+        double mx = 0.0;
+        for (int i = lane; i < p.kk; i += 32) mx = fmax(mx, d2s[i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        int cnt = 0;
+        if (mx < DBL_MAX) {
+            const ErrModel em = make_err_model(p, q);
+            const double dk = sqrt(mx);
+            for (int i = p.kk + lane; i < m; i += 32)
+                cnt += (keys[i] != ~0ull && em.lower(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(keys[i] >> 32)))) <= dk) ? 1 : 0;
+        } else {
+            cnt = (lane == 0) ? m - p.kk : 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) *m_s = p.kk + cnt;
+    }
+    __syncthreads();
+    return *m_s;
+}
+
 template <typename TX, typename TQ, int C, int NT>
 __global__ void __launch_bounds__(NT)
 rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const RerankParams p) {
@@ -256,9 +287,41 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
     // of the query row in registers across candidates, and issues its loads of the pool row back to back.
     const int warp = tid >> 5, lane = tid & 31;
     const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
+    if constexpr (NT > 128) {
+        // Few queries, many shortlists (the trainer's 24-row calls, config 1): the device is far from full, so the eight
+        // 128-thread groups of the block each take a candidate (named barrier per group), every candidate still summed
+        // by 128 lanes in the canonical order.
+        constexpr int NG = NT / 128;
+        __shared__ double gpart[NG][4];
+        const int grp = tid >> 7, gt = tid & 127;
+        bool tightened = false;
+        for (int c0 = 0; c0 < C; c0 += NG) {
+            if (!tightened && c0 >= p.kk && c0 < m) {      // uniform across the block
+                m = tighten_survivors(p, q, keys, d2s, m, &m_s, warp, lane);
+                tightened = true;
+            }
+            const int c = c0 + grp;
+            if (c < C) {                                     // uniform across the group
+                const unsigned long long key = keys[c];
+                if (c >= m || key == ~0ull) {
+                    if (gt == 0) d2s[c] = DBL_MAX;
+                } else {
+                    double a0 = 0.0, a1 = 0.0;
+                    canon_d2_lanes<(sizeof(TX) + sizeof(TQ) >= 16) ? 8 : 16>(x + static_cast<int64_t>(static_cast<uint32_t>(key)) * p.ld_x, qr, p.dim, gt, a0, a1);   // 64-register budget
+                    const double w = warp_sum(a0 + a1);
+                    if (lane == 0) gpart[grp][warp & 3] = w;
+                    asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+                    if (gt == 0) d2s[c] = ((gpart[grp][0] + gpart[grp][1]) + gpart[grp][2]) + gpart[grp][3];
+                }
+            }
+            __syncthreads();
+        }
+        if (warp == 0) rerank_finish<C>(p, q, keys, d2s, lane);
+        return;
+    }
     constexpr int RQ = 24;                      // dims per thread held in registers (128 threads x 24 = 3072)
-    constexpr int nth = 128;                    // the canonical 128 lanes (see canon_d2); extra threads of the 1024-thread
-    const bool act = tid < nth;                 // flavour only help with the merge sort above
+    constexpr int nth = 128;                    // the canonical 128 lanes (see canon_d2)
+    const bool act = tid < nth;
     __shared__ double partial[4];
     double qreg[RQ];
     const bool fits = p.dim <= RQ * nth;
@@ -277,31 +340,7 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
         for (int i = 0; i < RQ; i++) qreg[i] = static_cast<double>(qraw[i]);
     }
     for (int c = 0; c < C; c++) {
-        if (c == p.kk && c < m) {               // uniform across the block
-            // kk exact distances are known: the kk-th true distance is at most their maximum, which is a far tighter
-            // pruning limit than the a-priori upper bound (the survivors stay a prefix: scores are sorted)
-            __syncthreads();                    // d2s[0..kk) were written by thread 0, possibly without a barrier since
-            if (warp == 0) {
-                double mx = 0.0;
-                for (int i = lane; i < p.kk; i += 32) mx = fmax(mx, d2s[i]);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                int cnt = 0;
-                if (mx < DBL_MAX) {
-                    const ErrModel em = make_err_model(p, q);
-                    const double dk = sqrt(mx);
-                    for (int i = p.kk + lane; i < m; i += 32)
-                        cnt += (keys[i] != ~0ull && em.lower(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(keys[i] >> 32)))) <= dk) ? 1 : 0;
-                } else {
-                    cnt = (lane == 0) ? m - p.kk : 0;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-                if (lane == 0) m_s = p.kk + cnt;
-            }
-            __syncthreads();
-            m = m_s;
-        }
+        if (c == p.kk && c < m) m = tighten_survivors(p, q, keys, d2s, m, &m_s, warp, lane);   // uniform across the block
         const unsigned long long key = keys[c];
         if (c >= m || key == ~0ull) {           // uniform across the block
             if (tid == 0) d2s[c] = DBL_MAX;
@@ -358,13 +397,13 @@ struct CollectRerankParams {
     int *overflow_list;          // query rows that need the exact scan
 };
 
-template <typename TX, typename TQ>
-__global__ void __launch_bounds__(256)
+template <typename TX, typename TQ, int NW>      // NW warps per block: 8 with many lists, 32 when only a few blocks would run
+__global__ void __launch_bounds__(NW * 32)
 rerank_collect_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const CollectRerankParams p) {
     __shared__ double d2[COLLECT_CAP];
     __shared__ int idx[COLLECT_CAP];
-    __shared__ double sd[8];
-    __shared__ int si[8];
+    __shared__ double sd[NW];
+    __shared__ int si[NW];
     __shared__ double last_d_s;
     __shared__ int last_i_s;
     const int slot = blockIdx.x;
@@ -379,7 +418,7 @@ rerank_collect_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, con
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
-    for (int c = warp; c < cnt; c += 8) {       // one candidate per warp, canonical summation order
+    for (int c = warp; c < cnt; c += NW) {       // one candidate per warp, canonical summation order
         const int j = p.coll_idx[static_cast<int64_t>(slot) * COLLECT_CAP + c];
         const double a0 = canon_d2_warp(x + static_cast<int64_t>(j) * p.ld_x, qr, p.dim, lane);
         if (lane == 0) { d2[c] = a0; idx[c] = j; }
@@ -407,7 +446,7 @@ rerank_collect_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, con
         if (lane == 0) { sd[warp] = bd; si[warp] = bi; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int w = 1; w < 8; w++)
+            for (int w = 1; w < NW; w++)
                 if (sd[w] < bd || (sd[w] == bd && si[w] < bi)) { bd = sd[w]; bi = si[w]; }
             last_d_s = bd;
             last_i_s = bi;

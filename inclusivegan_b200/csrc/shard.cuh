@@ -604,14 +604,19 @@ struct Shard {
         cp.overflow_count = reinterpret_cast<int *>(scalars.p + 5);
         cp.overflow_list = overflow_list.p;
         prof_begin(K_SCAN);
-        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
-            rerank_collect_kernel<double, double><<<nun, 256, 0, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), cp);
-        else if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
-            rerank_collect_kernel<double, float><<<nun, 256, 0, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), cp);
-        else if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
-            rerank_collect_kernel<float, double><<<nun, 256, 0, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), cp);
-        else
-            rerank_collect_kernel<float, float><<<nun, 256, 0, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), cp);
+        // few lists (not more blocks than SMs): 32 warps per list, the sweep is latency-bound
+        auto launch = [&](auto tx, auto tq) {
+            using TX = decltype(tx);
+            using TQ = decltype(tq);
+            if (nun <= num_sms)
+                rerank_collect_kernel<TX, TQ, 32><<<nun, 1024, 0, stream>>>(static_cast<const TX *>(x_raw), static_cast<const TQ *>(d_query), cp);
+            else
+                rerank_collect_kernel<TX, TQ, 8><<<nun, 256, 0, stream>>>(static_cast<const TX *>(x_raw), static_cast<const TQ *>(d_query), cp);
+        };
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64) launch(double(), double());
+        else if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32) launch(double(), float());
+        else if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64) launch(float(), double());
+        else launch(float(), float());
         prof_end();
         CU_TRY(cudaGetLastError());
         CU_TRY(cudaMemcpyAsync(h_count, scalars.p + 5, sizeof(int), cudaMemcpyDeviceToHost, stream));
