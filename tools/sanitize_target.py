@@ -25,3 +25,6 @@ P = rng.normal(0, 0.01, size=(777, 129)); dbp = DCI(129); dbp.set_projector(P)
 rows = rng.standard_normal((300, 777)).astype(np.float32)
 dbp.add_projected(rows); dbp.query_projected_arrays(rows[:50], 3); dbp.project_rows(rows[:33].astype(np.float64))
 print("sanitize target (additions) done")
+# few queries x many shortlists: the 1024-thread re-rank flavour (group-parallel sweep) and the 32-warp list re-rank
+xs = rng.standard_normal((20000, 64)); dbs = DCI(64); dbs.add(xs); dbs.query_arrays(rng.standard_normal((24, 64)), 10)
+print("sanitize target (small-call flavours) done", dbs.stats()["uncertified"])
