@@ -191,6 +191,15 @@ int b200knn_set_profiling(b200knn_index *index, int profiling);
 int b200knn_get_stats(b200knn_index *index, b200knn_stats *out);   /* synchronises the handle's stream(s) */
 int b200knn_reset_stats(b200knn_index *index);
 
+/* Test hook (pure host code, no device needed): the work schedule the distance kernel would run for a pool of n rows,
+ * nq query rows and padded row length kp on a GPU with num_sms SMs.  cta_group 0 = automatic; wide_mode as
+ * $B200KNN_WIDE (0 never / 1 when cheaper in HBM traffic / 2 always the long-row grid schedule).  items receives up to
+ * `capacity` work items as 4 ints each (query tile, first pool tile, end pool tile, slot word: bits 0-15 shortlist slot,
+ * 16-23 workers sharing the pool stream, 24-31 workers in round-wide lockstep or 0), row-major [rounds][workers];
+ * geometry[8] receives {cta_group, workers, rounds, query tiles, pool tiles, max slots, query-tile group size, wide}. */
+int b200knn_debug_plan(int64_t n, int64_t nq, int kp, int num_sms, int cta_group, int max_slots, int a_budget_mb, int wide_mode,
+                       int32_t *items, int64_t capacity, int32_t *geometry);
+
 /* Test hook: copy out the BF16-pass shortlists of the LAST tensor pass of a single-device handle (the last query
  * chunk): scores[nq][slots][C] (s~ = ||x~||^2 - 2 q~.x~ as computed on the tensor cores) and rows[nq][slots][C]
  * (shard-local pool row, -1 = empty).  *nq, *slots, *c receive the geometry; the HOST buffers must hold `capacity`

@@ -254,6 +254,23 @@ int b200knn_add(b200knn_index *ix, const void *data, int dtype, int64_t n, int64
     return rc;
 }
 
+int b200knn_debug_plan(int64_t n, int64_t nq, int kp, int num_sms, int cta_group, int max_slots, int a_budget_mb, int wide_mode,
+                       int32_t *items, int64_t capacity, int32_t *geometry) {
+    if (n <= 0 || nq <= 0 || kp <= 0 || num_sms <= 0 || max_slots <= 0 || a_budget_mb <= 0) return fail(B200KNN_EINVAL, "plan arguments must be positive");
+    if (cta_group < 0 || cta_group > 2 || !geometry) return fail(B200KNN_EINVAL, "bad cta_group or NULL geometry");
+    Shard::Sched s;
+    TRY(Shard::plan_schedule(s, n, nq, kp, max_slots, cta_group, std::max(1, num_sms / 2), num_sms, a_budget_mb, wide_mode));
+    const int32_t g[8] = {s.cg, s.workers, s.nrounds, s.qt, s.nt, s.max_slots, s.qg, s.wide ? 1 : 0};
+    std::memcpy(geometry, g, sizeof(g));
+    const int64_t count = static_cast<int64_t>(s.items.size());
+    if (items) {
+        if (capacity < count) return fail(B200KNN_EINVAL, "items capacity %lld < %lld", (long long)capacity, (long long)count);
+        static_assert(sizeof(WorkItem) == 4 * sizeof(int32_t), "WorkItem is four ints");
+        std::memcpy(items, s.items.data(), static_cast<size_t>(count) * sizeof(WorkItem));
+    }
+    return B200KNN_OK;
+}
+
 int b200knn_debug_shortlists(b200knn_index *ix, float *scores, int32_t *rows, int64_t capacity, int64_t *nq, int *slots, int *c) {
     if (!ix || !scores || !rows || !nq || !slots || !c) return fail(B200KNN_EINVAL, "NULL argument");
     if (ix->shards.size() != 1 || !ix->shards[0].ready) return fail(B200KNN_ESTATE, "needs a single-device handle that has answered a query");

@@ -335,6 +335,11 @@ struct Shard {
     };
     Sched sched1;   // cached first-pass schedule
     int plan(Sched &s, int64_t nq, int kp, int max_slots_allowed) const {
+        return plan_schedule(s, n, nq, kp, max_slots_allowed, forced_cg, max_pairs, num_sms, a_budget_mb, wide_mode);
+    }
+    // pure host function (no device needed): also reachable through b200knn_debug_plan for the CPU tests
+    static int plan_schedule(Sched &s, int64_t n, int64_t nq, int kp, int max_slots_allowed, int forced_cg, int max_pairs, int num_sms,
+                             int a_budget_mb, int wide_mode) {
         s.key_nq = nq;
         s.key_n = n;
         s.key_kp = kp;

@@ -1,0 +1,76 @@
+"""Invariants of the distance kernel's work schedule (Shard::plan_schedule, reached through b200knn_debug_plan; pure
+host code, runs without a GPU): every (query tile, pool tile) pair is computed exactly once, shortlist slots are
+consistent, lockstep groups are well-formed — for the L2-resident group schedule and the long-row grid schedule."""
+import ctypes
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+BM, BN = 128, 256
+
+
+def plan(lib, n, nq, kp, num_sms=148, cg=0, max_slots=64, budget=64, wide=1):
+    lib.b200knn_debug_plan.restype = ctypes.c_int
+    lib.b200knn_debug_plan.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    geo = np.zeros(8, np.int32)
+    assert lib.b200knn_debug_plan(n, nq, kp, num_sms, cg, max_slots, budget, wide, None, 0, geo.ctypes.data) == 0, lib.b200knn_last_error()
+    cgr, workers, rounds = int(geo[0]), int(geo[1]), int(geo[2])
+    items = np.zeros((rounds * workers, 4), np.int32)
+    assert lib.b200knn_debug_plan(n, nq, kp, num_sms, cg, max_slots, budget, wide, items.ctypes.data, items.shape[0], geo.ctypes.data) == 0
+    keys = ("cg", "workers", "rounds", "qt", "nt", "max_slots", "qg", "wide")
+    return dict(zip(keys, (int(v) for v in geo))), items.reshape(rounds, workers, 4)
+
+
+def check_invariants(g, items, n, nq, max_slots):
+    qrows = BM * g["cg"]
+    assert g["qt"] == -(-nq // qrows) and g["nt"] == -(-n // BN)
+    assert g["max_slots"] <= max_slots
+    cover = np.zeros((g["qt"], g["nt"]), np.int32)
+    for r in range(g["rounds"]):
+        active = items[r][items[r][:, 0] >= 0]
+        assert len(active) > 0
+        word = active[:, 3].astype(np.uint32)
+        slot, sharers, wide = word & 0xFFFF, (word >> 16) & 0xFF, word >> 24
+        assert slot.max() < g["max_slots"]
+        for (qt, t0, t1, _), sl in zip(active, slot):
+            assert 0 <= t0 < t1 <= g["nt"]
+            cover[qt, t0:t1] += 1
+        # one shortlist slot per (query tile, pool stream): a query tile never meets the same slot twice
+        assert len({(int(a[0]), int(s)) for a, s in zip(active, slot)}) == len(active)
+        # workers sharing a pool stream sweep identical tile ranges and agree on how many they are
+        for s in np.unique(slot):
+            grp = active[slot == s]
+            assert len({(int(a[1]), int(a[2])) for a in grp}) == 1
+            assert (sharers[slot == s] == len(grp)).all()
+        if wide.any():            # round-wide lockstep: every active worker carries the same head count, chunk lengths differ by <= 1
+            assert (wide == len(active)).all()
+            lens = active[:, 2] - active[:, 1]
+            assert lens.max() - lens.min() <= 1
+            assert len(active) % len(np.unique(slot)) == 0
+    assert (cover == 1).all()
+
+
+def test_headline_shapes(native_lib):
+    g, items = plan(native_lib, 300000, 30000, 3072)                 # config 3: L2-resident groups of query tiles
+    assert (g["cg"], g["wide"]) == (2, 0) and g["qg"] * BM * 2 * 3072 * 2 <= 64 << 20
+    check_invariants(g, items, 300000, 30000, 64)
+    g, items = plan(native_lib, 125000, 30000, 49152)                # config 5 share: the grid schedule
+    assert g["wide"] == 1 and g["qg"] >= 6 and g["max_slots"] <= 16
+    check_invariants(g, items, 125000, 30000, 64)
+    g, items = plan(native_lib, 300000, 24, 3072)                    # the trainer's 24-row call: one tile over all SMs
+    assert (g["cg"], g["qt"], g["rounds"], g["workers"]) == (1, 1, 1, 148)
+    check_invariants(g, items, 300000, 24, 256)
+    g, items = plan(native_lib, 125000, 30000, 49152, wide=0)
+    assert g["wide"] == 0
+    check_invariants(g, items, 125000, 30000, 64)
+
+
+@settings(max_examples=150, deadline=None)
+@given(n=st.integers(1, 400000), nq=st.integers(1, 40000), kp=st.sampled_from([8, 64, 512, 2048, 3072, 5000, 12288, 24576, 49152, 98304]),
+       num_sms=st.sampled_from([2, 16, 132, 148]), cg=st.sampled_from([0, 1, 2]), max_slots=st.sampled_from([1, 2, 16, 64, 128, 256]),
+       budget=st.sampled_from([1, 26, 64, 104]), wide=st.sampled_from([0, 1, 2]))
+def test_every_tile_pair_is_scheduled_exactly_once(native_lib, n, nq, kp, num_sms, cg, max_slots, budget, wide):
+    g, items = plan(native_lib, n, nq, kp, num_sms, cg, max_slots, budget, wide)
+    check_invariants(g, items, n, nq, max_slots)
