@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — IMLE kNN matching throughput (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|c1|small] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|c1|c5|c5s|small] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -11,66 +11,140 @@ resident generated pool (exact kNN).  Prints ONE JSON line (rank 0).
   value     queries/s with the pool index built and the query matrix already resident in HBM
             (C-ABI device entry points, CUDA-event timed on the launching stream, max over ranks).
   e2e       the same metric through the host-buffer C-ABI call the DCI Python class makes
-            (b200knn_query): pinned HOST float64 queries in, HOST results out, H2D/D2H inside the timed region.
+            (b200knn_query): pinned HOST queries in, HOST results out, H2D/D2H inside the timed region.
   roofline  the tcgen05 distance kernel: 2*Q*N*d FLOPs per launch / its CUDA-event time, vs MEASURED_PEAKS.json.
-  cpu_baseline  the UNMODIFIED reference DCI (oracle/_ref/_dci.so) on this box's host cores, bounded sample.
+  add_s     DCI.add() of the workload's pool from pageable host memory (H2D + centre + BF16 convert + norms).
+  small_call  the trainer's call granularity (training_loop.py:374-403): 24-row b200knn_query calls, back to back.
+  cpu_baseline / --impl reference
+            the UNMODIFIED reference DCI (oracle/_ref/_dci.so) on this box's host cores with the trainer's
+            hyper-parameters, FULL pool, bounded query sample per step; its approximate answers are scored as
+            recall@k against the exact float64 answer on the same queries.
 
 torch is used for device memory, streams, events and torch.distributed only; no torch op is on the path.
-Multi-GPU: pool row-sharded over ranks, queries replicated, local exact top-k per rank, NCCL all-gather of
-(index, distance) lists, k-way merge kernel on every rank.  Total work is fixed as N grows -> "strong".
+Multi-GPU: pool row-sharded over ranks, queries replicated, local exact top-k per rank, NVLink peer-store
+exchange of (index, distance) lists, k-way merge kernel on every rank.  Total work is fixed as N grows -> "strong".
 """
 import argparse
+import ctypes
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "imle_knn_queries_per_sec"
+
+# name: (N pool, Q queries, dim, k, feature generator, description)   — BASELINE.json configs, generators per SURVEY.md 8d
 WORKLOADS = {
-    # name: (N pool, Q queries, dim, k, description)   — BASELINE.json configs
-    "c3": (300000, 30000, 3072, 1, "CelebA-128 IMLE match: 30k queries vs 300k pool, d=3072, k=1 (BASELINE.json configs[2]; north_star target shape)"),
-    "c2": (240000, 24000, 3072, 1, "Stacked MNIST IMLE match: 24k queries vs 240k pool, d=3072, k=1 (configs[1])"),
-    "c4": (50000, 50000, 2048, 4, "precision/recall self-kNN: 50k vs 50k, d=2048, k=3(+self) (configs[3])"),
-    "c1": (10000, 100, 5000, 10, "dci_code/example.py shape: 10k pool, 100 queries, d=5000, k=10 (configs[0])"),
-    "small": (20000, 2048, 512, 1, "smoke-sized"),
-    # configs[4]: 98 GB of BF16 pool + 197 GB of float32 originals -> needs >= 2 GPUs (>= 4 recommended); "c5s" is the
-    # 125k-row share one rank holds in the 8-GPU run, for single-GPU measurements
-    "c5": (1000000, 30000, 49152, 10, "scale sweep: 1M pool, d=49152 (128x128x3 raw pixels), 30k queries, k=10 (configs[4])"),
-    "c5s": (125000, 30000, 49152, 10, "one rank's 1/8 share (125k rows) of the configs[4] scale sweep: d=49152, 30k queries, k=10"),
+    "c3": (300000, 30000, 3072, 1, "gauss", "CelebA-128 IMLE match: 30k queries vs 300k pool, d=3072, k=1 (BASELINE.json configs[2]; north_star target shape)"),
+    "c2": (240000, 24000, 3072, 1, "pixels", "Stacked MNIST IMLE match: 24k queries vs 240k pool, d=3072, k=1 (configs[1])"),
+    "c4": (50000, 50000, 2048, 4, "relu", "precision/recall metric: self-kNN radii of two 50k x 2048 feature sets, k=3 (+self) (configs[3])"),
+    "c1": (10000, 100, 5000, 10, "lowrank", "dci_code/example.py shape: 10k pool, 100 queries, d=5000, k=10 (configs[0])"),
+    "small": (20000, 2048, 512, 1, "gauss", "smoke-sized"),
+    # configs[4]: 98 GB of BF16 pool + 197 GB of float32 originals -> needs >= 4 GPUs; "c5s" is the 125k-row share one
+    # rank holds in the 8-GPU run, for single-GPU measurements
+    "c5": (1000000, 30000, 49152, 10, "image", "scale sweep: 1M pool, d=49152 (128x128x3 raw pixels), 30k queries, k=10 (configs[4])"),
+    "c5s": (125000, 30000, 49152, 10, "image", "one rank's 1/8 share (125k rows) of the configs[4] scale sweep: d=49152, 30k queries, k=10"),
 }
-IMAGE_LIKE = ("c5", "c5s")       # float32 image-like features; the others: float64 N(0,1)
+# feature generators (SURVEY.md 8d).  dtype = what the caller hands to the library.
+GENERATORS = {
+    "gauss":   ("float64", "N(0,1) drawn in float32 and widened to float64 like the trainer's .astype(float64) (training_loop.py:363,379)"),
+    "pixels":  ("float64", "clip(N(0,0.5),-1,1) drawn in float32 ([-1,1] image range) and widened to float64 (training_loop.py:363,379)"),
+    "relu":    ("float32", "relu(N(0,1)) float32, Inception-pool-like features (metrics/precision_recall.py:184-216 hands float32)"),
+    "lowrank": ("float64", "dci_code/example.py:36-40: (2U-1)[rows x 50] @ (2U-1)[50 x d], float64"),
+    "image":   ("float32", "float32 image-like (16-d latent through a fixed basis + 0.05 pixel noise, clipped to [-1,1]), generated on device"),
+}
 IMAGE_LATENT = 16
+ROW_BLOCK = 4096           # rows are generated per 4096-row block seeded by (seed base + block id): any sharding sees the same matrix
+POOL_SEED, QUERY_SEED, SET_B_SEED = 1000, 500000, 900000
+SMALL_CALL_ROWS = 24       # 2 * minibatch with the README settings (run_training.py:67-68,200)
+SMALL_CALLS = 1250         # calls per refresh at config 3 (30000 / 24)
+
+
+def workload_config(name):
+    """The `config` object of the JSON line — identical in both arms (the driver compares them)."""
+    n, q, d, k, gen, desc = WORKLOADS[name]
+    return {"workload": "%s: %s" % (name, desc), "pool": n, "queries": q, "dim": d, "k": k,
+            "features": "%s; seeded per %d-row block" % (GENERATORS[gen][1], ROW_BLOCK)}
+
+
+def _gen_block(gen, rows, d, seed, dev, low_t=None, basis=None):
+    """One row block of a generator, on torch device `dev` (CPU works too: used by the CPU tests)."""
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    if gen == "gauss":
+        return torch.randn(rows, d, device=dev, dtype=torch.float32, generator=g).double()
+    if gen == "pixels":
+        return (torch.randn(rows, d, device=dev, dtype=torch.float32, generator=g) * 0.5).clamp_(-1.0, 1.0).double()
+    if gen == "relu":
+        return torch.randn(rows, d, device=dev, dtype=torch.float32, generator=g).clamp_(min=0.0)
+    if gen == "lowrank":
+        lat = torch.rand(rows, 50, device=dev, dtype=torch.float64, generator=g) * 2.0 - 1.0
+        return lat @ low_t
+    if gen == "image":
+        lat = torch.randn(rows, IMAGE_LATENT, device=dev, dtype=torch.float32, generator=g)
+        x = lat @ basis
+        x += 0.05 * torch.randn(rows, d, device=dev, dtype=torch.float32, generator=g)
+        return x.clamp_(-1.0, 1.0)
+    raise ValueError(gen)
 
 
 def synth_rows(workload, a, b, d, dev, seed_base):
-    """Rows [a, b) of a workload's synthetic feature matrix, generated on the device; a row's values depend only on
+    """Rows [a, b) of a workload's synthetic feature matrix, generated on `dev`; a row's values depend only on
     (seed_base, global row block), so every sharding sees the same matrix."""
     import torch
-    if workload not in IMAGE_LIKE:
-        raise ValueError(workload)
-    # image-like: a 16-dimensional latent through a fixed random basis + pixel noise, clipped to [-1, 1] (the
-    # trainer's pixel range, training_loop.py:362-365), float32 like the generator's output
-    gb = torch.Generator(device=dev)
-    gb.manual_seed(77)
-    basis = torch.randn(IMAGE_LATENT, d, device=dev, dtype=torch.float32, generator=gb) * 0.125
-    out = torch.empty(b - a, d, device=dev, dtype=torch.float32)
-    SB = 4096
-    for sb in range(a // SB, (b + SB - 1) // SB):
+    gen = WORKLOADS[workload][4]
+    dt = torch.float64 if GENERATORS[gen][0] == "float64" else torch.float32
+    low_t = basis = None
+    if gen == "lowrank":
         g = torch.Generator(device=dev)
-        g.manual_seed(seed_base + sb)
-        lat = torch.randn(SB, IMAGE_LATENT, device=dev, dtype=torch.float32, generator=g)
-        x = lat @ basis
-        x += 0.05 * torch.randn(SB, d, device=dev, dtype=torch.float32, generator=g)
-        x.clamp_(-1.0, 1.0)
-        lo, hi = max(a, sb * SB), min(b, (sb + 1) * SB)
-        out[lo - a:hi - a] = x[lo - sb * SB:hi - sb * SB]
+        g.manual_seed(77)
+        low_t = torch.rand(50, d, device=dev, dtype=torch.float64, generator=g) * 2.0 - 1.0
+    if gen == "image":
+        g = torch.Generator(device=dev)
+        g.manual_seed(77)
+        basis = torch.randn(IMAGE_LATENT, d, device=dev, dtype=torch.float32, generator=g) * 0.125
+    out = torch.empty(b - a, d, device=dev, dtype=dt)
+    for sb in range(a // ROW_BLOCK, (b + ROW_BLOCK - 1) // ROW_BLOCK):
+        x = _gen_block(gen, ROW_BLOCK, d, seed_base + sb, dev, low_t, basis)
+        lo, hi = max(a, sb * ROW_BLOCK), min(b, (sb + 1) * ROW_BLOCK)
+        out[lo - a:hi - a] = x[lo - sb * ROW_BLOCK:hi - sb * ROW_BLOCK]
+    return out
+
+
+def synth_rows_host(workload, a, b, d, seed_base, threads):
+    """The same distributions on the HOST with NumPy (reference arm: no GPU, no torch), float64 out; values differ
+    from the device generator's (another RNG), the distribution and the block seeding do not."""
+    gen = WORKLOADS[workload][4]
+    if gen == "image":
+        raise ValueError("image-like rows are generated on the device only")
+    low_t = None
+    if gen == "lowrank":
+        low_t = np.random.default_rng(77).random((50, d)) * 2.0 - 1.0
+    out = np.empty((b - a, d), dtype=np.float64)
+
+    def fill(sb):
+        rng = np.random.default_rng(seed_base + sb)
+        if gen == "lowrank":
+            x = (rng.random((ROW_BLOCK, 50)) * 2.0 - 1.0) @ low_t
+        else:
+            x = rng.standard_normal((ROW_BLOCK, d), dtype=np.float32)
+            if gen == "pixels":
+                x = np.clip(x * np.float32(0.5), -1.0, 1.0)
+            elif gen == "relu":
+                x = np.maximum(x, 0.0)
+        lo, hi = max(a, sb * ROW_BLOCK), min(b, (sb + 1) * ROW_BLOCK)
+        out[lo - a:hi - a] = x[lo - sb * ROW_BLOCK:hi - sb * ROW_BLOCK]
+
+    with ThreadPoolExecutor(max(1, threads)) as ex:
+        list(ex.map(fill, range(a // ROW_BLOCK, (b + ROW_BLOCK - 1) // ROW_BLOCK)))
     return out
 
 
@@ -155,63 +229,130 @@ def host_cores():
 # ---------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the unmodified reference DCI on host cores, bounded sample of the workload
 # ---------------------------------------------------------------------------------------------------------
-def reference_sample(workload, steps, warmup, budget_s=25.0):
-    """Times oracle/_ref (reference DCI, training hyper-parameters training_loop.py:197,368,398).
-
-    Sample: the workload's dim and k, a pool subsample sized for the box's core count and a query
-    subsample per step (per-query cost does not depend on Q: dci.c:801 parallelises over queries)."""
+def force_omp_threads(cores):
+    """torchrun exports OMP_NUM_THREADS=1 to its children when nproc > 1; the reference DCI parallelises its query loop
+    with OpenMP (dci.c:801), so the thread count is ASSIGNED here (before libgomp is loaded with oracle/_ref/_dci.so)
+    and then read back from the OpenMP runtime: the count reported is the one in effect."""
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ["OMP_STACKSIZE"] = "256M"          # dci.c:572-573 keeps ~1.3 MB VLAs on worker stacks
+    os.environ.pop("OMP_THREAD_LIMIT", None)
     from oracle import ref_dci
-    n, q, d, k, _ = WORKLOADS[workload]
-    cores = host_cores()
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     if not ref_dci.available():
         return None
-    ns = int(min(n, 120000, max(2048, int(3.5e9) // (8 * d))))        # pool subsample bounded to 3.5 GB of float64
-    qs = int(min(q, max(64, 16 * cores)))
-    rng = np.random.default_rng(0)
-    pool = rng.standard_normal((ns, d))
-    queries = np.random.default_rng(1).standard_normal((qs, d))
-    if workload == "c1":
-        m, L, levels, cfov, cpr, qfov, qpr = 2, 7, 2, 10, 0.002, 100, 0.05      # dci_code/example.py:44-66
+    ref_dci.ext()                                # loads _dci.so (and libgomp with it)
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(int(cores))     # also covers a libgomp that something loaded earlier
+        gomp.omp_get_max_threads.restype = ctypes.c_int
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return None
+
+
+def reference_params(workload):
+    if workload == "c1":     # dci_code/example.py:44-66
+        return dict(m=2, L=7, levels=2, cfov=10, cpr=0.002, qfov=100, qpr=0.05, source="dci_code/example.py:60-66")
+    return dict(m=3, L=15, levels=3, cfov=10, cpr=0.002, qfov=200, qpr=1.0, source="training/training_loop.py:197,368,398")
+
+
+def reference_sample(workload, steps, warmup, wall_budget_s=240.0, max_pool_gb=24.0):
+    """Times oracle/_ref (the reference DCI) with the reference's own hyper-parameters on the FULL pool of the workload
+    (bounded only by host memory), `steps` timed query calls of a bounded query sample each (per-query cost does not
+    depend on Q: dci.c:801 parallelises over queries), and scores the approximate answers as recall@k against the
+    exact float64 answer on the same queries."""
+    from oracle import ref_dci
+    from oracle import knn_oracle as ko
+    n, q, d, k, gen, _ = WORKLOADS[workload]
+    cores = host_cores()
+    threads = force_omp_threads(cores)
+    if threads is None:
+        return None
+    note = ""
+    if gen == "image":
+        # configs[4] is 197 GB even in float32: infeasible on the host (SURVEY.md 8d); same dim and k on Gaussian rows
+        gen_wl, note = "c3", " (configs[4] pool does not fit host memory: %d x %d subsample, Gaussian rows)" % (min(n, 60000), d)
+        ns = min(n, 60000)
     else:
-        m, L, levels, cfov, cpr, qfov, qpr = 3, 15, 3, 10, 0.002, 200, 1.0       # training/training_loop.py:197,368,398
-    db = ref_dci.RefDCI(d, m, L)
+        gen_wl = workload
+        ns = int(min(n, max_pool_gb * 1e9 // (8 * d)))
+    qs = int(min(q, max(64, 16 * cores), 512))
     t0 = time.perf_counter()
-    db.add(pool, num_levels=levels, field_of_view=cfov, prop_to_retrieve=cpr)
+    if gen_wl == workload:
+        pool = synth_rows_host(workload, 0, ns, d, POOL_SEED, cores)
+        queries = synth_rows_host(workload, 0, qs, d, QUERY_SEED, cores)
+    else:
+        rng = np.random.default_rng(0)
+        pool = rng.standard_normal((ns, d), dtype=np.float32).astype(np.float64)
+        queries = np.random.default_rng(1).standard_normal((qs, d), dtype=np.float32).astype(np.float64)
+    if workload == "c4":
+        queries = pool[:qs].copy()            # the precision/recall metric queries every row against its own set
+    t_gen = time.perf_counter() - t0
+    p = reference_params(workload)
+    db = ref_dci.RefDCI(d, p["m"], p["L"])
+    t0 = time.perf_counter()
+    db.add(pool, num_levels=p["levels"], field_of_view=p["cfov"], prop_to_retrieve=p["cpr"])
     t_add = time.perf_counter() - t0
+
+    def one(nq_):
+        t0_ = time.perf_counter()
+        r = db.query(queries[:nq_], k, field_of_view=p["qfov"], prop_to_retrieve=p["qpr"])
+        return time.perf_counter() - t0_, r
+
+    # the requested number of steps is kept; what shrinks, if the box is slow, is the query sample per step
+    t_probe, _ = one(min(qs, 32))
+    per_q = t_probe / min(qs, 32)
+    total_steps = warmup + steps
+    if per_q * qs * total_steps > wall_budget_s:
+        qs = int(max(16, min(qs, wall_budget_s / (per_q * total_steps))))
     times = []
-    t_begin = time.perf_counter()
-    for s in range(warmup + steps):
-        t0 = time.perf_counter()
-        db.query(queries, k, field_of_view=qfov, prop_to_retrieve=qpr)
-        dt = time.perf_counter() - t0
+    res = None
+    for s in range(total_steps):
+        dt, res = one(qs)
         if s >= warmup:
             times.append(dt)
-        if time.perf_counter() - t_begin > 4 * budget_s and len(times) >= 1:
-            break
+    # recall@k of the approximate answer against the exact float64 answer on the same queries
+    flat_idx, _flat_dist, counts = res
+    exact_idx, _ = ko.exact_knn_numpy(pool, queries[:qs], k)
+    off = np.concatenate([[0], np.cumsum(counts)])
+    hits = 0
+    top1 = 0
+    for i in range(qs):
+        got = flat_idx[off[i]:off[i + 1]]
+        hits += len(set(got.tolist()) & set(exact_idx[i].tolist()))
+        top1 += int(len(got) > 0 and got[0] == exact_idx[i, 0])
     db.clear()
     total = float(np.sum(times))
+    kk = min(k, ns)
     return {"qps": qs * len(times) / total, "ms_per_step": 1e3 * total / len(times), "steps_done": len(times), "cores": cores,
-            "add_s": t_add,
-            "sample": "reference DCI (oracle/_ref, unmodified dci.c) m=%d L=%d levels=%d; pool subsample %d x %d float64 N(0,1) of the "
-                      "%d-row workload, %d queries/step, k=%d, OMP threads=%d; add() took %.1f s (not in value)" % (
-                          m, L, levels, ns, d, n, qs, k, cores, t_add)}
+            "threads": threads, "add_s": t_add, "recall_at_k": hits / float(qs * kk), "top1_recall": top1 / float(qs),
+            "queries_per_step": qs, "pool_rows": ns,
+            "sample": "reference DCI (oracle/_ref, unmodified dci.c) m=%d L=%d levels=%d build fov=%d p_retr=%g, query fov=%d p_retr=%g (%s); "
+                      "pool %d of %d rows x %d float64%s, %d queries/step, k=%d, OpenMP threads in effect=%d on %d cores; "
+                      "add() %.1f s and data generation %.1f s are not in value; recall@%d vs exact float64 = %.3f" % (
+                          p["m"], p["L"], p["levels"], p["cfov"], p["cpr"], p["qfov"], p["qpr"], p["source"], ns, n, d, note, qs, k,
+                          threads, cores, t_add, t_gen, kk, hits / float(qs * kk))}
+
+
+def cpu_baseline_object(r):
+    return {"value": r["qps"], "unit": "queries/s", "cores": r["cores"], "threads": r["threads"], "kind": "reference",
+            "sample": r["sample"], "recall_at_k": r["recall_at_k"], "top1_recall": r["top1_recall"], "add_s": r["add_s"],
+            "pool_rows": r["pool_rows"], "queries_per_step": r["queries_per_step"]}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    r = reference_sample(args.workload, args.steps, max(args.warmup, 1))
-    n, q, d, k, desc = WORKLOADS[args.workload]
+    r = reference_sample(args.workload, args.steps, args.warmup)
     if r is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/_dci.so missing (build with `make -C oracle ref` where /root/reference exists)"}))
         return 0
-    line = {"impl": "reference", "metric": "imle_knn_queries_per_sec", "value": r["qps"], "unit": "queries/s", "n_gpus": args.gpus,
-            "steps": r["steps_done"], "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+    line = {"impl": "reference", "metric": METRIC, "value": r["qps"], "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": r["steps_done"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: %s" % (args.workload, desc), "pool": n, "queries": q, "dim": d, "k": k},
-            "cpu_baseline": {"value": r["qps"], "unit": "queries/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"]},
+            "config": workload_config(args.workload),
+            "cpu_baseline": cpu_baseline_object(r),
+            "recall_at_k": r["recall_at_k"], "add_s": r["add_s"],
             "e2e": {"value": r["qps"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -225,7 +366,6 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from inclusivegan_b200.dci import DeviceKNN, F32, F64, load_library
-    import ctypes
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -237,40 +377,44 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n, q, d, k, desc = WORKLOADS[args.workload]
-    image_like = args.workload in IMAGE_LIKE
-    fdt, FT, fbytes = (torch.float32, F32, 4) if image_like else (torch.float64, F64, 8)
+    n, q, d, k, gen, desc = WORKLOADS[args.workload]
+    f32_features = GENERATORS[gen][0] == "float32"
+    fdt, FT, fbytes = (torch.float32, F32, 4) if f32_features else (torch.float64, F64, 8)
+    self_knn = args.workload == "c4"           # the precision/recall metric: self-kNN radii of TWO feature sets per step
+    if self_knn and world > 1:
+        raise RuntimeError("workload c4 (two-set self-kNN) is measured on one GPU; use --gpus 1")
     per = (n + world - 1) // world
     r0, r1 = min(n, per * rank), min(n, per * (rank + 1))
     need_gb = (r1 - r0) * d * (fbytes + 2) / 1e9 + q * d * (fbytes + 2) / 1e9
     if need_gb > 150.0:
         raise RuntimeError("workload %s needs %.0f GB per GPU at %d GPU(s): use more GPUs (pool rows are sharded)" % (args.workload, need_gb, world))
-    if image_like:
-        # ---- image-like float32 features generated on the device per row block (configs[4]) ----
-        pool = synth_rows(args.workload, r0, r1, d, dev, 1000)
-        queries = synth_rows(args.workload, 0, q, d, dev, 500000)
+    pool = synth_rows(args.workload, r0, r1, d, dev, POOL_SEED)
+    if self_knn:
+        queries = synth_rows(args.workload, 0, q, d, dev, SET_B_SEED)      # the second feature set
     else:
-        # ---- synthetic features (float64, the dtype of the reference's interface), identical on every rank ----
-        # the pool is generated in 8 fixed row blocks, each seeded by its block id, so 1/2/4/8-GPU runs see the same rows
-        pool = torch.empty(r1 - r0, d, device=dev, dtype=torch.float64)
-        blk = (n + 7) // 8
-        for b in range(8):
-            b0, b1 = max(r0, b * blk), min(r1, (b + 1) * blk, n)
-            if b1 <= b0:
-                continue
-            g = torch.Generator(device=dev)
-            g.manual_seed(1000 + b)
-            full = torch.randn(min((b + 1) * blk, n) - b * blk, d, device=dev, dtype=torch.float64, generator=g)
-            pool[b0 - r0:b1 - r0] = full[b0 - b * blk:b1 - b * blk]
-            del full
-        gq = torch.Generator(device=dev)
-        gq.manual_seed(1)
-        queries = torch.randn(q, d, device=dev, dtype=torch.float64, generator=gq)
+        queries = synth_rows(args.workload, 0, q, d, dev, QUERY_SEED)
+
+    # N > 1: a tie batch rides along: the last row of every shard is duplicated as the first row of the next
+    # shard, and the first `world` queries ARE those rows — distance 0 on two shards at once, resolved to the lower index
+    n_tie = 0
+    if world > 1 and r1 > r0:
+        lasts = torch.empty(world, d, device=dev, dtype=fdt)
+        dist.all_gather_into_tensor(lasts, pool[-1:].contiguous())
+        if rank > 0:
+            pool[0] = lasts[rank - 1]
+        n_tie = min(world, q)
+        queries[:n_tie] = lasts[:n_tie]
 
     stream = torch.cuda.current_stream()
+    lib = load_library()
     ix = DeviceKNN(d, local_rank)
     ix.set_stream(stream.cuda_stream)
     ix.add(pool.data_ptr(), FT, r1 - r0, index_base=r0)
+    ix_b = None
+    if self_knn:
+        ix_b = DeviceKNN(d, local_rank)
+        ix_b.set_stream(stream.cuda_stream)
+        ix_b.add(queries.data_ptr(), FT, q, index_base=0)
     torch.cuda.synchronize()
     kk = min(k, n)
     loc_i = torch.empty(q, kk, device=dev, dtype=torch.int32)
@@ -280,6 +424,9 @@ def run_b200(args):
     if world > 1:
         all_i = torch.empty(world, q, kk, device=dev, dtype=torch.int32)
         all_d = torch.empty(world, q, kk, device=dev, dtype=torch.float64)
+    if self_knn:
+        self_i = [torch.empty(n, kk, dtype=torch.int32).pin_memory(), torch.empty(q, kk, dtype=torch.int32).pin_memory()]
+        self_d = [torch.empty(n, kk, dtype=torch.float64).pin_memory(), torch.empty(q, kk, dtype=torch.float64).pin_memory()]
 
     # ---- multi-GPU exchange: NVLink peer-memory all-gather + merge (no NCCL on the path); NCCL only as a fallback ----
     exchange = None
@@ -318,7 +465,16 @@ def run_b200(args):
         torch.cuda.synchronize()
         ix.merge(all_i.data_ptr(), all_d.data_ptr(), world, q, kk, out_i.data_ptr(), out_d.data_ptr(), stream.cuda_stream)
 
+    def query_self(handle, oi, od):
+        rc = lib.b200knn_query_self(handle._handle, k, 0, ctypes.c_void_p(oi.data_ptr()), ctypes.c_void_p(od.data_ptr()), None)
+        if rc != 0:
+            raise RuntimeError(lib.b200knn_last_error().decode())
+
     def step_device():
+        if self_knn:      # ManifoldEstimator.__init__ of both sets (precision_recall.py:149-150): rows already on the device
+            query_self(ix, self_i[0], self_d[0])
+            query_self(ix_b, self_i[1], self_d[1])
+            return
         ix.query(queries.data_ptr(), FT, q, k, loc_i.data_ptr(), loc_d.data_ptr())
         if world > 1:
             exchange_and_merge()
@@ -341,24 +497,33 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    units_per_step = (n + q) if self_knn else q          # query rows answered per step
+    flops_per_step = 2.0 * d * (float(n) * n + float(q) * q) if self_knn else 2.0 * q * n * d
+
     # ---- device-resident arm ------------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
         step_device()
-    ix.reset_stats()
-    ix.set_profiling(True)
+    for h in (ix, ix_b):
+        if h is not None:
+            h.reset_stats()
+            h.set_profiling(True)
     sampler.mark_begin()
     total_ms = timed(step_device, args.steps)
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     st = ix.stats()
-    ix.set_profiling(False)
+    if ix_b is not None:
+        sb = ix_b.stats()
+        st = {key: st[key] + sb[key] for key in st}
+    for h in (ix, ix_b):
+        if h is not None:
+            h.set_profiling(False)
     launches = st["kernel_launches"] + ((2 if exchange is not None else 1) * args.steps if world > 1 else 0)
 
     # ---- end-to-end arm: host-buffer C-ABI call (what DCI.query makes), pinned host queries ----------
-    lib = load_library()
     hq = torch.empty(q, d, dtype=fdt).pin_memory()
     hq.copy_(queries)
     torch.cuda.synchronize()
@@ -366,11 +531,16 @@ def run_b200(args):
     ids = (ctypes.c_int * 1)(local_rank)
     assert lib.b200knn_create(d, 1, ids, ctypes.byref(hx)) == 0
     assert lib.b200knn_set_stream(hx, ctypes.c_void_p(stream.cuda_stream)) == 0
-    assert lib.b200knn_add_device(hx, ctypes.c_void_p(pool.data_ptr()), FT, r1 - r0, d, r0) == 0, lib.b200knn_last_error()
+    if not self_knn:
+        assert lib.b200knn_add_device(hx, ctypes.c_void_p(pool.data_ptr()), FT, r1 - r0, d, r0) == 0, lib.b200knn_last_error()
     h_i = torch.empty(q, kk, dtype=torch.int32).pin_memory()
     h_d = torch.empty(q, kk, dtype=torch.float64).pin_memory()
     res_i = torch.empty(q, kk, dtype=torch.int32).pin_memory()
     res_d = torch.empty(q, kk, dtype=torch.float64).pin_memory()
+    if self_knn:
+        hp = torch.empty(n, d, dtype=fdt).pin_memory()
+        hp.copy_(pool)
+        torch.cuda.synchronize()
 
     # N > 1: the replicated query matrix is uploaded ONCE per box — every rank copies its 1/N row slice from pinned host
     # memory and the slices are all-gathered over NVLink ("queries are broadcast", north_star) — instead of N full
@@ -386,12 +556,21 @@ def run_b200(args):
 
     sliced = world >= 4          # N <= 2: every rank runs the pipelined host-buffer call (upload hidden behind compute)
 
+    def check_rc(rc):
+        if rc != 0:
+            raise RuntimeError(lib.b200knn_last_error().decode())
+
     def step_e2e():
+        if self_knn:
+            # per feature set: ManifoldEstimator(features) = add(host rows) + self-kNN radii (precision_recall.py:60-90)
+            for rows, nrows, oi, od in ((hp, n, self_i[0], self_d[0]), (hq, q, self_i[1], self_d[1])):
+                check_rc(lib.b200knn_clear(hx))
+                check_rc(lib.b200knn_add(hx, ctypes.c_void_p(rows.data_ptr()), FT, nrows, d))
+                check_rc(lib.b200knn_query_self(hx, k, 0, ctypes.c_void_p(oi.data_ptr()), ctypes.c_void_p(od.data_ptr()), None))
+            return
         if not sliced:
-            rc = lib.b200knn_query(hx, ctypes.c_void_p(hq.data_ptr()), FT, q, d, k, 0, ctypes.c_void_p(h_i.data_ptr()),
-                                   ctypes.c_void_p(h_d.data_ptr()), None)
-            if rc != 0:
-                raise RuntimeError(lib.b200knn_last_error().decode())
+            check_rc(lib.b200knn_query(hx, ctypes.c_void_p(hq.data_ptr()), FT, q, d, k, 0, ctypes.c_void_p(h_i.data_ptr()),
+                                       ctypes.c_void_p(h_d.data_ptr()), None))
             if world > 1:     # shard results back to the device for the NVLink exchange, merged result back to the host
                 loc_i.copy_(h_i, non_blocking=True)
                 loc_d.copy_(h_d, non_blocking=True)
@@ -413,37 +592,123 @@ def run_b200(args):
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     e2e_ms = timed(step_e2e, e2e_steps)
+
+    # ---- secondaries: the trainer's 24-row calls, and add() from pageable host memory ----
+    small_call = None
+    add_s = None
+    if not self_knn and args.workload not in ("c5", "c5s"):
+        nsc = min(SMALL_CALLS, max(1, q // SMALL_CALL_ROWS))
+        hq_np = hq.numpy()
+        sc_i = np.empty((SMALL_CALL_ROWS, kk), dtype=np.int32)
+        sc_d = np.empty((SMALL_CALL_ROWS, kk), dtype=np.float64)
+
+        def small(i):
+            rows = hq_np[i * SMALL_CALL_ROWS:(i + 1) * SMALL_CALL_ROWS]
+            check_rc(lib.b200knn_query(hx, ctypes.c_void_p(rows.ctypes.data), FT, SMALL_CALL_ROWS, d, k, 0,
+                                       ctypes.c_void_p(sc_i.ctypes.data), ctypes.c_void_p(sc_d.ctypes.data), None))
+        for i in range(min(20, nsc)):
+            small(i)
+        barrier()
+        lat = []
+        t_all = time.perf_counter()
+        for i in range(nsc):
+            t0 = time.perf_counter()
+            small(i)
+            lat.append(time.perf_counter() - t0)
+        t_all = time.perf_counter() - t_all
+        tl = torch.tensor([t_all], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        small_call = {"rows_per_call": SMALL_CALL_ROWS, "calls": nsc, "latency_ms_median": 1e3 * float(np.median(lat)),
+                      "latency_ms_p95": 1e3 * float(np.percentile(lat, 95)), "calls_per_s": nsc / float(tl.item()),
+                      "queries_per_s": nsc * SMALL_CALL_ROWS / float(tl.item()),
+                      "api": "b200knn_query, host rows, one call per %d rows, back to back (training_loop.py:374-403)%s" % (
+                          SMALL_CALL_ROWS, "" if world == 1 else "; per rank against its pool shard, no exchange")}
     lib.b200knn_destroy(hx)
+    if not self_knn and args.workload not in ("c5", "c5s") and (r1 - r0) * d * fbytes < 40e9:
+        pool_np = pool.cpu().numpy()             # pageable, like the trainer's np.zeros + fill (training_loop.py:358-365)
+        ha = ctypes.c_void_p()
+        assert lib.b200knn_create(d, 1, ids, ctypes.byref(ha)) == 0
+        ts = []
+        for _ in range(3):
+            check_rc(lib.b200knn_clear(ha))
+            barrier()
+            t0 = time.perf_counter()
+            check_rc(lib.b200knn_add(ha, ctypes.c_void_p(pool_np.ctypes.data), FT, r1 - r0, d))
+            ts.append(time.perf_counter() - t0)
+        lib.b200knn_destroy(ha)
+        del pool_np
+        ta = torch.tensor([min(ts)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        add_s = {"value": float(ta.item()), "unit": "s", "rows_per_rank": r1 - r0, "bytes_per_rank": (r1 - r0) * d * fbytes,
+                 "api": "b200knn_add from pageable host memory (H2D through the pinned ring + column means + BF16 convert + norms), best of 3, max over ranks"}
 
     # ---- self-check of the last device result against a float64 torch brute force on a query subsample ----
-    nchk = min(q, 64)
-    sub = queries[:nchk].double()
-    d2 = torch.empty(nchk, r1 - r0, device=dev, dtype=torch.float64)
-    for c0 in range(0, r1 - r0, 8192):                # float64 whatever the feature dtype
-        pc = pool[c0:c0 + 8192].double()
-        d2[:, c0:c0 + 8192] = (sub * sub).sum(1, keepdim=True) + (pc * pc).sum(1)[None, :] - 2.0 * sub @ pc.T
-    del pc
-    tk = torch.topk(d2, min(kk, r1 - r0), dim=1, largest=False)
-    if world == 1:
-        check = bool((tk.indices.to(torch.int32) == loc_i[:nchk]).all().item()) if rank == 0 else None
+    nchk = min(units_per_step if self_knn else q, args.check_queries)
+
+    def brute(sub, base, lo, hi):
+        """exact float64 top-kk of `sub` rows against base rows [lo, hi): direct differences, no cancellation"""
+        cand_d = torch.full((sub.shape[0], kk), float("inf"), device=dev, dtype=torch.float64)
+        cand_i = torch.full((sub.shape[0], kk), -1, device=dev, dtype=torch.int64)
+        for s0 in range(0, sub.shape[0], 256):
+            sq = sub[s0:s0 + 256].double()
+            d2 = torch.empty(sq.shape[0], hi - lo, device=dev, dtype=torch.float64)
+            for c0 in range(lo, hi, 16384):
+                pc = base[c0:min(c0 + 16384, hi)].double()
+                d2[:, c0 - lo:c0 - lo + pc.shape[0]] = (sq * sq).sum(1, keepdim=True) + (pc * pc).sum(1)[None, :] - 2.0 * sq @ pc.T
+            kt = min(kk + 4, hi - lo)
+            tk = torch.topk(d2, kt, dim=1, largest=False)
+            # re-evaluate the shortlist by direct differences (the GEMM form cancels), then order by (distance, index)
+            rows = base[(tk.indices + lo).reshape(-1)].double().view(sq.shape[0], kt, -1)
+            ex = ((rows - sq[:, None, :]) ** 2).sum(2)
+            key = torch.argsort(ex + 0.0, dim=1, stable=True)
+            order = torch.gather(tk.indices, 1, key)
+            exs = torch.gather(ex, 1, key)
+            m = min(kk, kt)
+            cand_d[s0:s0 + sq.shape[0], :m] = exs[:, :m]
+            cand_i[s0:s0 + sq.shape[0], :m] = order[:, :m] + lo
+        return cand_i, cand_d
+
+    def agree(got_i, got_d, ref_i, ref_d):
+        """indices equal, or the distance at that rank ties within 1e-6 relative (north_star acceptance)"""
+        same = got_i.long() == ref_i
+        tie = (got_d - ref_d.sqrt()).abs() <= 1e-6 * ref_d.sqrt().clamp_min(1e-300)
+        return bool((same | tie).all().item()) and bool(((got_d - ref_d.sqrt()).abs() <= 1e-5 * ref_d.sqrt().clamp_min(1e-300)).all().item())
+
+    if self_knn:
+        sel = torch.randperm(n, device=dev, generator=torch.Generator(device=dev).manual_seed(3))[:nchk // 2]
+        ri, rd = brute(pool[sel], pool, 0, n)
+        check = agree(self_i[0].to(dev)[sel], self_d[0].to(dev)[sel], ri, rd)
+        ri, rd = brute(queries[sel], queries, 0, q)
+        check = check and agree(self_i[1].to(dev)[sel], self_d[1].to(dev)[sel], ri, rd)
     else:
-        # global answer of the subsample from per-shard torch answers (float64), compared with the merged result
+        # a tie batch rides along at N > 1: queries that ARE pool rows sitting on shard boundaries (distance 0 on one
+        # shard, duplicates resolved to the lower index by the merge)
         step_device()
         torch.cuda.synchronize()
-        cand_d = torch.full((nchk, kk), float("inf"), device=dev, dtype=torch.float64)
-        cand_i = torch.full((nchk, kk), -1, device=dev, dtype=torch.int64)
-        cand_d[:, :tk.values.shape[1]] = tk.values
-        cand_i[:, :tk.indices.shape[1]] = tk.indices + r0
-        g_d = torch.empty(world * nchk, kk, device=dev, dtype=torch.float64)
-        g_i = torch.empty(world * nchk, kk, device=dev, dtype=torch.int64)
-        dist.all_gather_into_tensor(g_d, cand_d)
-        dist.all_gather_into_tensor(g_i, cand_i)
-        torch.cuda.synchronize()
-        g_d = g_d.view(world, nchk, kk).permute(1, 0, 2).reshape(nchk, world * kk)
-        g_i = g_i.view(world, nchk, kk).permute(1, 0, 2).reshape(nchk, world * kk)
-        best = torch.topk(g_d, kk, dim=1, largest=False).indices
-        ref = torch.gather(g_i, 1, best).to(torch.int32)
-        check = bool((ref == out_i[:nchk]).all().item()) if rank == 0 else None
+        sel = torch.randperm(q, device=dev, generator=torch.Generator(device=dev).manual_seed(3))[:nchk]
+        sel[:n_tie] = torch.arange(n_tie, device=dev)        # the tie batch is always checked
+        ci, cd = brute(queries[sel], pool, 0, r1 - r0)
+        ci = torch.where(ci >= 0, ci + r0, ci)
+        if world == 1:
+            check = agree(loc_i[sel], loc_d[sel], ci, cd)
+        else:
+            g_d = torch.empty(world * nchk, kk, device=dev, dtype=torch.float64)
+            g_i = torch.empty(world * nchk, kk, device=dev, dtype=torch.int64)
+            dist.all_gather_into_tensor(g_d, cd)
+            dist.all_gather_into_tensor(g_i, ci)
+            torch.cuda.synchronize()
+            g_d = g_d.view(world, nchk, kk).permute(1, 0, 2).reshape(nchk, world * kk)
+            g_i = g_i.view(world, nchk, kk).permute(1, 0, 2).reshape(nchk, world * kk)
+            best = torch.topk(g_d, kk, dim=1, largest=False).indices
+            check = agree(out_i[sel], out_d[sel], torch.gather(g_i, 1, best), torch.gather(g_d, 1, best))
+            # ties across shards resolve to the LOWER index: query g duplicates the last row of shard g
+            want = torch.tensor([min(n, per * (g + 1)) - 1 for g in range(n_tie)], device=dev, dtype=torch.int32)
+            check = check and bool((out_i[:n_tie, 0] == want).all().item()) and bool((out_d[:n_tie, 0] == 0).all().item())
+            flag = torch.tensor([1 if check else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # every rank holds the merged result: all must agree
+            check = bool(flag.item())
 
     if rank == 0:
         peaks = load_peaks()
@@ -455,18 +720,22 @@ def run_b200(args):
         if os.path.exists(prof):
             try:
                 with open(prof) as fh:
-                    traffic = json.load(fh).get(args.workload, {}).get("dram_bytes_per_launch")
+                    ent = json.load(fh).get(args.workload, {})
+                # an ncu capture describes ONE shard size: it applies to the GPU count it was taken at only
+                if int(ent.get("n_gpus", 1)) == world:
+                    traffic = ent.get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         line = {
-            "metric": "imle_knn_queries_per_sec", "value": q / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
+            "metric": METRIC, "value": units_per_step / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16 (tensor pass) + f64 (exact re-rank)", "data": "synthetic",
-            "config": {"workload": "%s: %s" % (args.workload, desc), "pool": n, "queries": q, "dim": d, "k": k,
-                       "features": ("float32 image-like (16-d latent through a fixed basis + 0.05 pixel noise, clipped to [-1,1]), seeded per 4096-row block, generated on device" if image_like else "float64 N(0,1), seeded"), "parallelism": "pool row-sharded x%d, queries replicated, exchange=%s + k-way merge kernel" % (world, exchange_kind)
-                       if world > 1 else "single GPU", "l2": "inputs exceed L2 (BF16 pool shard %.2f GB > 126 MB); no explicit flush" % ((r1 - r0) * d * 2 / 1e9),
-                       "timing": "CUDA events on the launching stream, max over ranks"},
-            "tensor_peak_frac": 2.0 * q * n * d / (ms_step * 1e-3) / 1e12 / (peaks["bf16_tflops"] * world),
+            "config": workload_config(args.workload),
+            "run": {"parallelism": ("pool row-sharded x%d, queries replicated, exchange=%s + k-way merge kernel" % (world, exchange_kind))
+                    if world > 1 else "single GPU",
+                    "l2": "inputs exceed L2 (BF16 pool shard %.2f GB > 126 MB); no explicit flush" % ((r1 - r0) * d * 2 / 1e9),
+                    "timing": "CUDA events on the launching stream, max over ranks"},
+            "tensor_peak_frac": flops_per_step / (ms_step * 1e-3) / 1e12 / (peaks["bf16_tflops"] * world),
             "roofline": {"bound": "tensor", "kernel": "dist_topc_kernel (tcgen05 BF16 distance GEMM + fused top-C)",
                          "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
                          "frac_of_sustained_peak": (ach / peaks["bf16_tflops_sustained"]) if peaks.get("bf16_tflops_sustained") else None,
@@ -475,19 +744,23 @@ def run_b200(args):
             "kernel_ms_per_step": {"convert": st["ms_convert"] / args.steps, "distance": st["ms_distance"] / args.steps,
                                    "rerank": st["ms_rerank"] / args.steps, "second_pass": st["ms_scan"] / args.steps},
             "uncertified_per_step": st["uncertified"] / args.steps,
-            "e2e": {"value": q / (e2e_ms / e2e_steps * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                    "h2d_bytes_per_step": q * d * fbytes, "d2h_bytes_per_step": q * kk * 12,
-                    "api": ("b200knn_query (host buffers; the call inclusivegan_b200.dci.DCI.query makes)" + ("" if world == 1 else " per rank + peer exchange + D2H of the merged result")) if not sliced else
-                           "per rank: H2D of a 1/N query slice from pinned host memory, NVLink all-gather of the slices, b200knn_query_device, peer exchange, D2H of the merged result"},
+            "e2e": {"value": units_per_step / (e2e_ms / e2e_steps * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                    "h2d_bytes_per_step": (n + q) * d * fbytes if self_knn else q * d * fbytes,
+                    "d2h_bytes_per_step": units_per_step * kk * 12,
+                    "api": "per feature set: b200knn_clear + b200knn_add (host rows) + b200knn_query_self (what ManifoldEstimator.__init__ does)" if self_knn else
+                           (("b200knn_query (host buffers; the call inclusivegan_b200.dci.DCI.query makes)" + ("" if world == 1 else " per rank + peer exchange + D2H of the merged result")) if not sliced else
+                            "per rank: H2D of a 1/N query slice from pinned host memory, NVLink all-gather of the slices, b200knn_query_device, peer exchange, D2H of the merged result")},
+            "add_s": add_s,
+            "small_call": small_call,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "self_check_top%d_vs_torch_f64" % kk: check,
+            "self_check": check, "self_check_queries": int(nchk), "self_check_rule": "top-%d vs torch float64 brute force (direct differences): index equal or distance tie <= 1e-6 rel, distances <= 1e-5 rel" % kk,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and args.workload != "small":
             try:
-                r = reference_sample(args.workload, steps=2, warmup=1)
+                r = reference_sample(args.workload, steps=2, warmup=1, wall_budget_s=30.0)
                 if r is not None:
-                    line["cpu_baseline"] = {"value": r["qps"], "unit": "queries/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"]}
+                    line["cpu_baseline"] = cpu_baseline_object(r)
                 else:
                     line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": host_cores(), "kind": "reference",
                                             "sample": "unavailable: oracle/_ref/_dci.so missing"}
@@ -508,6 +781,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--check-queries", type=int, default=2048, help="queries of the last step checked against a float64 brute force")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU result exchange: NVLink peer-memory kernels (default) or NCCL all-gather")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

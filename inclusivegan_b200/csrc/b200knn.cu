@@ -331,6 +331,7 @@ int b200knn_exchange_create(int device, int rank, int world, int64_t max_nq, int
     cudaError_t e = cudaMalloc(&ex->base, ex->bytes);
     if (e != cudaSuccess) { delete ex; return fail(B200KNN_ENOMEM, "cudaMalloc(%zu) for the exchange buffer failed: %s", ex->bytes, cudaGetErrorString(e)); }
     cudaMemset(ex->base, 0, ex->off_idx);
+    cudaDeviceSynchronize();   // flags are zero before any peer can map the buffer and publish into it
     ex->peer_base[rank] = ex->base;
     if (world == 1) ex->connected = true;
     *out = ex;
@@ -706,8 +707,6 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
     std::vector<int> active;
     for (int g = 0; g < G; g++)
         if (ix->shards[g].n > 0) active.push_back(g);
-    for (int g : active)
-        if (ix->shards[g].n < kk) return fail(B200KNN_EINVAL, "a shard holds fewer rows (%lld) than k=%d; use fewer devices", (long long)ix->shards[g].n, kk);
     const int lists = static_cast<int>(active.size());
     Shard &s0 = ix->shards[active[0]];
     // chunks of one query-tile group of the per-shard kernel (see the single-device path)
@@ -737,6 +736,10 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
         if (nchunks > 1) TRY(s.q_stage2.ensure(static_cast<size_t>(max_rows) * dim * esz));
         TRY(s.out_idx.ensure(static_cast<size_t>(max_rows) * kk));
         TRY(s.out_dist.ensure(static_cast<size_t>(max_rows) * kk));
+        if (s.n < kk) {   // a shard with fewer than kk rows answers min(kk, rows) per query; its lists are padded to kk below
+            TRY(s.pad_idx.ensure(static_cast<size_t>(max_rows) * kk));
+            TRY(s.pad_dist.ensure(static_cast<size_t>(max_rows) * kk));
+        }
     }
     CU_TRY(cudaSetDevice(s0.device));
     TRY(ix->g_idx.ensure(static_cast<size_t>(lists) * max_rows * kk));
@@ -793,10 +796,22 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
             unsigned char *qp = b ? s.q_stage2.p : s.q_stage.p;
             if (rc == B200KNN_OK) rc = s.query_device(qp, dtype, cq, dim, dim, ix->kp, kk, flags, s.out_idx.p, s.out_dist.p);
             if (rc == B200KNN_OK) {
-                cudaError_t e = cudaMemcpyPeerAsync(ix->g_idx.p + static_cast<size_t>(i) * cq * kk, s0.device, s.out_idx.p, s.device,
-                                                    static_cast<size_t>(cq) * kk * sizeof(int32_t), s.stream);
+                const int32_t *src_i = s.out_idx.p;
+                const double *src_d = s.out_dist.p;
+                cudaError_t e = cudaSuccess;
+                if (s.n < kk) {
+                    s.stats.kernel_launches++;
+                    pad_topk_kernel<<<static_cast<unsigned>(std::min<int64_t>(s.num_sms * 4, (cq * kk + 255) / 256)), 256, 0, s.stream>>>(
+                        s.out_idx.p, s.out_dist.p, cq, static_cast<int>(s.n), kk, s.pad_idx.p, s.pad_dist.p);
+                    e = cudaGetLastError();
+                    src_i = s.pad_idx.p;
+                    src_d = s.pad_dist.p;
+                }
                 if (e == cudaSuccess)
-                    e = cudaMemcpyPeerAsync(ix->g_dist.p + static_cast<size_t>(i) * cq * kk, s0.device, s.out_dist.p, s.device,
+                    e = cudaMemcpyPeerAsync(ix->g_idx.p + static_cast<size_t>(i) * cq * kk, s0.device, src_i, s.device,
+                                            static_cast<size_t>(cq) * kk * sizeof(int32_t), s.stream);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyPeerAsync(ix->g_dist.p + static_cast<size_t>(i) * cq * kk, s0.device, src_d, s.device,
                                             static_cast<size_t>(cq) * kk * sizeof(double), s.stream);
                 if (e == cudaSuccess) e = cudaEventRecord(done[i], s.stream);
                 if (e != cudaSuccess) rc = fail(B200KNN_ECUDA, "gathering shard results failed: %s", cudaGetErrorString(e));

@@ -34,6 +34,16 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// system-scope acquire load / release store: flags written by a peer GPU over NVLink (exchange kernels)
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // Opaque use of a register: everything loaded into the arguments must be issued before the compiler may start
 // consuming them (it otherwise re-fuses "load all, then convert all" into load/convert pairs that reuse three
 // registers, i.e. three loads in flight instead of twenty-four).

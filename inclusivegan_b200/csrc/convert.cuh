@@ -37,9 +37,10 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T *__restrict__ src, int64_t n, int64_t ld, int dim, double *__restrict__ sums) {
     const int rows_per_block = 256;
-    const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
+    // row blocks on grid.x (up to 2^31-1 blocks), column blocks on grid.y
+    const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
     const int64_t r1 = min(r0 + rows_per_block, n);
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
     if (c >= dim) return;
     double a0 = 0.0, a1 = 0.0;
     int64_t r = r0;

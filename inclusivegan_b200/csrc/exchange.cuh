@@ -36,6 +36,20 @@ merge_topk_kernel(const int32_t *__restrict__ idx, const double *__restrict__ di
     }
 }
 
+// A shard that holds fewer than kk rows answers with ks = its row count per query; pad its lists to kk entries with
+// (-1, DBL_MAX), which the merge kernels skip (dci.py:278-279: num_neighbours=-1 means all points, however the pool is sharded).
+__global__ void __launch_bounds__(256)
+pad_topk_kernel(const int32_t *__restrict__ idx, const double *__restrict__ dist, int64_t nq, int ks, int kk,
+                int32_t *__restrict__ out_idx, double *__restrict__ out_dist) {
+    const int64_t total = nq * kk;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t q = i / kk;
+        const int r = static_cast<int>(i % kk);
+        out_idx[i] = (r < ks) ? idx[q * ks + r] : -1;
+        out_dist[i] = (r < ks) ? dist[q * ks + r] : DBL_MAX;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // NVLink exchange for row-sharded pools, one process per GPU: all-gather by peer stores + merge, no NCCL.
 //   publish_topk_kernel : every rank writes its local [nq][kk] (index, distance) lists straight into slot `rank` of EVERY
@@ -84,15 +98,16 @@ merge_wait_kernel(const int32_t *__restrict__ gidx, const double *__restrict__ g
                   int world, unsigned int step, int64_t max_items, int64_t nq, int kk, int32_t *__restrict__ out_idx,
                   double *__restrict__ out_dist) {
     if (threadIdx.x < world) {
-        const volatile unsigned int *f = flags + threadIdx.x * 32;
+        // system-scope acquire: pairs with the publisher's __threadfence_system() + flag store on another GPU
+        const unsigned int *f = flags + threadIdx.x * 32;
         const uint64_t t0 = global_timer_ns();
-        while (*f < step) {                  // steps only grow; a peer one step ahead is fine
+        while (ld_acquire_sys(f) < step) {   // steps only grow; a peer one step ahead is fine
             __nanosleep(200);
             if (global_timer_ns() - t0 > 20000000000ull) __trap();   // 20 s: a peer died
         }
+        __threadfence_system();
     }
     __syncthreads();
-    __threadfence();
     const int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (q >= nq) return;
     const int64_t base = static_cast<int64_t>(step & 1u) * world * max_items;

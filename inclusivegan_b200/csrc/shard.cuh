@@ -59,8 +59,8 @@ struct Shard {
     cudaStream_t copy_stream = nullptr;
     int copy_threads = 8;            // $B200KNN_COPY_THREADS
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
-    DevBuf<int32_t> out_idx;
-    DevBuf<double> out_dist;
+    DevBuf<int32_t> out_idx, pad_idx;
+    DevBuf<double> out_dist, pad_dist;
     int *h_count = nullptr;          // pinned
     const __nv_bfloat16 *cur_q_bf = nullptr;   // BF16 query rows of the tensor pass in flight (second pass gathers from them)
     int64_t last_nq = 0;             // geometry of the last tensor pass (b200knn_debug_shortlists)
@@ -186,7 +186,7 @@ struct Shard {
         drain_events();
         q_bf.release(); qnorm_bf.release(); q_err.release(); q_bf2.release(); uncert_thr.release(); coll_count.release(); coll_idx.release(); overflow_list.release(); sched_items.release(); sched_items2.release(); sched_slots.release(); stream_sync.release(); radius2.release(); colterm.release(); rowthr.release(); member.release(); cand_s.release(); cand_i.release(); uncert_list.release();
         scan_d2.release(); scan_d2_sorted.release(); scan_iota.release(); scan_vals_sorted.release(); scan_offsets.release();
-        cub_tmp.release(); q_stage.release(); q_stage2.release(); out_idx.release(); out_dist.release(); scalars.release();
+        cub_tmp.release(); q_stage.release(); q_stage2.release(); out_idx.release(); out_dist.release(); pad_idx.release(); pad_dist.release(); scalars.release();
         if (h_count) cudaFreeHost(h_count);
         if (own_stream) cudaStreamDestroy(own_stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -266,7 +266,7 @@ struct Shard {
         if (!use_centering || rows <= 0) return B200KNN_OK;
         TRY(col_mean.ensure(dim));
         CU_TRY(cudaMemsetAsync(col_mean.p, 0, static_cast<size_t>(dim) * sizeof(double), stream));
-        dim3 grid(static_cast<unsigned>((dim + 255) / 256), static_cast<unsigned>((rows + 255) / 256));
+        dim3 grid(static_cast<unsigned>((rows + 255) / 256), static_cast<unsigned>((dim + 255) / 256));
         prof_begin(K_CONVERT);
         if (dtype == B200KNN_F64) colsum_kernel<double><<<grid, 256, 0, stream>>>(static_cast<const double *>(d_rows), rows, ld, dim, col_mean.p);
         else colsum_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(d_rows), rows, ld, dim, col_mean.p);
