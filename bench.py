@@ -407,63 +407,32 @@ def run_b200(args):
 
     stream = torch.cuda.current_stream()
     lib = load_library()
+    kk = min(k, n)
     ix = DeviceKNN(d, local_rank)
     ix.set_stream(stream.cuda_stream)
-    ix.add(pool.data_ptr(), FT, r1 - r0, index_base=r0)
+    # ---- multi-GPU: the library's collective protocol over NVLink peer memory (b200knn_exchange_*); torch.distributed only
+    # hands the 64-byte IPC handles round, once ----
+    exchange = None
+    if world > 1:
+        from inclusivegan_b200.dci import PeerExchange
+        exchange = PeerExchange(local_rank, rank, world, min(q, 32768), kk, dim=d)
+        handles = [None] * world
+        dist.all_gather_object(handles, exchange.handle())
+        exchange.connect(handles)
+        exchange.add_device(ix, pool.data_ptr(), FT, r1 - r0, index_base=r0)      # global centring vector: column sums gathered over peer memory
+    else:
+        ix.add(pool.data_ptr(), FT, r1 - r0, index_base=r0)
     ix_b = None
     if self_knn:
         ix_b = DeviceKNN(d, local_rank)
         ix_b.set_stream(stream.cuda_stream)
         ix_b.add(queries.data_ptr(), FT, q, index_base=0)
     torch.cuda.synchronize()
-    kk = min(k, n)
-    loc_i = torch.empty(q, kk, device=dev, dtype=torch.int32)
-    loc_d = torch.empty(q, kk, device=dev, dtype=torch.float64)
     out_i = torch.empty(q, kk, device=dev, dtype=torch.int32)
     out_d = torch.empty(q, kk, device=dev, dtype=torch.float64)
-    if world > 1:
-        all_i = torch.empty(world, q, kk, device=dev, dtype=torch.int32)
-        all_d = torch.empty(world, q, kk, device=dev, dtype=torch.float64)
     if self_knn:
         self_i = [torch.empty(n, kk, dtype=torch.int32).pin_memory(), torch.empty(q, kk, dtype=torch.int32).pin_memory()]
         self_d = [torch.empty(n, kk, dtype=torch.float64).pin_memory(), torch.empty(q, kk, dtype=torch.float64).pin_memory()]
-
-    # ---- multi-GPU exchange: NVLink peer-memory all-gather + merge (no NCCL on the path); NCCL only as a fallback ----
-    exchange = None
-    exchange_kind = "none"
-    if world > 1:
-        from inclusivegan_b200.dci import PeerExchange
-        try:
-            if args.exchange == "nccl":
-                raise RuntimeError("NCCL exchange requested")
-            exchange = PeerExchange(local_rank, rank, world, q, kk)
-            handles = [None] * world
-            dist.all_gather_object(handles, exchange.handle())       # once, at start-up: 64 bytes per rank
-            exchange.connect(handles)
-            ok = torch.tensor([1], device=dev)
-        except Exception as e:
-            exchange = None
-            ok = torch.tensor([0], device=dev)
-            if rank == 0 and args.exchange != "nccl":
-                sys.stderr.write("peer-memory exchange unavailable (%r); falling back to NCCL all-gather\n" % (e,))
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)                     # all ranks or none
-        if int(ok.item()) == 0:
-            exchange = None
-        exchange_kind = "nvlink-peer-stores" if exchange is not None else "nccl-allgather"
-
-    def exchange_and_merge():
-        if exchange is not None:
-            # publish kernel (P2P stores into every peer's buffer + step flag) and flag-waiting merge kernel
-            exchange.allgather_merge(loc_i.data_ptr(), loc_d.data_ptr(), q, kk, out_i.data_ptr(), out_d.data_ptr(), stream.cuda_stream)
-            return
-        # NCCL all-gather of the per-shard (index, distance) lists over NVLink, then the k-way merge kernel.
-        # The device-wide synchronisation keeps the collective's kernels (which may run on NCCL's own stream and
-        # spin until the peer arrives) from sharing the GPU with the next step's persistent distance kernel, which
-        # wants every SM: measured at N=2, overlapping them costs +45 % on the distance kernel.
-        dist.all_gather_into_tensor(all_i.view(world * q, kk), loc_i)
-        dist.all_gather_into_tensor(all_d.view(world * q, kk), loc_d)
-        torch.cuda.synchronize()
-        ix.merge(all_i.data_ptr(), all_d.data_ptr(), world, q, kk, out_i.data_ptr(), out_d.data_ptr(), stream.cuda_stream)
 
     def query_self(handle, oi, od):
         rc = lib.b200knn_query_self(handle._handle, k, 0, ctypes.c_void_p(oi.data_ptr()), ctypes.c_void_p(od.data_ptr()), None)
@@ -474,10 +443,10 @@ def run_b200(args):
         if self_knn:      # ManifoldEstimator.__init__ of both sets (precision_recall.py:149-150): rows already on the device
             query_self(ix, self_i[0], self_d[0])
             query_self(ix_b, self_i[1], self_d[1])
-            return
-        ix.query(queries.data_ptr(), FT, q, k, loc_i.data_ptr(), loc_d.data_ptr())
-        if world > 1:
-            exchange_and_merge()
+        elif world > 1:   # tensor pass on the local shard, bound exchange, globally pruned exact re-rank, list exchange + merge
+            exchange.query_device(ix, queries.data_ptr(), FT, q, k, out_i.data_ptr(), out_d.data_ptr())
+        else:
+            ix.query(queries.data_ptr(), FT, q, k, out_i.data_ptr(), out_d.data_ptr())
 
     def barrier():
         if world > 1:
@@ -521,7 +490,7 @@ def run_b200(args):
     for h in (ix, ix_b):
         if h is not None:
             h.set_profiling(False)
-    launches = st["kernel_launches"] + ((2 if exchange is not None else 1) * args.steps if world > 1 else 0)
+    launches = st["kernel_launches"]
 
     # ---- end-to-end arm: host-buffer C-ABI call (what DCI.query makes), pinned host queries ----------
     hq = torch.empty(q, d, dtype=fdt).pin_memory()
@@ -531,30 +500,14 @@ def run_b200(args):
     ids = (ctypes.c_int * 1)(local_rank)
     assert lib.b200knn_create(d, 1, ids, ctypes.byref(hx)) == 0
     assert lib.b200knn_set_stream(hx, ctypes.c_void_p(stream.cuda_stream)) == 0
-    if not self_knn:
+    if not self_knn and world == 1:
         assert lib.b200knn_add_device(hx, ctypes.c_void_p(pool.data_ptr()), FT, r1 - r0, d, r0) == 0, lib.b200knn_last_error()
     h_i = torch.empty(q, kk, dtype=torch.int32).pin_memory()
     h_d = torch.empty(q, kk, dtype=torch.float64).pin_memory()
-    res_i = torch.empty(q, kk, dtype=torch.int32).pin_memory()
-    res_d = torch.empty(q, kk, dtype=torch.float64).pin_memory()
     if self_knn:
         hp = torch.empty(n, d, dtype=fdt).pin_memory()
         hp.copy_(pool)
         torch.cuda.synchronize()
-
-    # N > 1: the replicated query matrix is uploaded ONCE per box — every rank copies its 1/N row slice from pinned host
-    # memory and the slices are all-gathered over NVLink ("queries are broadcast", north_star) — instead of N full
-    # uploads competing for the host's memory bandwidth (measured at N=8: 34 ms/step that way).
-    q_pad = (q + world - 1) // world * world
-    q_per = q_pad // world
-    if world > 1:
-        qa, qb = min(q, rank * q_per), min(q, (rank + 1) * q_per)
-        hq_slice = torch.zeros(q_per, d, dtype=fdt).pin_memory()
-        hq_slice[:qb - qa].copy_(queries[qa:qb])
-        dq_full = torch.empty(q_pad, d, device=dev, dtype=fdt)
-        torch.cuda.synchronize()
-
-    sliced = world >= 4          # N <= 2: every rank runs the pipelined host-buffer call (upload hidden behind compute)
 
     def check_rc(rc):
         if rc != 0:
@@ -567,26 +520,13 @@ def run_b200(args):
                 check_rc(lib.b200knn_clear(hx))
                 check_rc(lib.b200knn_add(hx, ctypes.c_void_p(rows.data_ptr()), FT, nrows, d))
                 check_rc(lib.b200knn_query_self(hx, k, 0, ctypes.c_void_p(oi.data_ptr()), ctypes.c_void_p(od.data_ptr()), None))
-            return
-        if not sliced:
+        elif world > 1:
+            # b200knn_exchange_query: every rank uploads 1/N of every query chunk from the (same) pinned host matrix; BF16 rows and,
+            # behind the tensor pass, the original rows are broadcast by the copy engines; merged result lands in host memory
+            exchange.query_host(ix, hq.data_ptr(), FT, q, k, h_i.data_ptr(), h_d.data_ptr())
+        else:
             check_rc(lib.b200knn_query(hx, ctypes.c_void_p(hq.data_ptr()), FT, q, d, k, 0, ctypes.c_void_p(h_i.data_ptr()),
                                        ctypes.c_void_p(h_d.data_ptr()), None))
-            if world > 1:     # shard results back to the device for the NVLink exchange, merged result back to the host
-                loc_i.copy_(h_i, non_blocking=True)
-                loc_d.copy_(h_d, non_blocking=True)
-                exchange_and_merge()
-                res_i.copy_(out_i, non_blocking=True)
-                res_d.copy_(out_d, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-            return
-        dq_full[rank * q_per:(rank + 1) * q_per].copy_(hq_slice, non_blocking=True)          # H2D of this rank's slice
-        dist.all_gather_into_tensor(dq_full, dq_full[rank * q_per:(rank + 1) * q_per])       # NVLink broadcast of the slices
-        torch.cuda.synchronize()       # keep NCCL's kernels off the SMs the persistent distance kernel wants
-        ix.query(dq_full.data_ptr(), FT, q, k, loc_i.data_ptr(), loc_d.data_ptr())
-        exchange_and_merge()
-        res_i.copy_(out_i, non_blocking=True)                                                 # D2H of the merged result
-        res_d.copy_(out_d, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
 
     e2e_steps = max(1, min(args.steps, 5))
     for _ in range(min(args.warmup, 2)):
@@ -604,8 +544,11 @@ def run_b200(args):
 
         def small(i):
             rows = hq_np[i * SMALL_CALL_ROWS:(i + 1) * SMALL_CALL_ROWS]
-            check_rc(lib.b200knn_query(hx, ctypes.c_void_p(rows.ctypes.data), FT, SMALL_CALL_ROWS, d, k, 0,
-                                       ctypes.c_void_p(sc_i.ctypes.data), ctypes.c_void_p(sc_d.ctypes.data), None))
+            if world > 1:
+                exchange.query_host(ix, rows.ctypes.data, FT, SMALL_CALL_ROWS, k, sc_i.ctypes.data, sc_d.ctypes.data)
+            else:
+                check_rc(lib.b200knn_query(hx, ctypes.c_void_p(rows.ctypes.data), FT, SMALL_CALL_ROWS, d, k, 0,
+                                           ctypes.c_void_p(sc_i.ctypes.data), ctypes.c_void_p(sc_d.ctypes.data), None))
         for i in range(min(20, nsc)):
             small(i)
         barrier()
@@ -622,27 +565,30 @@ def run_b200(args):
         small_call = {"rows_per_call": SMALL_CALL_ROWS, "calls": nsc, "latency_ms_median": 1e3 * float(np.median(lat)),
                       "latency_ms_p95": 1e3 * float(np.percentile(lat, 95)), "calls_per_s": nsc / float(tl.item()),
                       "queries_per_s": nsc * SMALL_CALL_ROWS / float(tl.item()),
-                      "api": "b200knn_query, host rows, one call per %d rows, back to back (training_loop.py:374-403)%s" % (
-                          SMALL_CALL_ROWS, "" if world == 1 else "; per rank against its pool shard, no exchange")}
+                      "api": "%s, host rows, one call per %d rows, back to back (training_loop.py:374-403)" % (
+                          "b200knn_query" if world == 1 else "b200knn_exchange_query (collective: slice upload, broadcast, bound + list exchange)", SMALL_CALL_ROWS)}
     lib.b200knn_destroy(hx)
     if not self_knn and args.workload not in ("c5", "c5s") and (r1 - r0) * d * fbytes < 40e9:
         pool_np = pool.cpu().numpy()             # pageable, like the trainer's np.zeros + fill (training_loop.py:358-365)
-        ha = ctypes.c_void_p()
-        assert lib.b200knn_create(d, 1, ids, ctypes.byref(ha)) == 0
+        ha = DeviceKNN(d, local_rank)
         ts = []
         for _ in range(3):
-            check_rc(lib.b200knn_clear(ha))
+            ha.clear()
             barrier()
             t0 = time.perf_counter()
-            check_rc(lib.b200knn_add(ha, ctypes.c_void_p(pool_np.ctypes.data), FT, r1 - r0, d))
+            if world > 1:
+                exchange.add(ha, pool_np, index_base=r0)
+            else:
+                check_rc(lib.b200knn_add(ha._handle, ctypes.c_void_p(pool_np.ctypes.data), FT, r1 - r0, d))
             ts.append(time.perf_counter() - t0)
-        lib.b200knn_destroy(ha)
+        del ha
         del pool_np
         ta = torch.tensor([min(ts)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ta, op=dist.ReduceOp.MAX)
         add_s = {"value": float(ta.item()), "unit": "s", "rows_per_rank": r1 - r0, "bytes_per_rank": (r1 - r0) * d * fbytes,
-                 "api": "b200knn_add from pageable host memory (H2D through the pinned ring + column means + BF16 convert + norms), best of 3, max over ranks"}
+                 "api": "%s from pageable host memory (H2D through the pinned ring + column means + BF16 convert + norms), best of 3, max over ranks" % (
+                     "b200knn_add" if world == 1 else "b200knn_exchange_add (each rank its shard; column sums gathered over peer memory)")}
 
     # ---- self-check of the last device result against a float64 torch brute force on a query subsample ----
     nchk = min(units_per_step if self_knn else q, args.check_queries)
@@ -692,7 +638,7 @@ def run_b200(args):
         ci, cd = brute(queries[sel], pool, 0, r1 - r0)
         ci = torch.where(ci >= 0, ci + r0, ci)
         if world == 1:
-            check = agree(loc_i[sel], loc_d[sel], ci, cd)
+            check = agree(out_i[sel], out_d[sel], ci, cd)
         else:
             g_d = torch.empty(world * nchk, kk, device=dev, dtype=torch.float64)
             g_i = torch.empty(world * nchk, kk, device=dev, dtype=torch.int64)
@@ -731,7 +677,8 @@ def run_b200(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16 (tensor pass) + f64 (exact re-rank)", "data": "synthetic",
             "config": workload_config(args.workload),
-            "run": {"parallelism": ("pool row-sharded x%d, queries replicated, exchange=%s + k-way merge kernel" % (world, exchange_kind))
+            "run": {"parallelism": ("pool row-sharded x%d, queries replicated; b200knn_exchange_query*: bound exchange + globally pruned exact re-rank, "
+                                    "list all-gather by NVLink peer stores + k-way merge kernel (no collective library on the path)" % world)
                     if world > 1 else "single GPU",
                     "l2": "inputs exceed L2 (BF16 pool shard %.2f GB > 126 MB); no explicit flush" % ((r1 - r0) * d * 2 / 1e9),
                     "timing": "CUDA events on the launching stream, max over ranks"},
@@ -742,14 +689,17 @@ def run_b200(args):
                          "peak_source": peaks["source"] + ", burst figure", "ms_per_launch": dist_ms, "launches": st["distance_launches"],
                          "flops_per_launch": st["distance_flops"] / max(st["distance_launches"], 1), "traffic": traffic},
             "kernel_ms_per_step": {"convert": st["ms_convert"] / args.steps, "distance": st["ms_distance"] / args.steps,
-                                   "rerank": st["ms_rerank"] / args.steps, "second_pass": st["ms_scan"] / args.steps},
+                                   "rerank": st["ms_rerank"] / args.steps, "second_pass": st["ms_scan"] / args.steps,
+                                   "wait_for_peers": st["ms_wait"] / args.steps},
             "uncertified_per_step": st["uncertified"] / args.steps,
             "e2e": {"value": units_per_step / (e2e_ms / e2e_steps * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                     "h2d_bytes_per_step": (n + q) * d * fbytes if self_knn else q * d * fbytes,
                     "d2h_bytes_per_step": units_per_step * kk * 12,
+                    "h2d_bytes_per_rank_per_step": ((n + q) * d * fbytes if self_knn else (q * d * fbytes + world - 1) // world),
                     "api": "per feature set: b200knn_clear + b200knn_add (host rows) + b200knn_query_self (what ManifoldEstimator.__init__ does)" if self_knn else
-                           (("b200knn_query (host buffers; the call inclusivegan_b200.dci.DCI.query makes)" + ("" if world == 1 else " per rank + peer exchange + D2H of the merged result")) if not sliced else
-                            "per rank: H2D of a 1/N query slice from pinned host memory, NVLink all-gather of the slices, b200knn_query_device, peer exchange, D2H of the merged result")},
+                           ("b200knn_query (host buffers; the call inclusivegan_b200.dci.DCI.query makes)" if world == 1 else
+                            "b200knn_exchange_query (host buffers, collective): per chunk every rank uploads 1/N of the rows from pinned host memory, converts them, "
+                            "copy engines broadcast BF16 rows + norms and (behind the tensor pass) the original rows over NVLink; merged result copied to the host")},
             "add_s": add_s,
             "small_call": small_call,
             "gpu_launches": int(launches),
@@ -782,7 +732,6 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--check-queries", type=int, default=2048, help="queries of the last step checked against a float64 brute force")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU result exchange: NVLink peer-memory kernels (default) or NCCL all-gather")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

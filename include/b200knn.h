@@ -170,6 +170,35 @@ int b200knn_exchange_allgather_merge(b200knn_exchange *ex, const int32_t *d_idx,
                                      int32_t *d_out_idx, double *d_out_dist, void *stream);
 int b200knn_exchange_destroy(b200knn_exchange *ex);
 
+/* ---- the whole multi-GPU step behind the library (north_star: "queries are broadcast, each GPU keeps a
+ * local top-k, ... a k-way merge kernel produces the global result") ----------------------------------------------
+ * One rank per GPU (a process of a torchrun job, or one device of an in-process group); rank r holds pool rows
+ * [index_base, index_base + n) in a single-device handle `index`.  All calls below are COLLECTIVE: every rank makes the
+ * same sequence of calls with the same nq / k / flags.  Nothing but these kernels and the copy engines touches NVLink.
+ *   create_for_queries : as create, plus per-rank buffers for one pass of max_nq query rows of `dim` columns (bounds,
+ *                        BF16 rows + norms, original rows; double-buffered).  handle/connect as above; connect_local
+ *                        wires the exchanges of ONE process together (all[] in rank order) through plain peer access.
+ *   add / add_device   : b200knn_add / b200knn_add_device of this rank's shard, except that the centring vector is the
+ *                        GLOBAL column mean (the shards' column sums are gathered over peer memory), so BF16 query rows
+ *                        converted by one rank are valid on every rank.
+ *   query_device       : d_query = ALL nq query rows, resident on every rank.  Tensor pass against the local shard; the
+ *                        ranks exchange an upper bound on their k-th nearest distance per query, and the exact re-rank
+ *                        evaluates only candidates that survive the minimum of the bounds (1/world of the re-rank work
+ *                        per rank instead of all of it); exact local lists -> all-gather by peer stores -> k-way merge.
+ *                        d_out_*: [nq][kk] on every rank, kk = min(k, rows of the WHOLE pool).
+ *   query              : the same with HOST rows (every rank passes the same matrix): per chunk every rank uploads and
+ *                        converts only 1/world of the rows, the copy engines broadcast the BF16 rows + norms and, behind
+ *                        the tensor pass, the original rows; uploads of chunk i+1 overlap the compute of chunk i. */
+int b200knn_exchange_create_for_queries(int device, int rank, int world, int dim, int64_t max_nq, int max_kk, b200knn_exchange **out);
+int b200knn_exchange_connect_local(b200knn_exchange *ex, b200knn_exchange *const *all);
+int b200knn_exchange_add(b200knn_exchange *ex, b200knn_index *index, const void *data, int dtype, int64_t n, int64_t ld, int64_t index_base);
+int b200knn_exchange_add_device(b200knn_exchange *ex, b200knn_index *index, const void *d_data, int dtype, int64_t n, int64_t ld,
+                                int64_t index_base);
+int b200knn_exchange_query(b200knn_exchange *ex, b200knn_index *index, const void *query, int dtype, int64_t nq, int64_t ld, int k,
+                           unsigned flags, int32_t *out_idx, double *out_dist, int *out_kk);
+int b200knn_exchange_query_device(b200knn_exchange *ex, b200knn_index *index, const void *d_query, int dtype, int64_t nq, int64_t ld, int k,
+                                  unsigned flags, int32_t *d_out_idx, double *d_out_dist, int *out_kk);
+
 /* ---- introspection -------------------------------------------------------------------------- */
 
 typedef struct b200knn_stats {
@@ -184,6 +213,7 @@ typedef struct b200knn_stats {
     int64_t distance_launches;     /* launches of the tcgen05 distance kernel counted in ms_distance */
     double  distance_flops;        /* 2*nq*n*dim summed over those launches */
     int64_t exact_scanned;         /* query rows whose second-pass list overflowed: answered by the exact CUDA-core scan */
+    double  ms_wait;               /* row-sharded pools: time the stream spent waiting for the peers' flags (skew between ranks) */
 } b200knn_stats;
 
 /* profiling != 0: bracket every kernel with CUDA events on the launching stream; read with get_stats. */

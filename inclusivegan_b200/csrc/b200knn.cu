@@ -55,6 +55,8 @@ struct b200knn_index {
     }
 };
 
+#include "exchange_host.cuh"
+
 // =================================================================================================
 // C ABI
 // =================================================================================================
@@ -142,6 +144,9 @@ int b200knn_get_stats(b200knn_index *ix, b200knn_stats *out) {
         cudaSetDevice(s.device);
         cudaStreamSynchronize(s.stream);
         s.drain_events();
+        unsigned int unc = 0;      // counted on the device (the host never learns the per-pass count)
+        if (cudaMemcpy(&unc, s.scalars.p + 8, sizeof(unc), cudaMemcpyDeviceToHost) != cudaSuccess) cudaGetLastError();
+        s.stats.uncertified = unc;
         out->kernel_launches += s.stats.kernel_launches;
         out->queries = std::max(out->queries, s.stats.queries);
         out->uncertified += s.stats.uncertified;
@@ -150,6 +155,7 @@ int b200knn_get_stats(b200knn_index *ix, b200knn_stats *out) {
         out->ms_distance += s.stats.ms_distance;
         out->ms_rerank += s.stats.ms_rerank;
         out->ms_scan += s.stats.ms_scan;
+        out->ms_wait += s.stats.ms_wait;
         out->distance_launches += s.stats.distance_launches;
         out->distance_flops += s.stats.distance_flops;
     }
@@ -159,7 +165,7 @@ int b200knn_get_stats(b200knn_index *ix, b200knn_stats *out) {
 int b200knn_reset_stats(b200knn_index *ix) {
     if (!ix) return fail(B200KNN_EINVAL, "index is NULL");
     for (auto &s : ix->shards) {
-        if (s.ready) { cudaSetDevice(s.device); cudaStreamSynchronize(s.stream); s.drain_events(); }
+        if (s.ready) { cudaSetDevice(s.device); cudaStreamSynchronize(s.stream); s.drain_events(); cudaMemset(s.scalars.p + 8, 0, sizeof(unsigned int)); }
         s.stats = b200knn_stats{};
     }
     return B200KNN_OK;
@@ -301,41 +307,12 @@ int b200knn_merge_topk_device(const int32_t *d_idx, const double *d_dist, int n_
 }
 
 // ------------------------------------------------------------------------------------------------ NVLink exchange
-struct b200knn_exchange {
-    int device = 0, rank = 0, world = 1;
-    int64_t max_items = 0;
-    void *base = nullptr;                 // one cudaMalloc: [flags world*128 B][done counter 128 B][idx 2*world*max_items][dist 2*world*max_items]
-    size_t off_idx = 0, off_dist = 0, off_done = 0, bytes = 0;
-    void *peer_base[EXCH_MAX_WORLD] = {};
-    bool connected = false;
-    unsigned int step = 0;
-};
-
 int b200knn_exchange_create(int device, int rank, int world, int64_t max_nq, int max_kk, b200knn_exchange **out) {
-    if (!out) return fail(B200KNN_EINVAL, "out is NULL");
-    *out = nullptr;
-    if (world < 1 || world > EXCH_MAX_WORLD || rank < 0 || rank >= world || max_nq <= 0 || max_kk <= 0)
-        return fail(B200KNN_EINVAL, "bad rank/world/size (world <= %d)", EXCH_MAX_WORLD);
-    CU_TRY(cudaSetDevice(device));
-    b200knn_exchange *ex = new (std::nothrow) b200knn_exchange();
-    if (!ex) return fail(B200KNN_ENOMEM, "out of host memory");
-    ex->device = device;
-    ex->rank = rank;
-    ex->world = world;
-    ex->max_items = (max_nq * max_kk + 3) / 4 * 4;
-    ex->off_done = static_cast<size_t>(world) * 128;
-    ex->off_idx = ex->off_done + 128;
-    ex->off_dist = ex->off_idx + static_cast<size_t>(2) * world * ex->max_items * sizeof(int32_t);
-    ex->off_dist = (ex->off_dist + 255) / 256 * 256;
-    ex->bytes = ex->off_dist + static_cast<size_t>(2) * world * ex->max_items * sizeof(double);
-    cudaError_t e = cudaMalloc(&ex->base, ex->bytes);
-    if (e != cudaSuccess) { delete ex; return fail(B200KNN_ENOMEM, "cudaMalloc(%zu) for the exchange buffer failed: %s", ex->bytes, cudaGetErrorString(e)); }
-    cudaMemset(ex->base, 0, ex->off_idx);
-    cudaDeviceSynchronize();   // flags are zero before any peer can map the buffer and publish into it
-    ex->peer_base[rank] = ex->base;
-    if (world == 1) ex->connected = true;
-    *out = ex;
-    return B200KNN_OK;
+    return ex_create(device, rank, world, 0, max_nq, max_kk, out);
+}
+int b200knn_exchange_create_for_queries(int device, int rank, int world, int dim, int64_t max_nq, int max_kk, b200knn_exchange **out) {
+    if (dim <= 0) return fail(B200KNN_EINVAL, "dim must be positive (got %d)", dim);
+    return ex_create(device, rank, world, dim, max_nq, max_kk, out);
 }
 
 int b200knn_exchange_handle(b200knn_exchange *ex, void *out_bytes) {
@@ -357,6 +334,26 @@ int b200knn_exchange_connect(b200knn_exchange *ex, const void *all_handles) {
         std::memcpy(&h, static_cast<const char *>(all_handles) + static_cast<size_t>(p) * B200KNN_IPC_BYTES, sizeof(h));
         CU_TRY(cudaIpcOpenMemHandle(&ex->peer_base[p], h, cudaIpcMemLazyEnablePeerAccess));
     }
+    ex->ipc_mapped = true;
+    ex->connected = true;
+    return B200KNN_OK;
+}
+
+int b200knn_exchange_connect_local(b200knn_exchange *ex, b200knn_exchange *const *all) {
+    if (!ex || !all) return fail(B200KNN_EINVAL, "NULL argument");
+    CU_TRY(cudaSetDevice(ex->device));
+    for (int p = 0; p < ex->world; p++) {
+        if (p == ex->rank) continue;
+        if (!all[p] || all[p]->world != ex->world || all[p]->rank != p || all[p]->bytes != ex->bytes)
+            return fail(B200KNN_EINVAL, "exchange %d of the group does not match (same world, sizes and rank order required)", p);
+        if (all[p]->device != ex->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(all[p]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(B200KNN_ECUDA, "no peer access from device %d to device %d: %s", ex->device, all[p]->device, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        ex->peer_base[p] = all[p]->base;
+    }
     ex->connected = true;
     return B200KNN_OK;
 }
@@ -365,39 +362,79 @@ int b200knn_exchange_allgather_merge(b200knn_exchange *ex, const int32_t *d_idx,
                                      int32_t *d_out_idx, double *d_out_dist, void *stream) {
     if (!ex || !d_idx || !d_dist || !d_out_idx || !d_out_dist) return fail(B200KNN_EINVAL, "NULL argument");
     if (!ex->connected) return fail(B200KNN_ESTATE, "exchange is not connected to its peers");
-    const int64_t items = nq * kk;
-    if (items <= 0 || items > ex->max_items) return fail(B200KNN_EINVAL, "nq*kk = %lld exceeds the exchange capacity %lld", (long long)items, (long long)ex->max_items);
     CU_TRY(cudaSetDevice(ex->device));
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    ex->step++;
-    ExchPeers peers{};
-    for (int p = 0; p < ex->world; p++) {
-        char *b = static_cast<char *>(ex->peer_base[p]);
-        peers.flags[p] = reinterpret_cast<unsigned int *>(b);
-        peers.idx[p] = reinterpret_cast<int32_t *>(b + ex->off_idx);
-        peers.dist[p] = reinterpret_cast<double *>(b + ex->off_dist);
-    }
-    char *lb = static_cast<char *>(ex->base);
-    const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(64, (items + 255) / 256)));
-    publish_topk_kernel<<<blocks, 256, 0, st>>>(d_idx, d_dist, items, ex->max_items, ex->rank, ex->world, ex->step, peers,
-                                                reinterpret_cast<unsigned int *>(lb + ex->off_done));
-    CU_TRY(cudaGetLastError());
-    merge_wait_kernel<<<static_cast<unsigned>((nq + 127) / 128), 128, 0, st>>>(
-        reinterpret_cast<const int32_t *>(lb + ex->off_idx), reinterpret_cast<const double *>(lb + ex->off_dist),
-        reinterpret_cast<const unsigned int *>(lb), ex->world, ex->step, ex->max_items, nq, kk, d_out_idx, d_out_dist);
-    CU_TRY(cudaGetLastError());
-    return B200KNN_OK;
+    return ex_allgather_merge(ex, d_idx, d_dist, nq, kk, d_out_idx, d_out_dist, static_cast<cudaStream_t>(stream), nullptr, nullptr);
 }
 
 int b200knn_exchange_destroy(b200knn_exchange *ex) {
-    if (!ex) return B200KNN_OK;
-    cudaSetDevice(ex->device);
-    cudaDeviceSynchronize();
-    for (int p = 0; p < ex->world; p++)
-        if (p != ex->rank && ex->peer_base[p]) cudaIpcCloseMemHandle(ex->peer_base[p]);
-    if (ex->base) cudaFree(ex->base);
-    delete ex;
+    ex_destroy(ex);
     return B200KNN_OK;
+}
+
+static int ex_index_args(b200knn_exchange *ex, b200knn_index *ix, const char *what) {
+    if (!ex || !ix) return fail(B200KNN_EINVAL, "NULL argument");
+    if (ix->device_ids.size() > 1) return fail(B200KNN_EINVAL, "%s takes a single-device handle (one rank per GPU)", what);
+    TRY(ix->ensure_devices());
+    return ex_check_pair(ex, ix->shards[0], ix->dim, what);
+}
+
+int b200knn_exchange_add_device(b200knn_exchange *ex, b200knn_index *ix, const void *d_data, int dtype, int64_t n, int64_t ld, int64_t index_base) {
+    TRY(check_matrix_args(ix, d_data, dtype, n, ld, "data"));
+    TRY(ex_index_args(ex, ix, "b200knn_exchange_add_device"));
+    if (ix->n_total > 0) return fail(B200KNN_ESTATE, "index already holds %lld points; clear() it first", (long long)ix->n_total);
+    if (n <= 0) return fail(B200KNN_EINVAL, "every rank must hold at least one pool row");
+    Shard &s = ix->shards[0];
+    CU_TRY(cudaSetDevice(s.device));
+    TRY(s.attach_pool(d_data, false, dtype, n, ld, ix->dim, ix->kp, index_base));
+    TRY(ex_finish_add(ex, s, ix->dim, ix->kp));
+    ix->n_total = n;
+    return B200KNN_OK;
+}
+
+int b200knn_exchange_add(b200knn_exchange *ex, b200knn_index *ix, const void *data, int dtype, int64_t n, int64_t ld, int64_t index_base) {
+    TRY(check_matrix_args(ix, data, dtype, n, ld, "data"));
+    TRY(ex_index_args(ex, ix, "b200knn_exchange_add"));
+    if (ix->n_total > 0) return fail(B200KNN_ESTATE, "index already holds %lld points; clear() it first", (long long)ix->n_total);
+    if (n <= 0) return fail(B200KNN_EINVAL, "every rank must hold at least one pool row");
+    Shard &s = ix->shards[0];
+    CU_TRY(cudaSetDevice(s.device));
+    const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
+    void *d_rows = nullptr;
+    CU_TRY(cudaMalloc(&d_rows, static_cast<size_t>(n) * ix->dim * esz));
+    int rc = s.attach_pool(d_rows, true, dtype, n, ix->dim, ix->dim, ix->kp, index_base);      // the shard owns d_rows from here
+    if (rc == B200KNN_OK) rc = s.upload_rows(d_rows, static_cast<const char *>(data), n, ix->dim * esz, ld * esz, s.stream);
+    if (rc == B200KNN_OK) rc = ex_finish_add(ex, s, ix->dim, ix->kp);
+    if (rc != B200KNN_OK) {
+        const std::string msg = g_last_error;
+        s.clear_pool();
+        cudaGetLastError();
+        g_last_error = msg;
+        return rc;
+    }
+    ix->n_total = n;
+    return B200KNN_OK;
+}
+
+int b200knn_exchange_query_device(b200knn_exchange *ex, b200knn_index *ix, const void *d_query, int dtype, int64_t nq, int64_t ld, int k,
+                                  unsigned flags, int32_t *d_out_idx, double *d_out_dist, int *out_kk) {
+    TRY(check_matrix_args(ix, d_query, dtype, nq, ld, "query"));
+    TRY(ex_index_args(ex, ix, "b200knn_exchange_query_device"));
+    if (k <= 0) return fail(B200KNN_EINVAL, "k must be positive (got %d)", k);
+    if (ix->n_total <= 0 || ex->n_global <= 0) return fail(B200KNN_ESTATE, "query on an empty index (use b200knn_exchange_add*)");
+    if (nq > 0 && (!d_out_idx || !d_out_dist)) return fail(B200KNN_EINVAL, "output buffer is NULL");
+    if (nq == 0) { if (out_kk) *out_kk = static_cast<int>(std::min<int64_t>(k, ex->n_global)); return B200KNN_OK; }
+    return ex_query_device(ex, ix->shards[0], ix->dim, ix->kp, d_query, dtype, nq, ld, k, flags, d_out_idx, d_out_dist, out_kk);
+}
+
+int b200knn_exchange_query(b200knn_exchange *ex, b200knn_index *ix, const void *query, int dtype, int64_t nq, int64_t ld, int k, unsigned flags,
+                           int32_t *out_idx, double *out_dist, int *out_kk) {
+    TRY(check_matrix_args(ix, query, dtype, nq, ld, "query"));
+    TRY(ex_index_args(ex, ix, "b200knn_exchange_query"));
+    if (k <= 0) return fail(B200KNN_EINVAL, "k must be positive (got %d)", k);
+    if (ix->n_total <= 0 || ex->n_global <= 0) return fail(B200KNN_ESTATE, "query on an empty index (use b200knn_exchange_add*)");
+    if (nq > 0 && (!out_idx || !out_dist)) return fail(B200KNN_EINVAL, "output buffer is NULL");
+    if (nq == 0) { if (out_kk) *out_kk = static_cast<int>(std::min<int64_t>(k, ex->n_global)); return B200KNN_OK; }
+    return ex_query_host(ex, ix->shards[0], ix->dim, ix->kp, query, dtype, nq, ld, k, flags, out_idx, out_dist, out_kk);
 }
 
 int b200knn_query_device(b200knn_index *ix, const void *d_query, int dtype, int64_t nq, int64_t ld, int k, unsigned flags,
@@ -411,12 +448,17 @@ int b200knn_query_device(b200knn_index *ix, const void *d_query, int dtype, int6
     const int kk = static_cast<int>(std::min<int64_t>(k, s.n));
     if (out_kk) *out_kk = kk;
     const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
+    if (nq == 0) return B200KNN_OK;
+    TRY(s.begin_call(nq));
     for (int64_t q0 = 0; q0 < nq; q0 += QUERY_CHUNK) {
         const int64_t cq = std::min(QUERY_CHUNK, nq - q0);
         TRY(s.query_device(static_cast<const char *>(d_query) + static_cast<size_t>(q0) * ld * esz, dtype, cq, ld, ix->dim, ix->kp, k, flags,
-                           d_out_idx + q0 * kk, d_out_dist + q0 * kk));
+                           d_out_idx + q0 * kk, d_out_dist + q0 * kk, nullptr, static_cast<int>(q0)));
     }
-    return B200KNN_OK;
+    // one synchronisation per call: did any second-pass list overflow?  (then: exact scan of those queries)
+    TRY(s.enqueue_overflow_readback());
+    CU_TRY(cudaStreamSynchronize(s.stream));
+    return s.fix_overflow_device(d_query, dtype, ld, *s.h_count, ix->dim, kk, flags, d_out_idx, d_out_dist);
 }
 
 int b200knn_query_self(b200knn_index *ix, int k, unsigned flags, int32_t *out_idx, double *out_dist, int *out_kk) {
@@ -432,16 +474,26 @@ int b200knn_query_self(b200knn_index *ix, int k, unsigned flags, int32_t *out_id
     TRY(s.out_idx.ensure(static_cast<size_t>(s.n) * kk));
     TRY(s.out_dist.ensure(static_cast<size_t>(s.n) * kk));
     const size_t esz = s.x_dtype == B200KNN_F64 ? 8 : 4;
+    TRY(s.begin_call(s.n));
     for (int64_t q0 = 0; q0 < s.n; q0 += QUERY_CHUNK) {
         const int64_t cq = std::min(QUERY_CHUNK, s.n - q0);
         const QuerySide pre{s.x_bf.p + static_cast<size_t>(q0) * ix->kp, s.xnorm_bf.p + q0, s.x_err.p + q0};
         TRY(s.query_device(static_cast<const char *>(s.x_raw) + static_cast<size_t>(q0) * s.ld_x * esz, s.x_dtype, cq, s.ld_x, ix->dim, ix->kp, k,
-                           flags, s.out_idx.p + q0 * kk, s.out_dist.p + q0 * kk, &pre));
+                           flags, s.out_idx.p + q0 * kk, s.out_dist.p + q0 * kk, &pre, static_cast<int>(q0)));
     }
-    CU_TRY(cudaMemcpyAsync(out_idx, s.out_idx.p, static_cast<size_t>(s.n) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
-    CU_TRY(cudaMemcpyAsync(out_dist, s.out_dist.p, static_cast<size_t>(s.n) * kk * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    auto copy_out = [&]() -> int {
+        CU_TRY(cudaMemcpyAsync(out_idx, s.out_idx.p, static_cast<size_t>(s.n) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        CU_TRY(cudaMemcpyAsync(out_dist, s.out_dist.p, static_cast<size_t>(s.n) * kk * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        return B200KNN_OK;
+    };
+    TRY(copy_out());
+    TRY(s.enqueue_overflow_readback());
     CU_TRY(cudaStreamSynchronize(s.stream));
-    if (s.index_base != 0) { /* indices already carry index_base */ }
+    if (*s.h_count > 0) {      // rare: overflowed second-pass lists are answered by the exact scan, results copied again
+        TRY(s.fix_overflow_device(s.x_raw, s.x_dtype, s.ld_x, *s.h_count, ix->dim, kk, flags, s.out_idx.p, s.out_dist.p));
+        TRY(copy_out());
+        CU_TRY(cudaStreamSynchronize(s.stream));
+    }
     return B200KNN_OK;
 }
 
@@ -559,7 +611,7 @@ int b200knn_query_projected(b200knn_index *ix, const void *rows, int dtype, int6
     for (int64_t q0 = 0; q0 < nq; q0 += QUERY_CHUNK) {
         const int64_t cq = std::min(QUERY_CHUNK, nq - q0);
         TRY(project_host_rows(ix, s, static_cast<const char *>(rows) + static_cast<size_t>(q0) * ld * esz, dtype, cq, ld, ix->proj_rows.p));
-        TRY(s.query_device(ix->proj_rows.p, B200KNN_F64, cq, ix->dim, ix->dim, ix->kp, k, flags, s.out_idx.p, s.out_dist.p));
+        TRY(s.query_device_sync(ix->proj_rows.p, B200KNN_F64, cq, ix->dim, ix->dim, ix->kp, k, flags, s.out_idx.p, s.out_dist.p));
         CU_TRY(cudaMemcpyAsync(out_idx + q0 * kk, s.out_idx.p, static_cast<size_t>(cq) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         CU_TRY(cudaMemcpyAsync(out_dist + q0 * kk, s.out_dist.p, static_cast<size_t>(cq) * kk * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         CU_TRY(cudaStreamSynchronize(s.stream));
@@ -648,16 +700,43 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
         TRY(s.out_dist.ensure(static_cast<size_t>(nq) * kk));
         unsigned char *stage[2] = {s.q_stage.p, s.q_stage2.p};
         const char *src = static_cast<const char *>(query);
+        TRY(s.begin_call(nq));
+        auto copy_out = [&]() -> int {
+            CU_TRY(cudaMemcpyAsync(out_idx, s.out_idx.p, static_cast<size_t>(nq) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+            CU_TRY(cudaMemcpyAsync(out_dist, s.out_dist.p, static_cast<size_t>(nq) * kk * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+            return B200KNN_OK;
+        };
+        // after the call's single synchronisation: overflowed second-pass lists (rare) -> exact scan of those queries,
+        // their rows re-uploaded from the caller's buffer (the stage buffers have been recycled), results copied again
+        auto finish = [&](Shard &sh) -> int {
+            const int nov = *sh.h_count;
+            if (nov <= 0) return B200KNN_OK;
+            TRY(sh.fix_overflow_host(query, dtype, ld, nov, dim, kk, flags, sh.out_idx.p, sh.out_dist.p));
+            TRY(copy_out());
+            CU_TRY(cudaStreamSynchronize(sh.stream));
+            return B200KNN_OK;
+        };
         // The uploads run on their own host thread (a pageable source keeps that thread busy with memcpy) and their
         // own stream; this thread enqueues the compute.  uploaded / consumed count chunks; the CUDA events order the
         // streams, the counters order the host threads.
         if (nchunks == 1) {   // small calls (the trainer's 24-row loop): no helper thread, everything on one stream
             TRY(upload(s, stage[0], src, nq, s.stream));
-            TRY(s.query_device(stage[0], dtype, nq, dim, dim, ix->kp, k, flags, s.out_idx.p, s.out_dist.p));
-            CU_TRY(cudaMemcpyAsync(out_idx, s.out_idx.p, static_cast<size_t>(nq) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
-            CU_TRY(cudaMemcpyAsync(out_dist, s.out_dist.p, static_cast<size_t>(nq) * kk * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-            CU_TRY(cudaStreamSynchronize(s.stream));
-            return B200KNN_OK;
+            s.defer_second_pass = true;       // decided after the call's one synchronisation: usually there is nothing to do
+            const int rcq = s.query_device(stage[0], dtype, nq, dim, dim, ix->kp, k, flags, s.out_idx.p, s.out_dist.p);
+            s.defer_second_pass = false;
+            TRY(rcq);
+            TRY(copy_out());
+            TRY(s.enqueue_uncertified_readback());
+            TRY(s.enqueue_overflow_readback());
+            CU_TRY(cudaStreamSynchronize(s.stream));      // the only synchronisation of a small call
+            if (s.deferred.armed && s.h_count[1] > 0) {
+                TRY(s.run_deferred_second_pass());
+                TRY(copy_out());
+                TRY(s.enqueue_overflow_readback());
+                CU_TRY(cudaStreamSynchronize(s.stream));
+            }
+            s.deferred.armed = false;
+            return finish(s);
         }
         std::atomic<int64_t> uploaded{0}, consumed{0};
         std::atomic<int> up_rc{B200KNN_OK};
@@ -688,7 +767,7 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
             while (uploaded.load(std::memory_order_acquire) < c + 1) std::this_thread::yield();
             if (up_rc.load() != B200KNN_OK) break;
             if (cudaStreamWaitEvent(s.stream, s.ev_copied[b], 0) != cudaSuccess) { rc_main = fail(B200KNN_ECUDA, "cudaStreamWaitEvent failed"); break; }
-            rc_main = s.query_device(stage[b], dtype, cq, dim, dim, ix->kp, k, flags, s.out_idx.p + q0 * kk, s.out_dist.p + q0 * kk);
+            rc_main = s.query_device(stage[b], dtype, cq, dim, dim, ix->kp, k, flags, s.out_idx.p + q0 * kk, s.out_dist.p + q0 * kk, nullptr, static_cast<int>(q0));
             if (rc_main == B200KNN_OK && cudaEventRecord(s.ev_consumed[b], s.stream) != cudaSuccess) rc_main = fail(B200KNN_ECUDA, "cudaEventRecord failed");
             consumed.store(c + 1, std::memory_order_release);
         }
@@ -696,10 +775,10 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
         uploader.join();
         if (up_rc.load() != B200KNN_OK) return fail(up_rc.load(), "%s", up_err.c_str());
         if (rc_main != B200KNN_OK) return rc_main;
-        CU_TRY(cudaMemcpyAsync(out_idx, s.out_idx.p, static_cast<size_t>(nq) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
-        CU_TRY(cudaMemcpyAsync(out_dist, s.out_dist.p, static_cast<size_t>(nq) * kk * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        TRY(copy_out());
+        TRY(s.enqueue_overflow_readback());
         CU_TRY(cudaStreamSynchronize(s.stream));
-        return B200KNN_OK;
+        return finish(s);
     }
     // ---- multi-device handle: every chunk is uploaded ONCE (to shard 0, on its own host thread and stream, double
     // buffered) and broadcast to the other shards over NVLink; every shard answers on its own host thread (the
@@ -794,7 +873,7 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
             cudaSetDevice(s.device);
             if (cudaStreamWaitEvent(s.stream, s.ev_copied[b], 0) != cudaSuccess) rc = fail(B200KNN_ECUDA, "cudaStreamWaitEvent failed");
             unsigned char *qp = b ? s.q_stage2.p : s.q_stage.p;
-            if (rc == B200KNN_OK) rc = s.query_device(qp, dtype, cq, dim, dim, ix->kp, kk, flags, s.out_idx.p, s.out_dist.p);
+            if (rc == B200KNN_OK) rc = s.query_device_sync(qp, dtype, cq, dim, dim, ix->kp, kk, flags, s.out_idx.p, s.out_dist.p);
             if (rc == B200KNN_OK) {
                 const int32_t *src_i = s.out_idx.p;
                 const double *src_d = s.out_dist.p;

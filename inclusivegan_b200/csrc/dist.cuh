@@ -37,7 +37,39 @@ struct DistParams {
     int *coll_idx;           // [nq][coll_cap]
     int coll_cap;
     unsigned opt;            // tuning switches (A/B measurements): bit2 grid barrier between rounds
+    const int *nq_dev;       // non-null: the number of valid query rows is read from device memory (second pass: the
+                             // uncertified count of the first pass; the host does not synchronise to learn it)
 };
+
+// Device-side planner of the second (collection) pass: the schedule depends on the number of uncertified queries,
+// which only the device knows.  Same layout as Shard::plan_schedule: per round a group of up to `group` query tiles
+// x rc pool-tile streams, chunk-major (workers sharing a stream are neighbours).  One block; items: [max_rounds][workers].
+__global__ void __launch_bounds__(256)
+plan_collect_kernel(const int *__restrict__ count_dev, int qrows, int nt, int workers, int group, int max_rounds, int wide,
+                    WorkItem *__restrict__ items, unsigned int *__restrict__ total_uncertified) {
+    const int cnt = *count_dev;
+    if (threadIdx.x == 0 && cnt > 0) atomicAdd(total_uncertified, static_cast<unsigned int>(cnt));
+    const int qt = (cnt + qrows - 1) / qrows;
+    for (int i = threadIdx.x; i < max_rounds * workers; i += blockDim.x) {
+        const int round = i / workers, w = i % workers;
+        const int q0 = round * group;
+        const int gs = min(group, qt - q0);
+        WorkItem it{-1, 0, 0, 0};
+        if (gs > 0) {
+            int rc = max(1, min(workers / gs, nt));
+            if (wide && gs * rc > 255) rc = max(1, 255 / gs);
+            const int c = w / gs, g = w % gs;
+            if (c < rc) {
+                const int wide_bits = (wide && gs > 1 && rc > 1) ? static_cast<int>(static_cast<unsigned int>(gs * rc) << 24) : 0;
+                it.qtile = q0 + g;
+                it.t0 = static_cast<int>(static_cast<int64_t>(c) * nt / rc);
+                it.t1 = static_cast<int>(static_cast<int64_t>(c + 1) * nt / rc);
+                it.slot = c | (gs << 16) | wide_bits;
+            }
+        }
+        items[i] = it;
+    }
+}
 
 __device__ __forceinline__ WorkItem load_item(const DistParams &p, int round, int worker) {
     const int4 v = __ldg(reinterpret_cast<const int4 *>(p.items) + static_cast<int64_t>(round) * p.workers + worker);
@@ -245,6 +277,7 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // ===================== epilogue: 4 warps, thread <-> query row =====================
         const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
         const int row_in_tile = quarter * 32 + lane;
+        const int nq_eff = p.nq_dev ? min(__ldcg(p.nq_dev), p.nq) : p.nq;
         const int et = threadIdx.x - 64;               // 0..127
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -258,7 +291,7 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             float thr = -FLT_MAX;
             int local_hits = 0;
             if constexpr (COLLECT) {
-                if (q < p.nq) thr = __ldg(p.thr + q);
+                if (q < nq_eff) thr = __ldg(p.thr + q);
             } else {
 #pragma unroll
                 for (int i = 0; i < C; i++) { v[i] = FLT_MAX; id[i] = -1; }
@@ -326,7 +359,7 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 if (acc == 0) acc_phase ^= 1;
             }
             if constexpr (!COLLECT) {
-                if (q < p.nq) {
+                if (q < nq_eff) {
                     float *cs = p.cand_s + (static_cast<int64_t>(q) * p.max_slots + (w.slot & 0xffff)) * C;
                     int *ci = p.cand_i + (static_cast<int64_t>(q) * p.max_slots + (w.slot & 0xffff)) * C;
 #pragma unroll

@@ -1,6 +1,7 @@
 // Multi-GPU: k-way merge of per-shard results and the NVLink peer-memory exchange.
 #pragma once
 #include "common.cuh"
+#include "rerank.cuh"
 
 namespace b200 {
 // ------------------------------------------------------------------------------------------------
@@ -67,7 +68,8 @@ struct ExchPeers {
 
 __global__ void __launch_bounds__(256)
 publish_topk_kernel(const int32_t *__restrict__ idx, const double *__restrict__ dist, int64_t items, int64_t max_items, int rank,
-                    int world, unsigned int step, ExchPeers peers, unsigned int *__restrict__ done_counter) {
+                    int world, unsigned int step, ExchPeers peers, unsigned int *__restrict__ done_counter,
+                    const int *__restrict__ local_overflow /* nullable: count of queries this rank still owes an exact scan */) {
     const int64_t par = step & 1u;
     const int64_t slot = (par * world + rank) * max_items;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -88,26 +90,38 @@ publish_topk_kernel(const int32_t *__restrict__ idx, const double *__restrict__ 
     }
     __syncthreads();
     if (last && threadIdx.x < world) {
+        // word 1 of the flag line: "this rank has overflowed second-pass lists in this call" (every rank must learn it,
+        // so that all of them repeat the exchange after the exact scan); ordered before the flag by the release store
+        peers.flags[threadIdx.x][rank * 32 + 1] = local_overflow ? static_cast<unsigned int>(*local_overflow) : 0u;
         __threadfence_system();
-        *reinterpret_cast<volatile unsigned int *>(peers.flags[threadIdx.x] + rank * 32) = step;
+        st_release_sys(peers.flags[threadIdx.x] + rank * 32, step);
     }
 }
 
 __global__ void __launch_bounds__(128)
 merge_wait_kernel(const int32_t *__restrict__ gidx, const double *__restrict__ gdist, const unsigned int *__restrict__ flags,
                   int world, unsigned int step, int64_t max_items, int64_t nq, int kk, int32_t *__restrict__ out_idx,
-                  double *__restrict__ out_dist) {
+                  double *__restrict__ out_dist, unsigned int *__restrict__ global_overflow /* nullable: sum over ranks */) {
     if (threadIdx.x < world) {
         // system-scope acquire: pairs with the publisher's __threadfence_system() + flag store on another GPU
         const unsigned int *f = flags + threadIdx.x * 32;
         const uint64_t t0 = global_timer_ns();
         while (ld_acquire_sys(f) < step) {   // steps only grow; a peer one step ahead is fine
             __nanosleep(200);
-            if (global_timer_ns() - t0 > 20000000000ull) __trap();   // 20 s: a peer died
+            if (global_timer_ns() - t0 > 10000000000ull) {           // 10 s: a peer died
+                printf("[b200knn] merge wait timed out: rank %d shows %u, want %u\n", static_cast<int>(threadIdx.x), ld_acquire_sys(f), step);
+                assert(0 && "b200knn: merge flag wait timed out");
+                __trap();
+            }
         }
         __threadfence_system();
     }
     __syncthreads();
+    if (global_overflow && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned int t = 0;
+        for (int r = 0; r < world; r++) t += __ldcg(flags + r * 32 + 1);
+        *global_overflow = t;
+    }
     const int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (q >= nq) return;
     const int64_t base = static_cast<int64_t>(step & 1u) * world * max_items;
@@ -133,6 +147,127 @@ merge_wait_kernel(const int32_t *__restrict__ gidx, const double *__restrict__ g
         out_idx[q * kk + r] = (bg >= 0) ? bi : -1;
         out_dist[q * kk + r] = (bg >= 0) ? bd : DBL_MAX;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-sharded query protocol (b200knn_exchange_query*): flag lines, the bound exchange, broadcast plumbing.
+// Every rank owns one buffer (CUDA IPC / peer mapped into the others); a flag "line" is 128 bytes, one per
+// (kind, source rank); counters only grow, so a reader waits for `>= step`.
+// ------------------------------------------------------------------------------------------------
+struct PeerPtrs {
+    char *base[EXCH_MAX_WORLD];            // every rank's buffer as mapped into THIS process (own entry: the local buffer)
+};
+
+// raise flag line (kind offset `flag_off`, slot `rank`) to `step` in every rank's buffer; everything the stream did
+// before this kernel (copy-engine broadcasts, kernels) is ordered before the flag
+__global__ void __launch_bounds__(32)
+raise_flags_kernel(PeerPtrs peers, int world, size_t flag_off, int rank, unsigned int step) {
+    if (static_cast<int>(threadIdx.x) < world) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned int *>(peers.base[threadIdx.x] + flag_off) + rank * 32, step);
+    }
+}
+
+// hold the stream until every rank's flag line of this kind (in the LOCAL buffer) shows `step`
+__global__ void __launch_bounds__(32)
+wait_flags_kernel(const unsigned int *__restrict__ flags, int world, unsigned int step, int tag) {
+    wait_peer_flags(flags, world, step, tag);
+}
+
+// Upper bound on the distance of this shard's kk-th nearest row, per query, from the tensor-pass shortlists
+// (kk-th smallest score over the query's slots -> ErrModel::upper), stored straight into slot `rank` of EVERY rank's
+// bound buffer (peer stores over NVLink); the last block raises the step flag everywhere.  One warp per query.
+struct BoundParams {
+    const float *cand_s;           // [nq][max_slots][C]
+    const int *cand_i;
+    int max_slots, c;
+    const int *slots_per_qtile;
+    int qtile_rows;
+    int nq, kk;
+    RerankParams em;               // error-model inputs (qnorm_bf, q_err, pool maxima, kp)
+    PeerPtrs peers;
+    int world, rank;
+    size_t bounds_off;             // byte offset of the bound array [2][world][stride] in every buffer
+    size_t flag_off;
+    int64_t stride;
+    unsigned int step;
+    unsigned int *done_counter;
+};
+__global__ void __launch_bounds__(256)
+bound_publish_kernel(const BoundParams p) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int64_t par = p.step & 1u;
+    for (int q = blockIdx.x * wpb + (threadIdx.x >> 5); q < p.nq; q += gridDim.x * wpb) {
+        const int total = __ldg(p.slots_per_qtile + q / p.qtile_rows) * p.c;
+        const float *cs = p.cand_s + static_cast<int64_t>(q) * p.max_slots * p.c;
+        const int *ci = p.cand_i + static_cast<int64_t>(q) * p.max_slots * p.c;
+        // kk-th smallest valid score: kk rounds of "smallest score above the previous pick" (scores of distinct rows may
+        // tie: picks are ordered by (score, position))
+        float last_s = -FLT_MAX;
+        int last_pos = -1;
+        bool ok = true;
+        for (int r = 0; r < p.kk && ok; r++) {
+            float bs = FLT_MAX;
+            int bp = 0x7fffffff;
+            for (int i = lane; i < total; i += 32) {
+                if (ci[i] < 0) continue;
+                const float sc = cs[i];
+                const bool after = (sc > last_s) || (sc == last_s && i > last_pos);
+                if (after && (sc < bs || (sc == bs && i < bp))) { bs = sc; bp = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+                const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+                if (os < bs || (os == bs && op < bp)) { bs = os; bp = op; }
+            }
+            ok = bp != 0x7fffffff;
+            last_s = bs;
+            last_pos = bp;
+        }
+        float u = __int_as_float(0x7f800000);      // +inf: fewer than kk rows in this shard's shortlists
+        if (ok) {
+            const ErrModel em = make_err_model(p.em, q);
+            u = __double2float_ru(em.upper(static_cast<double>(last_s)) * (1.0 + 1e-7));
+        }
+        if (lane < p.world)
+            reinterpret_cast<float *>(p.peers.base[lane] + p.bounds_off)[(par * p.world + p.rank) * p.stride + q] = u;
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        last = (atomicAdd(p.done_counter, 1u) == gridDim.x - 1u);
+        if (last) *p.done_counter = 0u;
+    }
+    __syncthreads();
+    if (last && static_cast<int>(threadIdx.x) < p.world) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned int *>(p.peers.base[threadIdx.x] + p.flag_off) + p.rank * 32, p.step);
+    }
+}
+
+// Column sums of every shard -> global column means (the centring vector must be the SAME on every rank: a query
+// row converted by one rank is compared with pool rows converted by another).  sums: [world][dim + 1] doubles in the
+// local buffer (slot r written by rank r; last entry = its row count); ranks are summed in rank order.
+__global__ void __launch_bounds__(256)
+publish_colsum_kernel(const double *__restrict__ colsum, double rows, int dim, PeerPtrs peers, int world, int rank, size_t sums_off) {
+    for (int p = 0; p < world; p++) {
+        double *dst = reinterpret_cast<double *>(peers.base[p] + sums_off) + static_cast<int64_t>(rank) * (dim + 1);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= dim; i += gridDim.x * blockDim.x) dst[i] = (i < dim) ? colsum[i] : rows;
+    }
+}
+__global__ void __launch_bounds__(256)
+global_mean_kernel(const double *__restrict__ sums, int world, int dim, double *__restrict__ mean) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dim) return;
+    double t = 0.0, n = 0.0;
+    for (int r = 0; r < world; r++) {
+        t += __ldcg(sums + static_cast<int64_t>(r) * (dim + 1) + i);
+        n += __ldcg(sums + static_cast<int64_t>(r) * (dim + 1) + dim);
+    }
+    mean[i] = n > 0.0 ? t / n : 0.0;
 }
 
 }  // namespace b200

@@ -2,7 +2,9 @@
 // mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld) and cluster helpers.
 // Nothing here is portable: compile with -gencode arch=compute_100a,code=sm_100a.
 #pragma once
+#include <cassert>
 #include <cstdint>
+#include <cstdio>
 #include <cuda.h>   // CUtensorMap (types only; the driver entry point is resolved at run time)
 
 namespace b200 {
@@ -63,7 +65,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if ((++spins & 0x3ffu) == 0) {
             const uint64_t now = global_timer_ns();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ull) __trap();   // 4 s: no legitimate wait in this library is longer than ms
+            else if (now - t0 > 4000000000ull) {            // 4 s: no legitimate wait in this library is longer than ms
+                printf("[b200knn] mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+                assert(0 && "b200knn: mbarrier wait timed out");
+                __trap();
+            }
         }
     }
 }

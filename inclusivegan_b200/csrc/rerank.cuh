@@ -108,7 +108,39 @@ struct RerankParams {
     int *uncert_count;             // number of uncertified queries
     int *uncert_list;              // their row numbers
     float *uncert_thr;             // score threshold for the collection pass, per list slot
+    // Row-sharded pools (one rank per GPU): ext_bounds[r * ext_stride + q] is rank r's upper bound on the distance of
+    // its kk-th nearest row to query q (+inf if it has fewer than kk rows), written into this rank's buffer by the
+    // peers' bound_publish_kernel.  The global kk-th distance is at most their minimum, so a local candidate whose
+    // lower bound exceeds it cannot be in the global answer: only the global survivors are evaluated exactly, and the
+    // local list may hold fewer than kk entries (padded with (-1, DBL_MAX), which the merge skips).
+    const float *ext_bounds;       // nullptr: single shard
+    int ext_world;
+    int64_t ext_stride;
 };
+
+// wait (bounded) until every rank's flag shows `step`; executed by the first `world` threads of a block
+__device__ __forceinline__ void wait_peer_flags(const unsigned int *flags, int world, unsigned int step, int tag = 0) {
+    if (static_cast<int>(threadIdx.x) < world) {
+        const unsigned int *f = flags + threadIdx.x * 32;
+        const uint64_t t0 = global_timer_ns();
+        while (static_cast<int>(ld_acquire_sys(f) - step) < 0) {      // counters only grow; a peer that is ahead is fine
+            __nanosleep(200);
+            if (global_timer_ns() - t0 > 10000000000ull) {            // 10 s: a peer died
+                printf("[b200knn] flag wait timed out: kind %d, rank %d shows %u, want %u (block %d)\n", tag, static_cast<int>(threadIdx.x),
+                       ld_acquire_sys(f), step, blockIdx.x);
+                assert(0 && "b200knn: peer flag wait timed out");
+                __trap();
+            }
+        }
+        __threadfence_system();
+    }
+}
+__device__ __forceinline__ double ext_bound_of(const RerankParams &p, int q) {
+    double u = DBL_MAX;
+    if (p.ext_bounds)
+        for (int r = 0; r < p.ext_world; r++) u = fmin(u, static_cast<double>(__ldcg(p.ext_bounds + r * p.ext_stride + q)));
+    return u;
+}
 
 // Error model shared by the pruning rule, the certificate and the second-pass threshold.  With q~, x~ the BF16
 // roundings:  s~ + ||q~||^2 = ||q~ - x~||^2 up to fp32 accumulation error eps_acc, and
@@ -141,7 +173,7 @@ __device__ __forceinline__ ErrModel make_err_model(const RerankParams &p, int q)
 // and certify the answer (or queue the query for the second pass).  keysC: the C best-scored shortlist entries,
 // ascending by (score, row); d2s: their exact squared distances (DBL_MAX = pruned / empty).
 template <int C>
-__device__ __forceinline__ void rerank_finish(const RerankParams &p, int q, const unsigned long long *keys, const double *d2s, int lane) {
+__device__ __forceinline__ void rerank_finish(const RerankParams &p, int q, const unsigned long long *keys, const double *d2s, int lane, double u_ext) {
     // rank the exact distances by (d2, index); each lane owns candidates lane, lane + 32 (C <= 64)
     constexpr int H = (C + 31) / 32;
     double myd[H];
@@ -170,8 +202,9 @@ __device__ __forceinline__ void rerank_finish(const RerankParams &p, int q, cons
     for (int h = 0; h < H; h++) {
         const bool valid = (lane + 32 * h) < C;
         if (valid && rank[h] < p.kk) {
-            p.out_idx[static_cast<int64_t>(q) * p.kk + rank[h]] = static_cast<int32_t>(p.index_base + myi[h]);
-            p.out_dist[static_cast<int64_t>(q) * p.kk + rank[h]] = (p.flags & 1u) ? myd[h] : sqrt(myd[h]);
+            const bool real = myd[h] < DBL_MAX;      // pruned / empty entries rank last: (-1, DBL_MAX) = no entry
+            p.out_idx[static_cast<int64_t>(q) * p.kk + rank[h]] = real ? static_cast<int32_t>(p.index_base + myi[h]) : -1;
+            p.out_dist[static_cast<int64_t>(q) * p.kk + rank[h]] = !real ? DBL_MAX : ((p.flags & 1u) ? myd[h] : sqrt(myd[h]));
         }
         // k-th exact distance (rank kk-1), broadcast
         const unsigned mh = __ballot_sync(0xffffffffu, valid && rank[h] == p.kk - 1);
@@ -184,13 +217,13 @@ __device__ __forceinline__ void rerank_finish(const RerankParams &p, int q, cons
         bool certified = true;
         const unsigned long long kc = keys[C - 1];
         const ErrModel em = make_err_model(p, q);
-        const double dk = sqrt(dk2);
-        if (p.n > C && kc != ~0ull && mk != 0) {
+        // bound on the (global) kk-th distance: the kk-th exact local distance if there is one, the peers' bound otherwise
+        const bool have_dk = (mk != 0) && (dk2 < DBL_MAX);
+        const double dk = fmin(have_dk ? sqrt(dk2) : DBL_MAX, u_ext);
+        if (p.n > C && kc != ~0ull) {
             const double lb = em.lower(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(kc >> 32))));
-            certified = (lb > 0.0) && (dk < lb);
-        } else if (mk == 0) {
-            certified = (p.n <= C);
-        }
+            certified = (dk < DBL_MAX) && (lb > 0.0) && (dk < lb);
+        }                                           // else: every row of the shard is in the shortlist, nothing was dropped
         if (!certified) {
             // second pass collects every row with score <= thr: any x with d(q,x) <= dk has
             // ||q~ - x~|| <= dk + eta, i.e. s~ <= (dk + eta)^2 - ||q~||^2 + eps_acc.
@@ -206,7 +239,7 @@ __device__ __forceinline__ void rerank_finish(const RerankParams &p, int q, cons
 // is at most their maximum — a far tighter limit than the a-priori upper bound.  Scores are sorted, so the survivors
 // stay a prefix; returns its new length.
 __device__ __forceinline__ int tighten_survivors(const RerankParams &p, int q, const unsigned long long *keys, const double *d2s, int m,
-                                                 int *m_s, int warp, int lane) {
+                                                 int *m_s, int warp, int lane, double u_ext) {
     __syncthreads();                    // d2s[0..kk) were written by single threads, possibly without a barrier since
     if (warp == 0) {
         double mx = 0.0;
@@ -216,7 +249,7 @@ __device__ __forceinline__ int tighten_survivors(const RerankParams &p, int q, c
         int cnt = 0;
         if (mx < DBL_MAX) {
             const ErrModel em = make_err_model(p, q);
-            const double dk = sqrt(mx);
+            const double dk = fmin(sqrt(mx), u_ext);
             for (int i = p.kk + lane; i < m; i += 32)
                 cnt += (keys[i] != ~0ull && em.lower(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(keys[i] >> 32)))) <= dk) ? 1 : 0;
         } else {
@@ -268,16 +301,21 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
     }
     // Pruning: candidate c (ascending score) can be among the true top-kk only if its distance lower bound does not
     // exceed the kk-th smallest distance upper bound.  Scores are sorted, so the survivors are a prefix of length m.
+    const double u_ext = ext_bound_of(p, q);       // DBL_MAX on a single shard
     if (tid == 0) {
-        int m = min(C, p.kk);
-        if (keys[p.kk - 1] != ~0ull) {
-            const ErrModel em = make_err_model(p, q);
-            const double u = em.upper(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(keys[p.kk - 1] >> 32))));
+        const ErrModel em = make_err_model(p, q);
+        double u = u_ext;
+        if (keys[p.kk - 1] != ~0ull)
+            u = fmin(u, em.upper(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(keys[p.kk - 1] >> 32)))));
+        int m = 0;
+        if (u < DBL_MAX) {
+            // (single shard: the first kk entries always pass, their lower bounds are below the kk-th upper bound)
             while (m < C && keys[m] != ~0ull &&
                    em.lower(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(keys[m] >> 32)))) <= u) m++;
         } else {
-            m = C;
+            m = C;                                  // fewer than kk candidates anywhere: evaluate them all
         }
+        if (!p.ext_bounds) m = max(m, min(C, p.kk));
         m_s = m;
     }
     __syncthreads();
@@ -297,7 +335,7 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
         bool tightened = false;
         for (int c0 = 0; c0 < C; c0 += NG) {
             if (!tightened && c0 >= p.kk && c0 < m) {      // uniform across the block
-                m = tighten_survivors(p, q, keys, d2s, m, &m_s, warp, lane);
+                m = tighten_survivors(p, q, keys, d2s, m, &m_s, warp, lane, u_ext);
                 tightened = true;
             }
             const int c = c0 + grp;
@@ -316,7 +354,7 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
             }
             __syncthreads();
         }
-        if (warp == 0) rerank_finish<C>(p, q, keys, d2s, lane);
+        if (warp == 0) rerank_finish<C>(p, q, keys, d2s, lane, u_ext);
         return;
     }
     constexpr int RQ = 24;                      // dims per thread held in registers (128 threads x 24 = 3072)
@@ -325,7 +363,7 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
     __shared__ double partial[4];
     double qreg[RQ];
     const bool fits = p.dim <= RQ * nth;
-    if (fits && act) {
+    if (fits && act && m > 0) {     // (row-sharded pools: most queries have no survivor on most ranks — their row is never read)
         // raw loads first, conversions after: a float->double conversion placed right behind its load would make the
         // in-order warp wait for that load before issuing the next one (24 serialized DRAM round trips)
         TQ qraw[RQ];
@@ -340,7 +378,7 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
         for (int i = 0; i < RQ; i++) qreg[i] = static_cast<double>(qraw[i]);
     }
     for (int c = 0; c < C; c++) {
-        if (c == p.kk && c < m) m = tighten_survivors(p, q, keys, d2s, m, &m_s, warp, lane);   // uniform across the block
+        if (c == p.kk && c < m) m = tighten_survivors(p, q, keys, d2s, m, &m_s, warp, lane, u_ext);   // uniform across the block
         const unsigned long long key = keys[c];
         if (c >= m || key == ~0ull) {           // uniform across the block
             if (tid == 0) d2s[c] = DBL_MAX;
@@ -376,28 +414,34 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
         __syncthreads();
     }
     __syncthreads();
-    if (warp == 0) rerank_finish<C>(p, q, keys, d2s, lane);
+    if (warp == 0) rerank_finish<C>(p, q, keys, d2s, lane, u_ext);
 }
 
-// Second pass, part 2: exact re-rank of the collected lists.  One block per uncertified query (list slot).
-// Lists longer than the capacity (or shorter than kk) are handed to the exact scan via the overflow list.
+// Second pass, part 2: exact re-rank of the collected lists.  The number of lists is read from device memory (the
+// first pass's uncertified counter): the host enqueues the whole second pass without synchronising, and with a count
+// of zero every kernel of it returns at once.  Blocks loop over the lists.
+// Lists longer than the capacity (or, on a single shard, shorter than kk) are handed to the exact scan via the
+// overflow list, which the host inspects once, at the end of the call.
 constexpr int COLLECT_CAP = 1024;
 struct CollectRerankParams {
-    const int *uncert_list;      // [nun] query rows
-    const int *coll_count;       // [nun]
-    const int *coll_idx;         // [nun][COLLECT_CAP]
+    const int *count_dev;        // number of lists (uncertified queries of this pass)
+    const int *uncert_list;      // [count] query rows
+    const int *coll_count;       // [count]
+    const int *coll_idx;         // [count][COLLECT_CAP]
     int dim;
     int64_t ld_x, ld_q;
     int kk;
     int64_t index_base;
     unsigned flags;
+    int allow_short;             // row-sharded pool: a list holds every local row within the GLOBAL bound, possibly fewer than kk
+    int q_offset;                // first query row of this pass within the call (overflow entries are call-global rows)
     int32_t *out_idx;
     double *out_dist;
     int *overflow_count;
-    int *overflow_list;          // query rows that need the exact scan
+    int *overflow_list;          // call-global query rows that need the exact scan
 };
 
-template <typename TX, typename TQ, int NW>      // NW warps per block: 8 with many lists, 32 when only a few blocks would run
+template <typename TX, typename TQ, int NW>      // NW warps per block
 __global__ void __launch_bounds__(NW * 32)
 rerank_collect_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const CollectRerankParams p) {
     __shared__ double d2[COLLECT_CAP];
@@ -406,60 +450,65 @@ rerank_collect_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, con
     __shared__ int si[NW];
     __shared__ double last_d_s;
     __shared__ int last_i_s;
-    const int slot = blockIdx.x;
-    const int q = p.uncert_list[slot];
-    const int cnt = p.coll_count[slot];
-    if (cnt > COLLECT_CAP || cnt < p.kk) {
-        if (threadIdx.x == 0) {
-            const int o = atomicAdd(p.overflow_count, 1);
-            p.overflow_list[o] = q;
-        }
-        return;
-    }
+    const int nlists = *p.count_dev;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
-    for (int c = warp; c < cnt; c += NW) {       // one candidate per warp, canonical summation order
-        const int j = p.coll_idx[static_cast<int64_t>(slot) * COLLECT_CAP + c];
-        const double a0 = canon_d2_warp(x + static_cast<int64_t>(j) * p.ld_x, qr, p.dim, lane);
-        if (lane == 0) { d2[c] = a0; idx[c] = j; }
-    }
-    if (threadIdx.x == 0) { last_d_s = -1.0; last_i_s = -1; }
-    __syncthreads();
-    for (int r = 0; r < p.kk; r++) {
-        const double ld = last_d_s;
-        const int li = last_i_s;
-        double bd = DBL_MAX;
-        int bi = 0x7fffffff;
-        for (int c = threadIdx.x; c < cnt; c += blockDim.x) {
-            const double d = d2[c];
-            const int j = idx[c];
-            const bool after = (d > ld) || (d == ld && j > li);
-            if (after && (d < bd || (d == bd && j < bi))) { bd = d; bi = j; }
+    for (int slot = blockIdx.x; slot < nlists; slot += gridDim.x) {
+        const int q = p.uncert_list[slot];
+        const int cnt = p.coll_count[slot];
+        if (cnt > COLLECT_CAP || (cnt < p.kk && !p.allow_short)) {      // uniform across the block
+            if (threadIdx.x == 0) {
+                const int o = atomicAdd(p.overflow_count, 1);
+                p.overflow_list[o] = p.q_offset + q;
+            }
+            continue;
         }
+        const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
+        for (int c = warp; c < cnt; c += NW) {       // one candidate per warp, canonical summation order
+            const int j = p.coll_idx[static_cast<int64_t>(slot) * COLLECT_CAP + c];
+            const double a0 = canon_d2_warp(x + static_cast<int64_t>(j) * p.ld_x, qr, p.dim, lane);
+            if (lane == 0) { d2[c] = a0; idx[c] = j; }
+        }
+        if (threadIdx.x == 0) { last_d_s = -1.0; last_i_s = -1; }
+        __syncthreads();
+        for (int r = 0; r < p.kk; r++) {
+            const double ld = last_d_s;
+            const int li = last_i_s;
+            double bd = DBL_MAX;
+            int bi = 0x7fffffff;
+            for (int c = threadIdx.x; c < cnt; c += blockDim.x) {
+                const double d = d2[c];
+                const int j = idx[c];
+                const bool after = (d > ld) || (d == ld && j > li);
+                if (after && (d < bd || (d == bd && j < bi))) { bd = d; bi = j; }
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+            __syncthreads();
+            if (lane == 0) { sd[warp] = bd; si[warp] = bi; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int w = 1; w < NW; w++)
+                    if (sd[w] < bd || (sd[w] == bd && si[w] < bi)) { bd = sd[w]; bi = si[w]; }
+                last_d_s = bd;
+                last_i_s = bi;
+                const bool real = bi != 0x7fffffff;      // the list ran out (allow_short): (-1, DBL_MAX) = no entry
+                p.out_idx[static_cast<int64_t>(q) * p.kk + r] = real ? static_cast<int32_t>(p.index_base + bi) : -1;
+                p.out_dist[static_cast<int64_t>(q) * p.kk + r] = !real ? DBL_MAX : ((p.flags & 1u) ? bd : sqrt(bd));
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        if (lane == 0) { sd[warp] = bd; si[warp] = bi; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < NW; w++)
-                if (sd[w] < bd || (sd[w] == bd && si[w] < bi)) { bd = sd[w]; bi = si[w]; }
-            last_d_s = bd;
-            last_i_s = bi;
-            p.out_idx[static_cast<int64_t>(q) * p.kk + r] = static_cast<int32_t>(p.index_base + bi);
-            p.out_dist[static_cast<int64_t>(q) * p.kk + r] = (p.flags & 1u) ? bd : sqrt(bd);
-        }
-        __syncthreads();
     }
 }
 
 // gather BF16 query rows of the uncertified queries into a compact matrix for the collection pass
 __global__ void __launch_bounds__(256)
-gather_rows_kernel(const __nv_bfloat16 *__restrict__ src, const int *__restrict__ list, int nsel, int kp, __nv_bfloat16 *__restrict__ dst) {
+gather_rows_kernel(const __nv_bfloat16 *__restrict__ src, const int *__restrict__ list, const int *__restrict__ nsel_dev, int kp,
+                   __nv_bfloat16 *__restrict__ dst) {
+    const int nsel = *nsel_dev;        // device-side count: zero -> nothing to do
     const int vec_per_row = kp >> 3;   // kp is a multiple of 8: 16-byte chunks
     const int64_t total = static_cast<int64_t>(nsel) * vec_per_row;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {

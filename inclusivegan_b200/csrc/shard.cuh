@@ -5,7 +5,7 @@
 
 namespace {
 
-enum Kind { K_CONVERT = 0, K_DISTANCE = 1, K_RERANK = 2, K_SCAN = 3, K_NKINDS = 4 };
+enum Kind { K_CONVERT = 0, K_DISTANCE = 1, K_RERANK = 2, K_SCAN = 3, K_WAIT = 4, K_NKINDS = 5 };
 
 struct Shard {
     int device = 0;
@@ -24,8 +24,10 @@ struct Shard {
     DevBuf<double> col_mean;         // pool column means (subtracted from pool and queries before BF16 rounding)
     bool centered = false;
     bool use_centering = true;       // $B200KNN_CENTER=0 disables
-    DevBuf<unsigned int> scalars;    // [0] max ||x~||^2 bits, [1] max ||x - x~|| bits, [2],[3] same for queries (unused), [4] uncertified count,
-                                     // [5] overflow count, [6] grid-barrier counter of the distance kernel, [7] max (r_j + e_j) bits (ball membership)
+    DevBuf<unsigned int> scalars;    // [0] max ||x~||^2 bits, [1] max ||x - x~|| bits, [2],[3] same for queries (unused), [4] uncertified count of
+                                     // the pass in flight, [5] overflow count of the call, [6] grid-barrier counter of the distance kernel,
+                                     // [7] max (r_j + e_j) bits (ball membership), [8] uncertified queries since the last stats reset,
+                                     // [9] done counter of bound_publish_kernel
     CUtensorMap tmap_x;              // pool, 256-row box (1-CTA kernel)
     CUtensorMap tmap_x128;           // pool, 128-row box (each CTA of a pair stages half of the 256-row tile)
     int forced_cg = 0;               // $B200KNN_CTA_GROUP=1|2 pins the kernel flavour (A/B measurements)
@@ -88,11 +90,43 @@ struct Shard {
             CU_TRY(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
             CU_TRY(cudaEventCreateWithFlags(&ev_consumed[i], cudaEventDisableTiming));
         }
-        TRY(scalars.ensure(8));
-        CU_TRY(cudaMemsetAsync(scalars.p, 0, 8 * sizeof(unsigned int), stream));
-        CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&h_count), sizeof(int)));
+        TRY(scalars.ensure(16));
+        CU_TRY(cudaMemsetAsync(scalars.p, 0, 16 * sizeof(unsigned int), stream));
+        CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&h_count), 4 * sizeof(int)));
         TRY(set_kernel_attrs());
         ready = true;
+        return B200KNN_OK;
+    }
+    // CUDA loads kernels lazily, at their first launch, and loading may synchronise the whole context.  The multi-GPU
+    // protocol has kernels that spin until a peer (or another stream) has made progress: a first launch that lands behind
+    // such a kernel would wait for it, and everything submitted after that waits too — a deadlock.  So every kernel of the
+    // library is loaded here, once per process and device.
+    int preload_kernels() {
+        cudaFuncAttributes a;
+#define B200_PRELOAD(k) CU_TRY(cudaFuncGetAttributes(&a, k))
+#define B200_PRELOAD_T2(k) B200_PRELOAD((k<double, double>)); B200_PRELOAD((k<double, float>)); B200_PRELOAD((k<float, double>)); B200_PRELOAD((k<float, float>))
+#define B200_PRELOAD_RR(C) B200_PRELOAD((rerank_kernel<double, double, C, 128>)); B200_PRELOAD((rerank_kernel<double, float, C, 128>)); \
+        B200_PRELOAD((rerank_kernel<float, double, C, 128>)); B200_PRELOAD((rerank_kernel<float, float, C, 128>));                       \
+        B200_PRELOAD((rerank_kernel<double, double, C, 1024>)); B200_PRELOAD((rerank_kernel<double, float, C, 1024>));                   \
+        B200_PRELOAD((rerank_kernel<float, double, C, 1024>)); B200_PRELOAD((rerank_kernel<float, float, C, 1024>))
+        B200_PRELOAD(colsum_kernel<double>); B200_PRELOAD(colsum_kernel<float>); B200_PRELOAD(scale_kernel);
+        B200_PRELOAD(convert_norm_kernel<double>); B200_PRELOAD(convert_norm_kernel<float>);
+        B200_PRELOAD(plan_collect_kernel); B200_PRELOAD(gather_rows_kernel);
+        B200_PRELOAD((dist_topc_kernel<16, false, 1>)); B200_PRELOAD((dist_topc_kernel<32, false, 1>)); B200_PRELOAD((dist_topc_kernel<64, false, 1>));
+        B200_PRELOAD((dist_topc_kernel<16, false, 2>)); B200_PRELOAD((dist_topc_kernel<32, false, 2>)); B200_PRELOAD((dist_topc_kernel<64, false, 2>));
+        B200_PRELOAD((dist_topc_kernel<16, true, 1>)); B200_PRELOAD((dist_topc_kernel<16, true, 2>));
+        B200_PRELOAD_RR(16); B200_PRELOAD_RR(32); B200_PRELOAD_RR(64);
+        B200_PRELOAD((rerank_collect_kernel<double, double, 32>)); B200_PRELOAD((rerank_collect_kernel<double, float, 32>));
+        B200_PRELOAD((rerank_collect_kernel<float, double, 32>)); B200_PRELOAD((rerank_collect_kernel<float, float, 32>));
+        B200_PRELOAD_T2(scan_dist_kernel); B200_PRELOAD(scan_select_kernel); B200_PRELOAD(iota_kernel); B200_PRELOAD(scatter_sorted_kernel);
+        B200_PRELOAD(merge_topk_kernel); B200_PRELOAD(pad_topk_kernel); B200_PRELOAD(publish_topk_kernel); B200_PRELOAD(merge_wait_kernel);
+        B200_PRELOAD(raise_flags_kernel); B200_PRELOAD(wait_flags_kernel); B200_PRELOAD(bound_publish_kernel);
+        B200_PRELOAD(publish_colsum_kernel); B200_PRELOAD(global_mean_kernel);
+        B200_PRELOAD(ball_colterm_kernel); B200_PRELOAD(ball_rowthr_kernel); B200_PRELOAD_T2(ball_member_kernel); B200_PRELOAD(scan_member_kernel);
+        B200_PRELOAD(project_kernel<double>); B200_PRELOAD(project_kernel<float>);
+#undef B200_PRELOAD_RR
+#undef B200_PRELOAD_T2
+#undef B200_PRELOAD
         return B200KNN_OK;
     }
     int set_kernel_attrs() {
@@ -104,6 +138,7 @@ struct Shard {
         CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<16, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
         CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<64, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<1>::SMEM_BYTES));
         CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<64, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
+        TRY(preload_kernels());
         if (const char *o = getenv("B200KNN_OPT")) opt_flags = static_cast<unsigned>(atoi(o));
         if (const char *o = getenv("B200KNN_A_BUDGET_MB")) a_budget_mb = std::max(1, atoi(o));
         if (const char *o = getenv("B200KNN_SYNC_TILES")) sync_tiles = std::max(0, atoi(o));
@@ -159,6 +194,7 @@ struct Shard {
                 case K_CONVERT: stats.ms_convert += ms; break;
                 case K_DISTANCE: stats.ms_distance += ms; stats.distance_launches++; stats.distance_flops += e.flops; break;
                 case K_RERANK: stats.ms_rerank += ms; break;
+                case K_WAIT: stats.ms_wait += ms; break;
                 default: stats.ms_scan += ms; break;
             }
             cudaEventDestroy(e.a);
@@ -175,6 +211,7 @@ struct Shard {
         x_raw = nullptr;
         n = 0;
         sched1.key_nq = -1;
+        sched2.key_nq = -1;
         x_bf.release();
         xnorm_bf.release();
         x_err.release();
@@ -280,8 +317,10 @@ struct Shard {
     }
 
     // ------------------------------------------------------------------ kernels: convert
+    // on_stream: launch there instead of the compute stream (the row-sharded protocol converts a rank's slice of the
+    // query rows on its upload stream, ahead of the compute of earlier chunks); not profiled then
     int launch_convert(const void *src, int dtype, int64_t rows, int64_t ld, int dim, int kp, __nv_bfloat16 *dst, float *nbf,
-                       float *nex, unsigned int *maxbits /* [2] */) {
+                       float *nex, unsigned int *maxbits /* [2] */, cudaStream_t on_stream = nullptr) {
         const double *mu = centered ? col_mean.p : nullptr;
         if (rows <= 0) return B200KNN_OK;
         const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
@@ -289,14 +328,16 @@ struct Shard {
         const int warps_per_block = 8;
         int64_t blocks = (rows + warps_per_block - 1) / warps_per_block;
         blocks = std::min<int64_t>(blocks, static_cast<int64_t>(num_sms) * 8);
-        prof_begin(K_CONVERT);
+        cudaStream_t st = on_stream ? on_stream : stream;
+        if (on_stream) stats.kernel_launches++;
+        else prof_begin(K_CONVERT);
         if (dtype == B200KNN_F64)
-            convert_norm_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+            convert_norm_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
                 static_cast<const double *>(src), mu, rows, ld, dim, kp, vec, dst, nbf, nex, maxbits, maxbits + 1);
         else
-            convert_norm_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+            convert_norm_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
                 static_cast<const float *>(src), mu, rows, ld, dim, kp, vec, dst, nbf, nex, maxbits, maxbits + 1);
-        prof_end();
+        if (!on_stream) prof_end();
         CU_TRY(cudaGetLastError());
         return B200KNN_OK;
     }
@@ -449,8 +490,10 @@ struct Shard {
     }
 
     // ------------------------------------------------------------------ exact scan of a query subset
+    // query s of the subset reads row d_inlist[s] of d_query (nullptr: row s) and writes row d_outlist[s] of the outputs
+    // (nullptr: row s)
     template <typename TX, typename TQ>
-    int scan_typed(const TQ *d_query, int64_t ld_q, const int *d_qlist, int nsub, int dim, int kk, unsigned flags,
+    int scan_typed(const TQ *d_query, int64_t ld_q, const int *d_inlist, const int *d_outlist, int nsub, int dim, int kk, unsigned flags,
                    int32_t *d_out_idx, double *d_out_dist) {
         const TX *x = static_cast<const TX *>(x_raw);
         // sub-batches bounded to ~1.5 GB of scratch
@@ -460,16 +503,16 @@ struct Shard {
         TRY(scan_d2.ensure(static_cast<size_t>(batch) * n));
         for (int s0 = 0; s0 < nsub; s0 += batch) {
             const int ns = std::min(batch, nsub - s0);
-            // qlist == nullptr means rows s0..s0+ns of the query matrix
-            const TQ *qbase = d_qlist ? d_query : d_query + static_cast<int64_t>(s0) * ld_q;
-            const int *ql = d_qlist ? d_qlist + s0 : nullptr;
+            const TQ *qbase = d_inlist ? d_query : d_query + static_cast<int64_t>(s0) * ld_q;
+            const int *qin = d_inlist ? d_inlist + s0 : nullptr;
+            const int *ql = d_outlist ? d_outlist + s0 : nullptr;
             dim3 grid(static_cast<unsigned>((n + SCAN_TX - 1) / SCAN_TX), static_cast<unsigned>((ns + SCAN_TQ - 1) / SCAN_TQ));
             prof_begin(K_SCAN);
-            scan_dist_kernel<TX, TQ><<<grid, 256, 0, stream>>>(x, ld_x, static_cast<int>(n), qbase, ld_q, ql, ns, dim, scan_d2.p);
+            scan_dist_kernel<TX, TQ><<<grid, 256, 0, stream>>>(x, ld_x, static_cast<int>(n), qbase, ld_q, qin, ns, dim, scan_d2.p);
             prof_end();
             CU_TRY(cudaGetLastError());
-            int32_t *oi = d_qlist ? d_out_idx : d_out_idx + static_cast<int64_t>(s0) * kk;
-            double *od = d_qlist ? d_out_dist : d_out_dist + static_cast<int64_t>(s0) * kk;
+            int32_t *oi = d_outlist ? d_out_idx : d_out_idx + static_cast<int64_t>(s0) * kk;
+            double *od = d_outlist ? d_out_dist : d_out_dist + static_cast<int64_t>(s0) * kk;
             if (kk <= 32) {
                 prof_begin(K_SCAN);
                 scan_select_kernel<<<ns, 256, 0, stream>>>(scan_d2.p, static_cast<int>(n), ql, kk, index_base, flags, oi, od);
@@ -506,15 +549,15 @@ struct Shard {
         }
         return B200KNN_OK;
     }
-    int scan(const void *d_query, int q_dtype, int64_t ld_q, const int *d_qlist, int nsub, int dim, int kk, unsigned flags,
+    int scan(const void *d_query, int q_dtype, int64_t ld_q, const int *d_inlist, const int *d_outlist, int nsub, int dim, int kk, unsigned flags,
              int32_t *d_out_idx, double *d_out_dist) {
         if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
-            return scan_typed<double, double>(static_cast<const double *>(d_query), ld_q, d_qlist, nsub, dim, kk, flags, d_out_idx, d_out_dist);
+            return scan_typed<double, double>(static_cast<const double *>(d_query), ld_q, d_inlist, d_outlist, nsub, dim, kk, flags, d_out_idx, d_out_dist);
         if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
-            return scan_typed<double, float>(static_cast<const float *>(d_query), ld_q, d_qlist, nsub, dim, kk, flags, d_out_idx, d_out_dist);
+            return scan_typed<double, float>(static_cast<const float *>(d_query), ld_q, d_inlist, d_outlist, nsub, dim, kk, flags, d_out_idx, d_out_dist);
         if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
-            return scan_typed<float, double>(static_cast<const double *>(d_query), ld_q, d_qlist, nsub, dim, kk, flags, d_out_idx, d_out_dist);
-        return scan_typed<float, float>(static_cast<const float *>(d_query), ld_q, d_qlist, nsub, dim, kk, flags, d_out_idx, d_out_dist);
+            return scan_typed<float, double>(static_cast<const double *>(d_query), ld_q, d_inlist, d_outlist, nsub, dim, kk, flags, d_out_idx, d_out_dist);
+        return scan_typed<float, float>(static_cast<const float *>(d_query), ld_q, d_inlist, d_outlist, nsub, dim, kk, flags, d_out_idx, d_out_dist);
     }
 
     // ------------------------------------------------------------------ rerank dispatch
@@ -564,28 +607,133 @@ struct Shard {
         return dp;
     }
 
-    // Second pass for the `nun` queries the certificate rejected: the same tcgen05 GEMM, but the epilogue collects
-    // every pool row whose score is within the query's error margin; those short lists are re-ranked exactly.
-    // Lists that overflow go to the exact CUDA-core scan.
-    int second_pass(const void *d_query, int q_dtype, int64_t ld_q, int nun, int dim, int kp, int kk, unsigned flags,
-                    int32_t *d_out_idx, double *d_out_dist) {
-        TRY(q_bf2.ensure(static_cast<size_t>(nun) * kp));
-        TRY(coll_count.ensure(nun));
-        TRY(coll_idx.ensure(static_cast<size_t>(nun) * COLLECT_CAP));
-        TRY(overflow_list.ensure(nun));
+    // ------------------------------------------------------------------ call bracket: overflow bookkeeping
+    // A call (one C-ABI query) may span several passes (query chunks).  Queries whose second-pass list overflowed are
+    // appended to overflow_list as call-global rows; the host looks at the counter ONCE, after the last pass.
+    int begin_call(int64_t total_nq) {
+        CU_TRY(cudaSetDevice(device));
+        TRY(overflow_list.ensure(static_cast<size_t>(std::max<int64_t>(total_nq, 1))));
+        CU_TRY(cudaMemsetAsync(scalars.p + 5, 0, sizeof(unsigned int), stream));
+        return B200KNN_OK;
+    }
+    // enqueue the read-back of the overflow counter (the caller synchronises the stream, then reads *h_count)
+    int enqueue_overflow_readback() {
+        CU_TRY(cudaMemcpyAsync(h_count, scalars.p + 5, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        return B200KNN_OK;
+    }
+    // exact scan of the overflowed queries; d_query_all holds every query row of the call on the device
+    int fix_overflow_device(const void *d_query_all, int q_dtype, int64_t ld_q, int nov, int dim, int kk, unsigned flags,
+                            int32_t *d_out_idx_all, double *d_out_dist_all) {
+        if (nov <= 0) return B200KNN_OK;
+        stats.exact_scanned += nov;
+        return scan(d_query_all, q_dtype, ld_q, overflow_list.p, overflow_list.p, nov, dim, kk, flags, d_out_idx_all, d_out_dist_all);
+    }
+    // the same when the query rows live on the HOST (chunks already recycled on the device): re-upload just those rows
+    int fix_overflow_host(const void *h_query_all, int q_dtype, int64_t ld_q, int nov, int dim, int kk, unsigned flags,
+                          int32_t *d_out_idx_all, double *d_out_dist_all) {
+        if (nov <= 0) return B200KNN_OK;
+        stats.exact_scanned += nov;
+        const size_t esz = q_dtype == B200KNN_F64 ? 8 : 4;
+        std::vector<int> rows(nov);
+        CU_TRY(cudaMemcpyAsync(rows.data(), overflow_list.p, static_cast<size_t>(nov) * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        std::vector<unsigned char> packed(static_cast<size_t>(nov) * dim * esz);
+        for (int i = 0; i < nov; i++)
+            std::memcpy(packed.data() + static_cast<size_t>(i) * dim * esz,
+                        static_cast<const char *>(h_query_all) + static_cast<size_t>(rows[i]) * ld_q * esz, static_cast<size_t>(dim) * esz);
+        TRY(q_stage.ensure(packed.size()));
+        CU_TRY(cudaMemcpyAsync(q_stage.p, packed.data(), packed.size(), cudaMemcpyHostToDevice, stream));
+        CU_TRY(cudaStreamSynchronize(stream));          // `packed` is a stack-lifetime host buffer
+        return scan(q_stage.p, q_dtype, dim, nullptr, overflow_list.p, nov, dim, kk, flags, d_out_idx_all, d_out_dist_all);
+    }
+
+    // hook of the row-sharded query protocol (one rank per GPU, b200knn_exchange_query*): after the tensor pass every
+    // rank publishes an upper bound on its kk-th nearest distance per query; the re-rank prunes against their minimum
+    struct ShardHook {
+        PeerPtrs peers;
+        int world = 1, rank = 0;
+        size_t bounds_off = 0, bound_flag_off = 0;
+        int64_t bounds_stride = 0;
+        unsigned int bound_step = 0;
+        const char *local_base = nullptr;
+        int kk_global = 0;              // neighbours of the GLOBAL answer (a shard with fewer rows publishes +inf)
+        size_t raw_flag_off = 0;        // != 0: the re-rank also waits until every rank's slice of the original query rows has arrived
+        unsigned int raw_step = 0;
+        cudaEvent_t pre_rerank_event = nullptr;   // own upload stream: this rank's slice of the original rows has been sent
+    };
+    // a single-pass call may postpone the second pass until the host has seen the uncertified count at the call's one
+    // synchronisation (the common small call has none: nothing is launched for it)
+    struct Deferred {
+        bool armed = false;
+        const void *d_query = nullptr;
+        int q_dtype = 0, dim = 0, kp = 0, kk = 0, q_offset = 0;
+        int64_t ld_q = 0, nq = 0;
+        unsigned flags = 0;
+        int32_t *out_idx = nullptr;
+        double *out_dist = nullptr;
+    } deferred;
+    bool defer_second_pass = false;     // set by the caller around query_device()
+    int enqueue_uncertified_readback() {     // h_count[1] <- uncertified count of the last pass
+        CU_TRY(cudaMemcpyAsync(h_count + 1, scalars.p + 4, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        return B200KNN_OK;
+    }
+    int run_deferred_second_pass() {
+        if (!deferred.armed) return B200KNN_OK;
+        deferred.armed = false;
+        return enqueue_second_pass(deferred.d_query, deferred.q_dtype, deferred.ld_q, deferred.nq, deferred.dim, deferred.kp, deferred.kk,
+                                   deferred.flags, deferred.out_idx, deferred.out_dist, deferred.q_offset, false);
+    }
+
+    // Second pass for the queries the certificate rejected: the same tcgen05 GEMM, but the epilogue collects every pool
+    // row whose score is within the query's error margin; those short lists are re-ranked exactly.  Everything is
+    // enqueued without knowing how many such queries there are (the count lives in scalars[4]; the schedule is planned
+    // on the device): no host synchronisation, and with a count of zero every kernel returns at once.
+    // Lists that overflow go to the exact CUDA-core scan at the end of the call (fix_overflow_*).
+    Sched sched2;   // cached worst-case plan of the second pass (group size, kernel flavour)
+    CUtensorMap tmap_q2;
+    const void *tmap_q2_ptr = nullptr;
+    int64_t tmap_q2_rows = -1;
+    int tmap_q2_kp = -1;
+    int enqueue_second_pass(const void *d_query, int q_dtype, int64_t ld_q, int64_t nq_cap, int dim, int kp, int kk, unsigned flags,
+                            int32_t *d_out_idx, double *d_out_dist, int q_offset, bool allow_short) {
+        TRY(q_bf2.ensure(static_cast<size_t>(nq_cap) * kp));
+        TRY(coll_count.ensure(nq_cap));
+        TRY(coll_idx.ensure(static_cast<size_t>(nq_cap) * COLLECT_CAP));
+        if (!sched2.matches(nq_cap, n, kp, 1 << 20)) TRY(plan(sched2, nq_cap, kp, 1 << 20));
+        const Sched &s = sched2;
+        const int max_rounds = (s.qt + s.qg - 1) / s.qg;
+        TRY(sched_items2.ensure(static_cast<size_t>(max_rounds) * s.workers));
+        if (tmap_q2_ptr != q_bf2.p || tmap_q2_rows != nq_cap || tmap_q2_kp != kp) {
+            TRY(make_tmap(&tmap_q2, q_bf2.p, nq_cap, kp, BM));
+            tmap_q2_ptr = q_bf2.p; tmap_q2_rows = nq_cap; tmap_q2_kp = kp;
+        }
+        const int *count_dev = reinterpret_cast<const int *>(scalars.p + 4);
         prof_begin(K_SCAN);
-        gather_rows_kernel<<<std::min<int64_t>(num_sms * 4, (static_cast<int64_t>(nun) * (kp / 8) + 255) / 256), 256, 0, stream>>>(
-            cur_q_bf, uncert_list.p, nun, kp, q_bf2.p);
+        plan_collect_kernel<<<1, 256, 0, stream>>>(count_dev, BM * s.cg, s.nt, s.workers, s.qg, max_rounds, s.wide ? 1 : 0, sched_items2.p, scalars.p + 8);
+        prof_end();
+        prof_begin(K_SCAN);
+        gather_rows_kernel<<<num_sms * 4, 256, 0, stream>>>(cur_q_bf, uncert_list.p, count_dev, kp, q_bf2.p);
         prof_end();
         CU_TRY(cudaGetLastError());
-        CU_TRY(cudaMemsetAsync(coll_count.p, 0, static_cast<size_t>(nun) * sizeof(int), stream));
-        CU_TRY(cudaMemsetAsync(scalars.p + 5, 0, sizeof(unsigned int), stream));
-        CUtensorMap tmap_q2;
-        TRY(make_tmap(&tmap_q2, q_bf2.p, nun, kp, BM));
-        Sched s;
-        TRY(plan(s, nun, kp, 1 << 20));
-        TRY(upload_schedule(s, sched_items2, false, false));
-        DistParams dp = base_dist_params(nun, kp, s, sched_items2.p);
+        CU_TRY(cudaMemsetAsync(coll_count.p, 0, static_cast<size_t>(nq_cap) * sizeof(int), stream));
+        CU_TRY(cudaMemsetAsync(scalars.p + 6, 0, sizeof(unsigned int), stream));
+        TRY(stream_sync.ensure(static_cast<size_t>(max_rounds) * s.workers));
+        CU_TRY(cudaMemsetAsync(stream_sync.p, 0, static_cast<size_t>(max_rounds) * s.workers * sizeof(unsigned int), stream));
+        DistParams dp{};
+        dp.xnorm = xnorm_bf.p;
+        dp.n = static_cast<int>(n);
+        dp.nq = static_cast<int>(nq_cap);
+        dp.nq_dev = count_dev;
+        dp.num_kb = (kp + BK - 1) / BK;
+        dp.items = sched_items2.p;
+        dp.nrounds = max_rounds;
+        dp.workers = s.workers;
+        dp.round_counter = scalars.p + 6;
+        dp.stream_sync = stream_sync.p;
+        dp.sync_tiles = sync_tiles >= 0 ? sync_tiles : (s.wide ? 1 : std::max(1, 16 * 3072 / std::max(kp, 1)));
+        dp.sync_timeout_ns = 40000u * static_cast<unsigned>(std::max(1, kp / 3072));
+        dp.max_slots = s.workers;
+        dp.opt = opt_flags;
         dp.thr = uncert_thr.p;
         dp.coll_count = coll_count.p;
         dp.coll_idx = coll_idx.p;
@@ -595,6 +743,7 @@ struct Shard {
         prof_end();
         TRY(rc2);
         CollectRerankParams cp{};
+        cp.count_dev = count_dev;
         cp.uncert_list = uncert_list.p;
         cp.coll_count = coll_count.p;
         cp.coll_idx = coll_idx.p;
@@ -604,40 +753,32 @@ struct Shard {
         cp.kk = kk;
         cp.index_base = index_base;
         cp.flags = flags;
+        cp.allow_short = allow_short ? 1 : 0;
+        cp.q_offset = q_offset;
         cp.out_idx = d_out_idx;
         cp.out_dist = d_out_dist;
         cp.overflow_count = reinterpret_cast<int *>(scalars.p + 5);
         cp.overflow_list = overflow_list.p;
         prof_begin(K_SCAN);
-        // few lists (not more blocks than SMs): 32 warps per list, the sweep is latency-bound
-        auto launch = [&](auto tx, auto tq) {
-            using TX = decltype(tx);
-            using TQ = decltype(tq);
-            if (nun <= num_sms)
-                rerank_collect_kernel<TX, TQ, 32><<<nun, 1024, 0, stream>>>(static_cast<const TX *>(x_raw), static_cast<const TQ *>(d_query), cp);
-            else
-                rerank_collect_kernel<TX, TQ, 8><<<nun, 256, 0, stream>>>(static_cast<const TX *>(x_raw), static_cast<const TQ *>(d_query), cp);
-        };
-        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64) launch(double(), double());
-        else if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32) launch(double(), float());
-        else if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64) launch(float(), double());
-        else launch(float(), float());
+        const unsigned g = static_cast<unsigned>(std::min<int64_t>(nq_cap, static_cast<int64_t>(num_sms) * 2));
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
+            rerank_collect_kernel<double, double, 32><<<g, 1024, 0, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), cp);
+        else if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
+            rerank_collect_kernel<double, float, 32><<<g, 1024, 0, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), cp);
+        else if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
+            rerank_collect_kernel<float, double, 32><<<g, 1024, 0, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), cp);
+        else
+            rerank_collect_kernel<float, float, 32><<<g, 1024, 0, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), cp);
         prof_end();
         CU_TRY(cudaGetLastError());
-        CU_TRY(cudaMemcpyAsync(h_count, scalars.p + 5, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        CU_TRY(cudaStreamSynchronize(stream));
-        const int nov = *h_count;
-        if (nov > 0) {
-            stats.exact_scanned += nov;
-            TRY(scan(d_query, q_dtype, ld_q, overflow_list.p, nov, dim, kk, flags, d_out_idx, d_out_dist));
-        }
         return B200KNN_OK;
     }
 
     template <int C>
     int tensor_pass(const void *d_query, int q_dtype, int64_t nq, int64_t ld_q, int dim, int kp, int kk, unsigned flags,
-                    int32_t *d_out_idx, double *d_out_dist, const QuerySide *pre = nullptr) {
-        // query side: BF16 rows + norms, either converted now or (self-kNN) the pool's own, already converted by add()
+                    int32_t *d_out_idx, double *d_out_dist, const QuerySide *pre, int q_offset, const ShardHook *hook) {
+        // query side: BF16 rows + norms, either converted now or already there (self-kNN: the pool's own, converted by
+        // add(); row-sharded protocol: broadcast by the ranks that converted them)
         const __nv_bfloat16 *qb;
         const float *qn, *qe;
         if (pre) {
@@ -694,15 +835,60 @@ struct Shard {
         rp.uncert_count = reinterpret_cast<int *>(scalars.p + 4);
         rp.uncert_list = uncert_list.p;
         rp.uncert_thr = uncert_thr.p;
+        if (hook) {
+            // every rank tells every rank how close its kk-th candidate is at most (peer stores + step flag) ...
+            BoundParams bp{};
+            bp.cand_s = cand_s.p;
+            bp.cand_i = cand_i.p;
+            bp.max_slots = s.max_slots;
+            bp.c = C;
+            bp.slots_per_qtile = sched_slots.p;
+            bp.qtile_rows = BM * s.cg;
+            bp.nq = static_cast<int>(nq);
+            bp.kk = hook->kk_global > 0 ? hook->kk_global : kk;
+            bp.em = rp;
+            bp.peers = hook->peers;
+            bp.world = hook->world;
+            bp.rank = hook->rank;
+            bp.bounds_off = hook->bounds_off;
+            bp.flag_off = hook->bound_flag_off;
+            bp.stride = hook->bounds_stride;
+            bp.step = hook->bound_step;
+            bp.done_counter = scalars.p + 9;
+            prof_begin(K_RERANK);
+            bound_publish_kernel<<<static_cast<unsigned>(std::min<int64_t>(num_sms * 4, (nq + 7) / 8)), 256, 0, stream>>>(bp);
+            prof_end();
+            CU_TRY(cudaGetLastError());
+            // ... and the re-rank prunes against the minimum (it waits for the peers' flags itself)
+            rp.ext_bounds = reinterpret_cast<const float *>(hook->local_base + hook->bounds_off) +
+                            static_cast<int64_t>(hook->bound_step & 1u) * hook->world * hook->bounds_stride;
+            rp.ext_world = hook->world;
+            rp.ext_stride = hook->bounds_stride;
+            // dependencies on this device's OTHER stream are taken through events, never through spinning on a flag:
+            // a spinning kernel must only wait for work that is guaranteed to run without it finishing
+            if (hook->pre_rerank_event) CU_TRY(cudaStreamWaitEvent(stream, hook->pre_rerank_event, 0));
+            // the peers' bounds (and, with host rows, their slices of the original query rows) must have arrived: one
+            // tiny spinning block each, so that the skew between ranks is not billed to the re-rank
+            prof_begin(K_WAIT);
+            wait_flags_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<const unsigned int *>(hook->local_base + hook->bound_flag_off), hook->world,
+                                                    hook->bound_step, 101);
+            if (hook->raw_flag_off)
+                wait_flags_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<const unsigned int *>(hook->local_base + hook->raw_flag_off), hook->world,
+                                                        hook->raw_step, 103);
+            prof_end();
+            CU_TRY(cudaGetLastError());
+        }
         CU_TRY(cudaMemsetAsync(scalars.p + 4, 0, sizeof(unsigned int), stream));
         TRY(launch_rerank<C>(d_query, q_dtype, nq, rp));
+        deferred.armed = false;
         if (!(flags & B200KNN_FLAG_NO_CERTIFY)) {
-            CU_TRY(cudaMemcpyAsync(h_count, scalars.p + 4, sizeof(int), cudaMemcpyDeviceToHost, stream));
-            CU_TRY(cudaStreamSynchronize(stream));
-            const int nun = *h_count;
-            if (nun > 0) {
-                stats.uncertified += nun;
-                TRY(second_pass(d_query, q_dtype, ld_q, nun, dim, kp, kk, flags, d_out_idx, d_out_dist));
+            if (defer_second_pass && !hook) {
+                deferred.armed = true;
+                deferred.d_query = d_query; deferred.q_dtype = q_dtype; deferred.ld_q = ld_q; deferred.nq = nq; deferred.dim = dim;
+                deferred.kp = kp; deferred.kk = kk; deferred.flags = flags; deferred.out_idx = d_out_idx; deferred.out_dist = d_out_dist;
+                deferred.q_offset = q_offset;
+            } else {
+                TRY(enqueue_second_pass(d_query, q_dtype, ld_q, nq, dim, kp, kk, flags, d_out_idx, d_out_dist, q_offset, hook != nullptr));
             }
         }
         return B200KNN_OK;
@@ -810,18 +996,76 @@ struct Shard {
         return scan_members_typed<float, float>(static_cast<const float *>(d_query), ld_q, nsub, dim, d_out);
     }
 
-    // queries and outputs on this device; nq bounded by the caller's chunking
+    // Allocate every per-pass buffer a tensor pass over `nq` rows will touch (same formulas as tensor_pass /
+    // enqueue_second_pass).  Growing a buffer frees the old one, and cudaFree synchronises the context: inside the
+    // multi-GPU protocol that must not happen while flag-waiting kernels are in flight, so the protocol reserves for all
+    // its chunk sizes before it enqueues anything.
+    int reserve_pass(int64_t nq, int kp, int kk, bool pre) {
+        if (nq <= 0 || kk > 32) return B200KNN_OK;
+        const int C = kk <= 4 ? 16 : (kk <= 16 ? 32 : 64);
+        if (!pre) {
+            TRY(q_bf.ensure(static_cast<size_t>(nq) * kp));
+            TRY(qnorm_bf.ensure(nq));
+            TRY(q_err.ensure(nq));
+        }
+        Sched a;
+        TRY(plan(a, nq, kp, MAX_KEYS / C));
+        TRY(sched_items.ensure(a.items.size()));
+        TRY(sched_slots.ensure(a.slots_per_qtile.size()));
+        TRY(stream_sync.ensure(static_cast<size_t>(a.nrounds) * a.max_slots));
+        TRY(cand_s.ensure(static_cast<size_t>(nq) * a.max_slots * C));
+        TRY(cand_i.ensure(static_cast<size_t>(nq) * a.max_slots * C));
+        TRY(uncert_list.ensure(nq));
+        TRY(uncert_thr.ensure(nq));
+        TRY(q_bf2.ensure(static_cast<size_t>(nq) * kp));
+        TRY(coll_count.ensure(nq));
+        TRY(coll_idx.ensure(static_cast<size_t>(nq) * COLLECT_CAP));
+        Sched b;
+        TRY(plan(b, nq, kp, 1 << 20));
+        const int max_rounds = (b.qt + b.qg - 1) / b.qg;
+        TRY(sched_items2.ensure(static_cast<size_t>(max_rounds) * b.workers));
+        TRY(stream_sync.ensure(static_cast<size_t>(max_rounds) * b.workers));
+        return B200KNN_OK;
+    }
+    // the pinned ring of upload_rows (pageable sources): allocated before the protocol starts, for the same reason
+    int reserve_upload_ring() {
+        PinnedRing &rg = g_rings[device & 63];
+        std::lock_guard<std::mutex> lock(rg.mu);
+        for (int i = 0; i < PinnedRing::RING; i++) {
+            if (!rg.buf[i]) {
+                CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&rg.buf[i]), PinnedRing::BYTES));
+                CU_TRY(cudaEventCreateWithFlags(&rg.done[i], cudaEventDisableTiming));
+            }
+        }
+        return B200KNN_OK;
+    }
+
+    // a whole call in one pass, device-resident queries: bracket + pass + overflow fix-up; synchronises the stream once
+    int query_device_sync(const void *d_query, int q_dtype, int64_t nq, int64_t ld_q, int dim, int kp, int k, unsigned flags,
+                          int32_t *d_out_idx, double *d_out_dist, const QuerySide *pre = nullptr) {
+        if (nq <= 0) return B200KNN_OK;
+        const int kk = static_cast<int>(std::min<int64_t>(k, n));
+        TRY(begin_call(nq));
+        TRY(query_device(d_query, q_dtype, nq, ld_q, dim, kp, k, flags, d_out_idx, d_out_dist, pre, 0, nullptr));
+        TRY(enqueue_overflow_readback());
+        CU_TRY(cudaStreamSynchronize(stream));
+        return fix_overflow_device(d_query, q_dtype, ld_q, *h_count, dim, kk, flags, d_out_idx, d_out_dist);
+    }
+
+    // One pass: queries and outputs on this device; nq bounded by the caller's chunking.  Everything is ENQUEUED on the
+    // stream; the caller brackets the passes of a call with begin_call() ... enqueue_overflow_readback() + synchronise +
+    // fix_overflow_*().  q_offset: first row of this pass within the call.
     int query_device(const void *d_query, int q_dtype, int64_t nq, int64_t ld_q, int dim, int kp, int k, unsigned flags,
-                     int32_t *d_out_idx, double *d_out_dist, const QuerySide *pre = nullptr) {
+                     int32_t *d_out_idx, double *d_out_dist, const QuerySide *pre = nullptr, int q_offset = 0, const ShardHook *hook = nullptr) {
         if (nq <= 0) return B200KNN_OK;
         CU_TRY(cudaSetDevice(device));
         const int kk = static_cast<int>(std::min<int64_t>(k, n));
         stats.queries += nq;
         if (kk > 32 || (flags & B200KNN_FLAG_FORCE_SCAN))
-            return scan(d_query, q_dtype, ld_q, nullptr, static_cast<int>(nq), dim, kk, flags, d_out_idx, d_out_dist);
-        if (kk <= 4) return tensor_pass<16>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist, pre);
-        if (kk <= 16) return tensor_pass<32>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist, pre);
-        return tensor_pass<64>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist, pre);
+            return scan(d_query, q_dtype, ld_q, nullptr, nullptr, static_cast<int>(nq), dim, kk, flags, d_out_idx, d_out_dist);
+        if (kk <= 4) return tensor_pass<16>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist, pre, q_offset, hook);
+        if (kk <= 16) return tensor_pass<32>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist, pre, q_offset, hook);
+        return tensor_pass<64>(d_query, q_dtype, nq, ld_q, dim, kp, kk, flags, d_out_idx, d_out_dist, pre, q_offset, hook);
     }
 };
 

@@ -47,7 +47,7 @@ class Stats(ctypes.Structure):
     _fields_ = [("kernel_launches", ctypes.c_int64), ("queries", ctypes.c_int64), ("uncertified", ctypes.c_int64),
                 ("ms_convert", ctypes.c_double), ("ms_distance", ctypes.c_double), ("ms_rerank", ctypes.c_double),
                 ("ms_scan", ctypes.c_double), ("distance_launches", ctypes.c_int64), ("distance_flops", ctypes.c_double),
-                ("exact_scanned", ctypes.c_int64)]
+                ("exact_scanned", ctypes.c_int64), ("ms_wait", ctypes.c_double)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -104,6 +104,18 @@ def load_library(path=None):
     lib.b200knn_exchange_allgather_merge.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp]
     lib.b200knn_exchange_destroy.restype = i32
     lib.b200knn_exchange_destroy.argtypes = [vp]
+    lib.b200knn_exchange_create_for_queries.restype = i32
+    lib.b200knn_exchange_create_for_queries.argtypes = [i32, i32, i32, i32, i64, i32, ctypes.POINTER(vp)]
+    lib.b200knn_exchange_connect_local.restype = i32
+    lib.b200knn_exchange_connect_local.argtypes = [vp, ctypes.POINTER(vp)]
+    lib.b200knn_exchange_add.restype = i32
+    lib.b200knn_exchange_add.argtypes = [vp, vp, vp, i32, i64, i64, i64]
+    lib.b200knn_exchange_add_device.restype = i32
+    lib.b200knn_exchange_add_device.argtypes = [vp, vp, vp, i32, i64, i64, i64]
+    lib.b200knn_exchange_query.restype = i32
+    lib.b200knn_exchange_query.argtypes = [vp, vp, vp, i32, i64, i64, i32, u32, vp, vp, ctypes.POINTER(i32)]
+    lib.b200knn_exchange_query_device.restype = i32
+    lib.b200knn_exchange_query_device.argtypes = [vp, vp, vp, i32, i64, i64, i32, u32, vp, vp, ctypes.POINTER(i32)]
     lib.b200knn_ball_membership.restype = i32
     lib.b200knn_ball_membership.argtypes = [vp, vp, i32, i64, i64, vp, vp]
     lib.b200knn_set_projector.restype = i32
@@ -631,12 +643,55 @@ class PeerExchange(object):
 
     IPC_BYTES = 64
 
-    def __init__(self, device, rank, world, max_nq, max_kk):
+    def __init__(self, device, rank, world, max_nq, max_kk, dim=0):
+        """dim > 0: also allocate the query-side buffers of the collective protocol (add / query / query_device below)."""
         self._lib = load_library()
         h = ctypes.c_void_p()
-        _check(self._lib.b200knn_exchange_create(int(device), int(rank), int(world), int(max_nq), int(max_kk), ctypes.byref(h)))
+        if dim:
+            _check(self._lib.b200knn_exchange_create_for_queries(int(device), int(rank), int(world), int(dim), int(max_nq), int(max_kk),
+                                                                 ctypes.byref(h)))
+        else:
+            _check(self._lib.b200knn_exchange_create(int(device), int(rank), int(world), int(max_nq), int(max_kk), ctypes.byref(h)))
         self._h = h
         self.world = world
+
+    # ---- collective protocol: every rank makes the same calls (see include/b200knn.h) ----
+    def add_device(self, knn, data_ptr, dtype, n, ld=None, index_base=0):
+        _check(self._lib.b200knn_exchange_add_device(self._h, knn._handle, ctypes.c_void_p(data_ptr), int(dtype), int(n),
+                                                     int(ld if ld is not None else knn.dim), int(index_base)))
+
+    def add(self, knn, rows, index_base=0):
+        rows = np.ascontiguousarray(rows)
+        _check(self._lib.b200knn_exchange_add(self._h, knn._handle, rows.ctypes.data, F64 if rows.dtype == np.float64 else F32,
+                                              rows.shape[0], rows.shape[1], int(index_base)))
+
+    def query_device(self, knn, query_ptr, dtype, nq, k, out_idx_ptr, out_dist_ptr, ld=None, flags=0):
+        kk = ctypes.c_int(0)
+        _check(self._lib.b200knn_exchange_query_device(self._h, knn._handle, ctypes.c_void_p(query_ptr), int(dtype), int(nq),
+                                                       int(ld if ld is not None else knn.dim), int(k), int(flags),
+                                                       ctypes.c_void_p(out_idx_ptr), ctypes.c_void_p(out_dist_ptr), ctypes.byref(kk)))
+        return kk.value
+
+    def query_host(self, knn, query_ptr, dtype, nq, k, out_idx_ptr, out_dist_ptr, ld=None, flags=0):
+        kk = ctypes.c_int(0)
+        _check(self._lib.b200knn_exchange_query(self._h, knn._handle, ctypes.c_void_p(query_ptr), int(dtype), int(nq),
+                                                int(ld if ld is not None else knn.dim), int(k), int(flags),
+                                                ctypes.c_void_p(out_idx_ptr), ctypes.c_void_p(out_dist_ptr), ctypes.byref(kk)))
+        return kk.value
+
+    def query(self, knn, queries, k, flags=0):
+        """NumPy face of query_host: (idx int32 [Q, kk], dist float64 [Q, kk]) on every rank."""
+        q = np.ascontiguousarray(queries)
+        if q.dtype not in (np.float32, np.float64):
+            q = q.astype(np.float64)
+        idx = np.empty((q.shape[0], k), dtype=np.int32)
+        dist = np.empty((q.shape[0], k), dtype=np.float64)
+        kk = self.query_host(knn, q.ctypes.data, F64 if q.dtype == np.float64 else F32, q.shape[0], k, idx.ctypes.data, dist.ctypes.data,
+                             flags=flags)
+        if kk != k:          # fewer rows in the whole pool than k: the library wrote [Q][kk] densely
+            idx = idx.reshape(-1)[:q.shape[0] * kk].reshape(q.shape[0], kk)
+            dist = dist.reshape(-1)[:q.shape[0] * kk].reshape(q.shape[0], kk)
+        return idx, dist
 
     def handle(self):
         buf = ctypes.create_string_buffer(self.IPC_BYTES)

@@ -1,4 +1,8 @@
-"""NVLink peer-memory exchange (b200knn_exchange_*): two processes, two GPUs — skipped on a single-GPU box."""
+"""Multi-GPU path (b200knn_exchange_*): two processes, two GPUs — skipped on a single-GPU box.
+
+Covers the result exchange alone (all-gather by peer stores + merge) and the whole collective protocol: global
+centring at add, BF16 query slices broadcast over peer memory, bound exchange + globally pruned exact re-rank, padded
+short shards, the scan path, host- and device-resident queries, several chunks and calls in a row."""
 import os
 import socket
 import sys
@@ -18,18 +22,33 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_path):
+def _setup(rank, world, port):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
-    from inclusivegan_b200.dci import DeviceKNN, PeerExchange, F64
-    from inclusivegan_b200.sharding import shard_range
-    from oracle import knn_oracle as ko
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
-    dev = torch.device("cuda", rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)      # control plane only: hands the IPC handles round
+    return torch, dist, torch.device("cuda", rank)
+
+
+def _finish(dist, torch, rank, ok, msgs, out_path):
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    gathered = [None] * dist.get_world_size()
+    dist.all_gather_object(gathered, msgs)
+    if rank == 0:
+        with open(out_path, "w") as fh:
+            fh.write("ok" if int(flag.item()) == 1 else "mismatch: %r" % (gathered,))
+    dist.barrier()
+
+
+def _worker(rank, world, port, out_path):
+    torch, dist, dev = _setup(rank, world, port)
+    from inclusivegan_b200.dci import DeviceKNN, PeerExchange, F64
+    from inclusivegan_b200.sharding import shard_range
+    from oracle import knn_oracle as ko
     n, q, d, k = 20011, 700, 160, 5
     rng = np.random.default_rng(5)
     pool = rng.standard_normal((n, d)); queries = rng.standard_normal((q, d))
@@ -44,6 +63,7 @@ def _worker(rank, world, port, out_path):
     dist.all_gather_object(handles, ex.handle())
     ex.connect(handles)
     ok = True
+    msgs = []
     for step in range(5):                                            # several steps: flags and double buffering
         qq = ty if step % 2 == 0 else ty.flip(0).contiguous()
         ix.query(qq.data_ptr(), F64, q, k, li.data_ptr(), ld.data_ptr())
@@ -52,21 +72,125 @@ def _worker(rank, world, port, out_path):
         ri, rd = ko.exact_knn_c(pool, qq.cpu().numpy(), k)
         good, msg = ko.compare_knn(oi.cpu().numpy(), od.cpu().numpy(), ri, rd, pool, qq.cpu().numpy())
         ok = ok and good
-    flag = torch.tensor([1 if ok else 0])
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    if rank == 0:
-        with open(out_path, "w") as fh:
-            fh.write("ok" if int(flag.item()) == 1 else "mismatch")
-    dist.barrier()
+        if not good:
+            msgs.append(msg)
+    _finish(dist, torch, rank, ok, msgs, out_path)
     ex.close()
     dist.destroy_process_group()
 
 
-def test_peer_exchange_two_gpus(native_lib, tmp_path):
-    if native_lib.b200knn_device_count() < 2:
-        pytest.skip("needs >= 2 GPUs")
+def _protocol_worker(rank, world, port, out_path):
+    torch, dist, dev = _setup(rank, world, port)
+    from inclusivegan_b200.dci import DeviceKNN, PeerExchange, F32, F64, FLAG_FORCE_SCAN
+    from inclusivegan_b200.sharding import shard_range
+    from oracle import knn_oracle as ko
+    st = torch.cuda.current_stream().cuda_stream
+    ok = True
+    msgs = []
+
+    def connect(ex):
+        handles = [None] * world
+        dist.all_gather_object(handles, ex.handle())
+        ex.connect(handles)
+
+    def check(tag, gi, gd, pool, queries, k):
+        nonlocal ok
+        ri, rd = ko.exact_knn_c(pool, queries, k)
+        good, msg = ko.compare_knn(gi, gd, ri, rd, pool, queries)
+        if not good:
+            ok = False
+            msgs.append("%s: %s" % (tag, msg))
+
+    # ---- case 1: float64, several chunks per call (max_nq 1024), k = 1 and 5, host and device queries, a tie batch ----
+    n, q, d = 30011, 2600, 160
+    rng = np.random.default_rng(11)
+    pool = rng.standard_normal((n, d)) + 2.0          # a common offset: the GLOBAL mean must be the centring vector
+    a, b = shard_range(n, world, rank)
+    e0 = shard_range(n, world, 0)[1]
+    pool[e0] = pool[e0 - 1]                            # the same row on both sides of the shard boundary
+    queries = rng.standard_normal((q, d)) + 2.0
+    queries[:4] = pool[[e0 - 1, n - 1, 17, 9000]]      # exact hits, the first one duplicated on two shards
+    ix = DeviceKNN(d, rank); ix.set_stream(st)
+    ex = PeerExchange(rank, rank, world, 1024, 8, dim=d)
+    connect(ex)
+    ex.add(ix, pool[a:b], index_base=a)
+    for k in (1, 5):
+        for rep in range(2):
+            qq = queries if rep == 0 else np.ascontiguousarray(queries[::-1])
+            gi, gd = ex.query(ix, qq, k)
+            check("host f64 k=%d rep=%d" % (k, rep), gi, gd, pool, qq, k)
+    boundary = shard_range(n, world, 0)[1] - 1
+    gi, gd = ex.query(ix, queries[:4], 1)
+    if gi[0, 0] != boundary or gd[0, 0] != 0.0:          # ties across shards resolve to the LOWER index
+        ok = False
+        msgs.append("tie: got %d (d=%r), want %d" % (gi[0, 0], gd[0, 0], boundary))
+    tq = torch.from_numpy(queries).to(dev)
+    oi = torch.empty(q, 5, dtype=torch.int32, device=dev); od = torch.empty(q, 5, dtype=torch.float64, device=dev)
+    for rep in range(3):
+        ex.query_device(ix, tq.data_ptr(), F64, q, 5, oi.data_ptr(), od.data_ptr())
+        torch.cuda.synchronize()
+        check("device f64 rep=%d" % rep, oi.cpu().numpy(), od.cpu().numpy(), pool, queries, 5)
+    # scan path (k > 32) and forced scan through the same exchange
+    ex2 = PeerExchange(rank, rank, world, 1024, 40, dim=d)
+    connect(ex2)
+    ix2 = DeviceKNN(d, rank); ix2.set_stream(st)
+    ex2.add(ix2, pool[a:b], index_base=a)
+    gi, gd = ex2.query(ix2, queries[:300], 40)
+    check("host k=40 (scan)", gi, gd, pool, queries[:300], 40)
+    gi, gd = ex2.query(ix2, queries[:300], 3, flags=FLAG_FORCE_SCAN)
+    check("host forced scan", gi, gd, pool, queries[:300], 3)
+    gi, gd = ex2.query(ix2, queries[:300], 3)
+    check("host after scans", gi, gd, pool, queries[:300], 3)
+
+    # ---- case 2: float32 rows, clustered queries (tiny gaps), long rows ----
+    n, q, d = 9001, 1500, 1030
+    rng = np.random.default_rng(12)
+    pool = rng.standard_normal((n, d)).astype(np.float32)
+    queries = (pool[rng.integers(0, n, q)] + 0.05 * rng.standard_normal((q, d))).astype(np.float32)
+    a, b = shard_range(n, world, rank)
+    ix3 = DeviceKNN(d, rank); ix3.set_stream(st)
+    ex3 = PeerExchange(rank, rank, world, 4096, 10, dim=d)
+    connect(ex3)
+    ex3.add(ix3, pool[a:b], index_base=a)
+    gi, gd = ex3.query(ix3, queries, 10)
+    check("host f32 k=10", gi, gd, pool.astype(np.float64), queries.astype(np.float64), 10)
+
+    # ---- case 3: fewer rows per shard than k (lists padded with -1 before the merge) ----
+    n, q, d = 3 * world + 1, 300, 64
+    pool = rng.standard_normal((n, d)); queries = rng.standard_normal((q, d))
+    a, b = shard_range(n, world, rank)
+    ix4 = DeviceKNN(d, rank); ix4.set_stream(st)
+    ex4 = PeerExchange(rank, rank, world, 512, n + 1, dim=d)
+    connect(ex4)
+    ex4.add(ix4, pool[a:b], index_base=a)
+    gi, gd = ex4.query(ix4, queries, 6)
+    check("tiny pool k=6", gi, gd, pool, queries, 6)
+    gi, gd = ex4.query(ix4, queries, n + 1)      # k > N: min(k, N) = N columns
+    if gi.shape != (q, n):
+        ok = False
+        msgs.append("k > N: shape %r" % (gi.shape,))
+    else:
+        check("tiny pool k>N", gi, gd, pool, queries, n + 1)
+    _finish(dist, torch, rank, ok, msgs, out_path)
+    for e in (ex, ex2, ex3, ex4):
+        e.close()
+    dist.destroy_process_group()
+
+
+def _run(worker, native_lib, tmp_path, world=2):
+    if native_lib.b200knn_device_count() < world:
+        pytest.skip("needs >= %d GPUs" % world)
     import torch.multiprocessing as mp
     out = str(tmp_path / "result.txt")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(worker, args=(world, _free_port(), out), nprocs=world, join=True)
     with open(out) as fh:
         assert fh.read() == "ok"
+
+
+def test_peer_exchange_two_gpus(native_lib, tmp_path):
+    _run(_worker, native_lib, tmp_path)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_collective_protocol(native_lib, tmp_path, world):
+    _run(_protocol_worker, native_lib, tmp_path, world)

@@ -322,7 +322,7 @@ def test_multi_device_handle_if_available(lib):
 def test_full_size_config3_properties(lib):
     """BASELINE config 3 shape (300k pool x 30k queries, d=3072, k=1) through size-independent properties:
       * planted neighbours: query i = pool[p_i] + noise much smaller than any inter-point distance -> index p_i;
-      * a 48-query subsample checked against the oracle over the full pool;
+      * a 2048-query subsample (SURVEY 8c) of unplanted rows checked against the oracle over the full pool;
       * idempotence: the same call twice gives identical output."""
     from inclusivegan_b200 import DCI
     rng = np.random.default_rng(300)
@@ -330,17 +330,41 @@ def test_full_size_config3_properties(lib):
     x = rng.standard_normal((n, d), dtype=np.float32)
     plant = rng.integers(0, n, q)
     y = x[plant] + 0.05 * rng.standard_normal((q, d), dtype=np.float32)
-    y[:48] = rng.standard_normal((48, d), dtype=np.float32)             # unplanted rows for the oracle subsample
+    ns = 2048
+    y[:ns] = rng.standard_normal((ns, d), dtype=np.float32)             # unplanted rows for the oracle subsample
     db = DCI(d, 3, 15)
     db.add(x, num_levels=3, field_of_view=10, prop_to_retrieve=0.002)
     idx, dist = db.query_arrays(y, 1)
-    assert np.array_equal(idx[48:, 0], plant[48:].astype(np.int32))
-    assert np.all(np.abs(dist[48:, 0] - 0.05 * np.sqrt(d)) < 0.2)
-    ri, rd = ko.exact_knn_numpy(x, y[:48], 1)
-    ok, msg = ko.compare_knn(idx[:48], dist[:48], ri, rd)
+    assert np.array_equal(idx[ns:, 0], plant[ns:].astype(np.int32))
+    assert np.all(np.abs(dist[ns:, 0] - 0.05 * np.sqrt(d)) < 0.2)
+    ri, rd = ko.exact_knn_numpy(x, y[:ns], 1, qblock=1024)
+    ok, msg = ko.compare_knn(idx[:ns], dist[:ns], ri, rd)
     assert ok, msg
     idx2, dist2 = db.query_arrays(y, 1)
     assert np.array_equal(idx, idx2) and np.array_equal(dist, dist2)
+
+
+def test_full_size_config4_self_knn(lib):
+    """BASELINE config 4 shape: self-kNN radii (k = 3 + the row itself) of a 50k x 2048 non-negative float32 feature set
+    (relu(N(0,1)), Inception-pool-like), the call ManifoldEstimator makes (metrics/precision_recall.py:73-90).
+      * every row finds itself first, at distance 0;
+      * a 2048-row subsample checked against the oracle over the full set (squared distances, like the metric);
+      * the radii equal the oracle's k-th order statistic."""
+    from inclusivegan_b200 import DCI
+    rng = np.random.default_rng(400)
+    n, d, k = 50000, 2048, 4
+    x = np.maximum(rng.standard_normal((n, d), dtype=np.float32), 0)
+    db = DCI(d)
+    db.add(x)
+    idx, d2 = db.query_self_arrays(k, squared=True)
+    assert idx.shape == (n, k) and np.array_equal(idx[:, 0], np.arange(n, dtype=np.int32)) and np.all(d2[:, 0] == 0.0)
+    assert np.all(np.diff(d2, axis=1) >= 0)
+    sel = rng.choice(n, 2048, replace=False)
+    ri, rd = ko.exact_knn_numpy(x, x[sel], k, squared=True, qblock=1024)
+    ok, msg = ko.compare_knn(idx[sel], d2[sel], ri, rd)
+    assert ok, msg
+    st = db.stats()
+    assert st["exact_scanned"] == 0, st          # structured or not, this shape stays on the tensor path
 
 
 # ------------------------------------------------------------------------------------------------ certificate's error model
