@@ -536,7 +536,7 @@ def run_b200(args):
     # ---- secondaries: the trainer's 24-row calls, and add() from pageable host memory ----
     small_call = None
     add_s = None
-    if not self_knn and args.workload not in ("c5", "c5s"):
+    if not self_knn and args.workload not in ("c5", "c5s") and not args.no_secondaries:
         nsc = min(SMALL_CALLS, max(1, q // SMALL_CALL_ROWS))
         hq_np = hq.numpy()
         sc_i = np.empty((SMALL_CALL_ROWS, kk), dtype=np.int32)
@@ -568,7 +568,7 @@ def run_b200(args):
                       "api": "%s, host rows, one call per %d rows, back to back (training_loop.py:374-403)" % (
                           "b200knn_query" if world == 1 else "b200knn_exchange_query (collective: slice upload, broadcast, bound + list exchange)", SMALL_CALL_ROWS)}
     lib.b200knn_destroy(hx)
-    if not self_knn and args.workload not in ("c5", "c5s") and (r1 - r0) * d * fbytes < 40e9:
+    if not self_knn and args.workload not in ("c5", "c5s") and (r1 - r0) * d * fbytes < 40e9 and not args.no_secondaries:
         pool_np = pool.cpu().numpy()             # pageable, like the trainer's np.zeros + fill (training_loop.py:358-365)
         ha = DeviceKNN(d, local_rank)
         ts = []
@@ -731,6 +731,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondaries", action="store_true", help="skip add_s and small_call (development runs)")
     ap.add_argument("--check-queries", type=int, default=2048, help="queries of the last step checked against a float64 brute force")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -20,6 +20,10 @@ struct b200knn_index {
     int64_t proj_in_dim = 0;
     DevBuf<unsigned char> proj_stage;
     DevBuf<double> proj_rows;
+    // multi-device handles: one exchange per non-empty shard, wired together in-process (b200knn_exchange_connect_local);
+    // add() and query() then run the same collective protocol a torchrun job runs, one host thread per shard
+    std::vector<b200knn_exchange *> exch;
+    std::vector<int> exch_shards;       // shard index of rank i
 
     int ensure_devices() {
         if (devices_ready) return B200KNN_OK;
@@ -56,6 +60,69 @@ struct b200knn_index {
 };
 
 #include "exchange_host.cuh"
+
+namespace {
+
+void drop_group(b200knn_index *ix) {
+    for (auto *e : ix->exch) ex_destroy(e);
+    ix->exch.clear();
+    ix->exch_shards.clear();
+}
+
+// one exchange per non-empty shard, capacity bounded to ~2 GiB of original query rows per device
+int ensure_group(b200knn_index *ix, const std::vector<int> &active) {
+    if (ix->exch_shards == active && ix->exch.size() == active.size()) return B200KNN_OK;
+    drop_group(ix);
+    const int W = static_cast<int>(active.size());
+    int64_t max_nq = (int64_t(1) << 31) / (int64_t(2) * ix->dim * 8);
+    max_nq = std::max<int64_t>(BM * 2, std::min<int64_t>(QUERY_CHUNK, max_nq / (BM * 2) * (BM * 2)));
+    for (int i = 0; i < W; i++) {
+        b200knn_exchange *e = nullptr;
+        const int rc = ex_create(ix->shards[active[i]].device, i, W, ix->dim, max_nq, 32, &e);
+        if (rc != B200KNN_OK) { drop_group(ix); return rc; }
+        ix->exch.push_back(e);
+    }
+    ix->exch_shards = active;
+    for (int i = 0; i < W; i++) {
+        b200knn_exchange *e = ix->exch[i];
+        if (cudaSetDevice(e->device) != cudaSuccess) { drop_group(ix); return fail(B200KNN_ECUDA, "cudaSetDevice failed"); }
+        for (int p = 0; p < W; p++) {
+            if (p == i) continue;
+            if (ix->exch[p]->device != e->device) {
+                cudaError_t ce = cudaDeviceEnablePeerAccess(ix->exch[p]->device, 0);
+                if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) {
+                    drop_group(ix);
+                    return fail(B200KNN_ECUDA, "no peer access between devices %d and %d: %s", e->device, ix->exch[p]->device, cudaGetErrorString(ce));
+                }
+                cudaGetLastError();
+            }
+            e->peer_base[p] = ix->exch[p]->base;
+        }
+        e->connected = true;
+    }
+    return B200KNN_OK;
+}
+
+// run fn(rank) on one host thread per rank; the first failure (if any) is reported
+template <typename Fn>
+int for_each_rank(int W, Fn fn) {
+    std::vector<int> rcs(W, B200KNN_OK);
+    std::vector<std::string> errs(W);
+    std::vector<std::thread> th;
+    for (int i = 1; i < W; i++)
+        th.emplace_back([&, i]() {
+            rcs[i] = fn(i);
+            if (rcs[i] != B200KNN_OK) errs[i] = g_last_error;
+        });
+    rcs[0] = fn(0);
+    if (rcs[0] != B200KNN_OK) errs[0] = g_last_error;
+    for (auto &t : th) t.join();
+    for (int i = 0; i < W; i++)
+        if (rcs[i] != B200KNN_OK) return fail(rcs[i], "%s", errs[i].c_str());
+    return B200KNN_OK;
+}
+
+}  // namespace
 
 // =================================================================================================
 // C ABI
@@ -95,6 +162,7 @@ int b200knn_create(int dim, int n_devices, const int *device_ids, b200knn_index 
 
 int b200knn_destroy(b200knn_index *ix) {
     if (!ix) return B200KNN_OK;
+    drop_group(ix);
     for (auto &s : ix->shards) {
         if (s.ready) cudaSetDevice(s.device);
         s.destroy();
@@ -218,6 +286,7 @@ static int add_impl(b200knn_index *ix, const void *data, int dtype, int64_t n, i
         if (r != B200KNN_OK) return r;
         const char *src = static_cast<const char *>(data) + static_cast<size_t>(r0) * ld * esz;
         TRY(s.upload_rows(d_rows, src, rows, ix->dim * esz, ld * esz, s.stream));
+        if (G > 1) return B200KNN_OK;        // phase 2 below: the centring vector is the GLOBAL column mean
         TRY(s.compute_mean(d_rows, dtype, rows, ix->dim, ix->dim));
         TRY(s.launch_convert(d_rows, dtype, rows, ix->dim, ix->dim, ix->kp, s.x_bf.p, s.xnorm_bf.p, s.x_err.p, s.scalars.p));
         return B200KNN_OK;
@@ -239,6 +308,17 @@ static int add_impl(b200knn_index *ix, const void *data, int dtype, int64_t n, i
         for (auto &s : ix->shards) s.copy_threads = saved_threads;
         for (int g = 0; g < G; g++)
             if (rcs[g] != B200KNN_OK) return fail(rcs[g], "%s", errs[g].c_str());
+        // phase 2 (collective over the non-empty shards; every rank got this far): column sums gathered over peer memory ->
+        // global means -> BF16 convert + norms
+        std::vector<int> active;
+        for (int g = 0; g < G; g++)
+            if (ix->shards[g].n > 0) active.push_back(g);
+        TRY(ensure_group(ix, active));
+        TRY(for_each_rank(static_cast<int>(active.size()), [&](int i) -> int {
+            Shard &s = ix->shards[active[i]];
+            CU_TRY(cudaSetDevice(s.device));
+            return ex_finish_add(ix->exch[i], s, ix->dim, ix->kp);
+        }));
     }
     for (auto &s : ix->shards) {
         CU_TRY(cudaSetDevice(s.device));
@@ -787,6 +867,20 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
     for (int g = 0; g < G; g++)
         if (ix->shards[g].n > 0) active.push_back(g);
     const int lists = static_cast<int>(active.size());
+    if (kk <= 32 && ix->exch_shards == active && !ix->exch.empty()) {
+        // The collective protocol (exchange_host.cuh), one host thread per shard: every shard uploads 1/lists of every chunk,
+        // BF16 rows + norms and (behind the tensor pass) the original rows are broadcast over NVLink by the copy engines,
+        // bound exchange + globally pruned exact re-rank, list exchange + merge; no host synchronisation between chunks.
+        std::vector<ExCall> calls(lists);
+        for (int i = 0; i < lists; i++)       // phase 1: geometry + every allocation, nothing collective yet
+            TRY(ex_query_host_prepare(ix->exch[i], ix->shards[active[i]], ix->kp, nq, k, flags, calls[i]));
+        return for_each_rank(lists, [&](int i) -> int {
+            return ex_query_host_run(ix->exch[i], ix->shards[active[i]], dim, ix->kp, query, dtype, nq, ld, k, flags,
+                                     i == 0 ? out_idx : nullptr, i == 0 ? out_dist : nullptr, calls[i]);
+        });
+    }
+    // k > 32 (exact scan per shard, lists of any length): every chunk uploaded once and broadcast, per-shard answers
+    // gathered on shard 0 and merged there
     Shard &s0 = ix->shards[active[0]];
     // chunks of one query-tile group of the per-shard kernel (see the single-device path)
     std::vector<std::pair<int64_t, int64_t>> chunks;

@@ -41,33 +41,56 @@ struct DistParams {
                              // uncertified count of the first pass; the host does not synchronise to learn it)
 };
 
-// Device-side planner of the second (collection) pass: the schedule depends on the number of uncertified queries,
-// which only the device knows.  Same layout as Shard::plan_schedule: per round a group of up to `group` query tiles
-// x rc pool-tile streams, chunk-major (workers sharing a stream are neighbours).  One block; items: [max_rounds][workers].
+// Device-side planner of a pass (same layout as the host's Shard::plan_schedule, which sizes the buffers): per round a
+// group of up to `group` query tiles x rc pool-tile streams, chunk-major (workers sharing a stream are neighbours).
+// The schedule is WRITTEN on the device instead of copied to it: a host-to-device copy of a few KB would queue behind
+// the multi-megabyte query uploads on the same copy engine (measured: 1 ms stalls per chunk at 8 GPUs).  For the
+// second (collection) pass the number of query rows is only known on the device (count_dev).  The kernel also zeroes
+// every counter the pass uses, so a pass needs no memset either.  One block.
+struct PlanParams {
+    const int *count_dev;          // non-null: number of query rows (second pass: the uncertified count); else count
+    int count;
+    int qrows, nt, workers, group, max_rounds, wide, max_slots_cap;
+    WorkItem *items;               // [max_rounds][workers]
+    int *slots_per_qtile;          // nullable [ceil(count / qrows)]
+    unsigned int *round_counter;   // zeroed
+    unsigned int *stream_sync;     // [sync_entries] zeroed
+    int sync_entries;
+    unsigned int *zero_a;          // nullable single counters to zero (first pass: the uncertified count)
+    int *zero_list;                // nullable [zero_list_n] (second pass: coll_count)
+    int zero_list_n;
+    unsigned int *total_uncertified;   // nullable: += count (second pass accounting)
+};
 __global__ void __launch_bounds__(256)
-plan_collect_kernel(const int *__restrict__ count_dev, int qrows, int nt, int workers, int group, int max_rounds, int wide,
-                    WorkItem *__restrict__ items, unsigned int *__restrict__ total_uncertified) {
-    const int cnt = *count_dev;
-    if (threadIdx.x == 0 && cnt > 0) atomicAdd(total_uncertified, static_cast<unsigned int>(cnt));
-    const int qt = (cnt + qrows - 1) / qrows;
-    for (int i = threadIdx.x; i < max_rounds * workers; i += blockDim.x) {
-        const int round = i / workers, w = i % workers;
-        const int q0 = round * group;
-        const int gs = min(group, qt - q0);
+plan_pass_kernel(const PlanParams p) {
+    const int cnt = p.count_dev ? *p.count_dev : p.count;
+    if (threadIdx.x == 0) {
+        if (p.total_uncertified && cnt > 0) atomicAdd(p.total_uncertified, static_cast<unsigned int>(cnt));
+        *p.round_counter = 0u;
+        if (p.zero_a) *p.zero_a = 0u;
+    }
+    for (int i = threadIdx.x; i < p.sync_entries; i += blockDim.x) p.stream_sync[i] = 0u;
+    for (int i = threadIdx.x; i < p.zero_list_n; i += blockDim.x) p.zero_list[i] = 0;
+    const int qt = (cnt + p.qrows - 1) / p.qrows;
+    for (int i = threadIdx.x; i < p.max_rounds * p.workers; i += blockDim.x) {
+        const int round = i / p.workers, w = i % p.workers;
+        const int q0 = round * p.group;
+        const int gs = min(p.group, qt - q0);
         WorkItem it{-1, 0, 0, 0};
         if (gs > 0) {
-            int rc = max(1, min(workers / gs, nt));
-            if (wide && gs * rc > 255) rc = max(1, 255 / gs);
+            int rc = max(1, min(min(p.workers / gs, p.nt), p.max_slots_cap));
+            if (p.wide && gs * rc > 255) rc = max(1, 255 / gs);
             const int c = w / gs, g = w % gs;
             if (c < rc) {
-                const int wide_bits = (wide && gs > 1 && rc > 1) ? static_cast<int>(static_cast<unsigned int>(gs * rc) << 24) : 0;
+                const int wide_bits = (p.wide && gs > 1 && rc > 1) ? static_cast<int>(static_cast<unsigned int>(gs * rc) << 24) : 0;
                 it.qtile = q0 + g;
-                it.t0 = static_cast<int>(static_cast<int64_t>(c) * nt / rc);
-                it.t1 = static_cast<int>(static_cast<int64_t>(c + 1) * nt / rc);
+                it.t0 = static_cast<int>(static_cast<int64_t>(c) * p.nt / rc);
+                it.t1 = static_cast<int>(static_cast<int64_t>(c + 1) * p.nt / rc);
                 it.slot = c | (gs << 16) | wide_bits;
+                if (c == 0 && p.slots_per_qtile) p.slots_per_qtile[q0 + g] = rc;
             }
         }
-        items[i] = it;
+        p.items[i] = it;
     }
 }
 

@@ -174,6 +174,68 @@ wait_flags_kernel(const unsigned int *__restrict__ flags, int world, unsigned in
     wait_peer_flags(flags, world, step, tag);
 }
 
+// Broadcast of up to four byte ranges of THIS rank's buffer to the same offsets of every peer's buffer, by peer stores
+// from the SMs (NVLink).  The copy engines cannot do it without stalling: peer copies and host-to-device uploads share
+// an engine on this part, and a broadcast queued behind the next chunk's 30 MB upload arrives a millisecond late
+// (measured).  A few dozen blocks are enough to fill the links; they share the SMs with the persistent distance kernel
+// of the previous chunk for a fraction of a millisecond.  Every thread fences its stores at system scope before it
+// exits, so the flag kernel that follows in the stream publishes complete data.
+struct BcastSeg { size_t off; size_t bytes; };     // byte offset in the buffer, length (multiples of 4)
+struct BcastParams {
+    PeerPtrs peers;
+    int world, rank, nseg;
+    BcastSeg seg[4];
+};
+__global__ void __launch_bounds__(512)
+broadcast_segments_kernel(const BcastParams p) {
+    const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const char *src = p.peers.base[p.rank];
+    for (int sgi = 0; sgi < p.nseg; sgi++) {
+        const size_t off = p.seg[sgi].off, bytes = p.seg[sgi].bytes;
+        if (((off | bytes) & 15u) == 0) {
+            const size_t n = bytes >> 4;
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(src + off);
+            for (size_t i = tid; i < n; i += 4 * nthreads) {      // four 16-byte loads in flight per thread, each stored world-1 times
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (i + u * nthreads < n) v[u] = __ldcs(s4 + i + u * nthreads);
+                for (int r = 0; r < p.world; r++) {
+                    if (r == p.rank) continue;
+                    uint4 *d4 = reinterpret_cast<uint4 *>(p.peers.base[r] + off);
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (i + u * nthreads < n) d4[i + u * nthreads] = v[u];
+                }
+            }
+        } else {
+            const size_t n = bytes >> 2;
+            const uint32_t *s1 = reinterpret_cast<const uint32_t *>(src + off);
+            for (size_t i = tid; i < n; i += nthreads) {
+                const uint32_t v = s1[i];
+                for (int r = 0; r < p.world; r++)
+                    if (r != p.rank) reinterpret_cast<uint32_t *>(p.peers.base[r] + off)[i] = v;
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+// Rare path (k > 32 / forced scan with host-resident queries): the exact scan wants the whole chunk's original rows in
+// local memory — pull the other ranks' slices over NVLink (peer loads, 16-byte units when the rows allow it).
+__global__ void __launch_bounds__(256)
+pull_rows_kernel(QueryPull qp, int rank, int64_t rows, size_t row_bytes, char *__restrict__ dst) {
+    const size_t units = row_bytes >> 2;
+    const size_t total = static_cast<size_t>(rows) * units;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int q = static_cast<int>(i / units);
+        const int owner = q / qp.slice_rows;
+        if (owner == rank) continue;
+        reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(qp.base[owner] + qp.off)[i];
+    }
+}
+
 // Upper bound on the distance of this shard's kk-th nearest row, per query, from the tensor-pass shortlists
 // (kk-th smallest score over the query's slots -> ErrModel::upper), stored straight into slot `rank` of EVERY rank's
 // bound buffer (peer stores over NVLink); the last block raises the step flag everywhere.  One warp per query.
@@ -192,6 +254,7 @@ struct BoundParams {
     int64_t stride;
     unsigned int step;
     unsigned int *done_counter;
+    float *min_score;              // [nq] local: the smallest shortlist score of the query (the re-rank's early exit reads it)
 };
 __global__ void __launch_bounds__(256)
 bound_publish_kernel(const BoundParams p) {
@@ -204,7 +267,7 @@ bound_publish_kernel(const BoundParams p) {
         const int *ci = p.cand_i + static_cast<int64_t>(q) * p.max_slots * p.c;
         // kk-th smallest valid score: kk rounds of "smallest score above the previous pick" (scores of distinct rows may
         // tie: picks are ordered by (score, position))
-        float last_s = -FLT_MAX;
+        float last_s = -FLT_MAX, first_s = FLT_MAX;
         int last_pos = -1;
         bool ok = true;
         for (int r = 0; r < p.kk && ok; r++) {
@@ -225,7 +288,9 @@ bound_publish_kernel(const BoundParams p) {
             ok = bp != 0x7fffffff;
             last_s = bs;
             last_pos = bp;
+            if (r == 0) first_s = bs;          // FLT_MAX when the query has no candidate at all
         }
+        if (lane == 0) p.min_score[q] = first_s;
         float u = __int_as_float(0x7f800000);      // +inf: fewer than kk rows in this shard's shortlists
         if (ok) {
             const ErrModel em = make_err_model(p.em, q);

@@ -6,17 +6,17 @@
 //   add     every rank sums the columns of its shard, stores the sums into every rank's buffer and raises a flag; the
 //           global column means (the centring vector MUST be the same everywhere: a query row converted by one rank is
 //           compared with pool rows converted by another) follow from the gathered sums in rank order.
-//   query   per chunk of query rows: every rank uploads and converts 1/world of the rows, copy engines broadcast the
-//           BF16 rows + norms (needed before the tensor pass) and then the original rows (needed only by the exact
-//           re-rank, so their broadcast hides behind the tensor pass) over NVLink; tensor pass on all rows against the
-//           local shard; every rank publishes an upper bound on its k-th nearest distance per query; the exact re-rank
-//           evaluates only candidates that survive the minimum of those bounds (the replicated re-rank of round 1 becomes
-//           1/world of it per rank); the exact local lists are exchanged and merged (publish_topk / merge_wait).
+//   query   per chunk of query rows: every rank uploads and converts 1/world of the rows and broadcasts the BF16 rows +
+//           norms (what the tensor pass needs) over NVLink by peer stores; tensor pass on all rows against the local shard;
+//           every rank publishes an upper bound on its k-th nearest distance per query; the exact re-rank evaluates only
+//           candidates that survive the minimum of those bounds (the replicated re-rank of round 1 becomes 1/world of it
+//           per rank) and reads the ORIGINAL row of such a query straight from the rank that uploaded it (peer loads:
+//           the float64 rows are never broadcast); the exact local lists are exchanged and merged.
 #pragma once
 #include <chrono>
 #include "shard.cuh"
 
-enum ExFlag { F_TOPK = 0, F_BOUND, F_QBF, F_QRAW, F_CONSUMED, F_MEAN, F_NKINDS };
+enum ExFlag { F_TOPK = 0, F_BOUND, F_QBF, F_CONSUMED, F_MEAN, F_NKINDS };
 
 struct b200knn_exchange {
     int device = 0, rank = 0, world = 1;
@@ -31,12 +31,13 @@ struct b200knn_exchange {
     void *peer_base[EXCH_MAX_WORLD] = {};
     bool connected = false, ipc_mapped = false;
     unsigned int step = 0;       // F_TOPK
-    unsigned int qstep = 0;      // F_QBF / F_QRAW / F_CONSUMED: one id per chunk of a host-row query
+    unsigned int qstep = 0;      // F_QBF / F_CONSUMED: one id per chunk of a host-row query
     unsigned int bstep = 0;      // F_BOUND: one id per tensor pass of any collective query
     unsigned int mstep = 0;      // F_MEAN
     int64_t n_global = 0;        // rows of the whole pool (known after add)
-    cudaStream_t up_stream = nullptr;    // uploads + broadcasts run ahead of the compute stream
-    cudaEvent_t ev_bf[2] = {nullptr, nullptr}, ev_raw[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};   // per buffer parity
+    cudaStream_t up_stream = nullptr;    // host-to-device uploads + conversion of this rank's slices, ahead of the compute stream
+    cudaStream_t bc_stream = nullptr;    // NVLink broadcasts of the slices: the next upload (PCIe) overlaps them
+    cudaEvent_t ev_conv[2] = {nullptr, nullptr}, ev_bf[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};   // per buffer parity
     DevBuf<int32_t> loc_idx, pad_idx;    // this rank's exact lists of a call, before the merge
     DevBuf<double> loc_dist, pad_dist;
     DevBuf<unsigned int> gl_overflow;    // [1] overflowed second-pass lists over ALL ranks (written by the last merge of a call)
@@ -121,6 +122,7 @@ int ex_create(int device, int rank, int world, int dim, int64_t max_nq, int max_
     if (world == 1) ex->connected = true;
     if (dim > 0) {
         if (cudaStreamCreateWithFlags(&ex->up_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&ex->bc_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaMallocHost(reinterpret_cast<void **>(&ex->h_glovf), sizeof(unsigned int)) != cudaSuccess ||
             cudaMallocHost(reinterpret_cast<void **>(&ex->h_counts), sizeof(double) * EXCH_MAX_WORLD) != cudaSuccess ||
             ex->gl_overflow.ensure(1) != B200KNN_OK) {
@@ -130,8 +132,8 @@ int ex_create(int device, int rank, int world, int dim, int64_t max_nq, int max_
         }
         cudaMemset(ex->gl_overflow.p, 0, sizeof(unsigned int));
         for (int i = 0; i < 2; i++) {
+            cudaEventCreateWithFlags(&ex->ev_conv[i], cudaEventDisableTiming);
             cudaEventCreateWithFlags(&ex->ev_bf[i], cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&ex->ev_raw[i], cudaEventDisableTiming);
             cudaEventCreateWithFlags(&ex->ev_consumed[i], cudaEventDisableTiming);
         }
     }
@@ -216,10 +218,14 @@ int ex_chunks(const Shard &s, int64_t nq, int kp, int64_t cap_rows, std::vector<
         chunks.emplace_back(0, nq);
         return B200KNN_OK;
     }
+    // The ragged remainder first (the only upload nothing hides), then whole groups.  (A ramp of growing chunks was tried
+    // at 8 ranks to start the tensor cores earlier: every extra chunk costs two rank-wide exchanges and a second-pass
+    // sweep, and the small chunks ran at half efficiency next to the uploads — 8.4 ms against 7.7 without it.)
     const int64_t rem = nq % group_rows;
     int64_t q0 = 0;
-    if (rem > 0) { chunks.emplace_back(0, rem); q0 = rem; }
-    for (; q0 < nq; q0 += group_rows) chunks.emplace_back(q0, std::min(group_rows, nq - q0));
+    auto push = [&](int64_t rows) { if (rows > 0) { chunks.emplace_back(q0, rows); q0 += rows; } };
+    push(rem);
+    while (q0 < nq) push(std::min(group_rows, nq - q0));
     return B200KNN_OK;
 }
 
@@ -244,7 +250,7 @@ int ex_begin_query(b200knn_exchange *ex, Shard &s, int64_t nq, int k, unsigned f
     return B200KNN_OK;
 }
 
-Shard::ShardHook ex_hook(b200knn_exchange *ex, int kk_g, bool wait_raw, unsigned int raw_step, cudaEvent_t pre_rerank = nullptr) {
+Shard::ShardHook ex_hook(b200knn_exchange *ex, int kk_g) {
     Shard::ShardHook h{};
     h.peers = ex->peers();
     h.world = ex->world;
@@ -255,11 +261,6 @@ Shard::ShardHook ex_hook(b200knn_exchange *ex, int kk_g, bool wait_raw, unsigned
     h.bound_step = ++ex->bstep;
     h.local_base = ex->local();
     h.kk_global = kk_g;
-    if (wait_raw) {
-        h.raw_flag_off = ex->off_flags[F_QRAW];
-        h.raw_step = raw_step;
-        h.pre_rerank_event = pre_rerank;
-    }
     return h;
 }
 
@@ -302,12 +303,51 @@ int ex_query_device(b200knn_exchange *ex, Shard &s, int dim, int kp, const void 
     const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
     const int64_t step_rows = std::min<int64_t>(ex->max_nq, QUERY_CHUNK);
     for (int64_t q0 = 0; q0 < nq; q0 += step_rows) c.chunks.emplace_back(q0, std::min(step_rows, nq - q0));
-    for (auto &ch : c.chunks) TRY(s.reserve_pass(ch.second, kp, c.kk_l, false));      // no (re)allocation once flag-waiting kernels are in flight
+    for (auto &ch : c.chunks) TRY(s.reserve_pass(ch.second, kp, c.kk_l, ex->world > 1));      // no (re)allocation once flag-waiting kernels are in flight
+    const int W = ex->world, R = ex->rank;
+    char *lb = ex->local();
+    const bool tensor_path = c.kk_l <= 32 && !(flags & B200KNN_FLAG_FORCE_SCAN);
     for (size_t i = 0; i < c.chunks.size(); i++) {
         const int64_t q0 = c.chunks[i].first, cq = c.chunks[i].second;
-        const Shard::ShardHook hook = ex_hook(ex, c.kk_g, false, 0);
-        TRY(s.query_device(static_cast<const char *>(d_query) + static_cast<size_t>(q0) * ld * esz, dtype, cq, ld, dim, kp, k, flags,
-                           ex->loc_idx.p + q0 * c.kk_l, ex->loc_dist.p + q0 * c.kk_l, nullptr, static_cast<int>(q0), &hook));
+        const char *qsrc = static_cast<const char *>(d_query) + static_cast<size_t>(q0) * ld * esz;
+        const Shard::ShardHook hook = ex_hook(ex, c.kk_g);
+        if (W > 1 && tensor_path) {
+            // The rows are replicated, the conversion need not be: every rank converts 1/world of the chunk to BF16 + norms
+            // and broadcasts that slice by peer stores (same buffers, flags and step counter as the host-row protocol; all
+            // on the compute stream here — there is no upload to overlap).
+            const unsigned int step = ++ex->qstep;
+            const unsigned par = step & 1u;
+            __nv_bfloat16 *qb = reinterpret_cast<__nv_bfloat16 *>(lb + ex->off_qbf) + static_cast<size_t>(par) * ex->max_nq * kp;
+            float *qn = reinterpret_cast<float *>(lb + ex->off_qnorm) + static_cast<size_t>(par) * ex->max_nq;
+            float *qe = reinterpret_cast<float *>(lb + ex->off_qerr) + static_cast<size_t>(par) * ex->max_nq;
+            const int64_t slice = (cq + W - 1) / W;
+            const int64_t a = std::min(cq, slice * R), b = std::min(cq, slice * (R + 1));
+            s.stats.kernel_launches += 4;
+            if (step > 2) wait_flags_kernel<<<1, 32, 0, s.stream>>>(ex->local_flags(F_CONSUMED), W, step - 2, F_CONSUMED);
+            if (b > a) {
+                TRY(s.launch_convert(qsrc + static_cast<size_t>(a) * ld * esz, dtype, b - a, ld, dim, kp, qb + a * kp, qn + a, qe + a, s.scalars.p + 2));
+                BcastParams bp{};
+                bp.peers = ex->peers(); bp.world = W; bp.rank = R; bp.nseg = 3;
+                bp.seg[0] = {static_cast<size_t>(reinterpret_cast<char *>(qb + a * kp) - lb), static_cast<size_t>(b - a) * kp * sizeof(__nv_bfloat16)};
+                bp.seg[1] = {static_cast<size_t>(reinterpret_cast<char *>(qn + a) - lb), static_cast<size_t>(b - a) * sizeof(float)};
+                bp.seg[2] = {static_cast<size_t>(reinterpret_cast<char *>(qe + a) - lb), static_cast<size_t>(b - a) * sizeof(float)};
+                broadcast_segments_kernel<<<static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(148, ((bp.seg[0].bytes >> 4) + 2047) / 2048))), 512, 0, s.stream>>>(bp);
+            }
+            raise_flags_kernel<<<1, 32, 0, s.stream>>>(ex->peers(), W, ex->off_flags[F_QBF], R, step);
+            s.prof_begin(K_WAIT);
+            wait_flags_kernel<<<1, 32, 0, s.stream>>>(ex->local_flags(F_QBF), W, step, F_QBF);
+            s.prof_end();
+            CU_TRY(cudaGetLastError());
+            const QuerySide pre{qb, qn, qe};
+            TRY(s.query_device(qsrc, dtype, cq, ld, dim, kp, k, flags, ex->loc_idx.p + q0 * c.kk_l, ex->loc_dist.p + q0 * c.kk_l, &pre,
+                               static_cast<int>(q0), &hook));
+            TRY(ex_merge_chunk(ex, s, c, q0, cq, d_out_idx, d_out_dist, i + 1 == c.chunks.size()));
+            raise_flags_kernel<<<1, 32, 0, s.stream>>>(ex->peers(), W, ex->off_flags[F_CONSUMED], R, step);
+            CU_TRY(cudaGetLastError());
+            continue;
+        }
+        TRY(s.query_device(qsrc, dtype, cq, ld, dim, kp, k, flags, ex->loc_idx.p + q0 * c.kk_l, ex->loc_dist.p + q0 * c.kk_l, nullptr,
+                           static_cast<int>(q0), &hook));
         TRY(ex_merge_chunk(ex, s, c, q0, cq, d_out_idx, d_out_dist, i + 1 == c.chunks.size()));
     }
     TRY(s.enqueue_overflow_readback());
@@ -319,20 +359,63 @@ int ex_query_device(b200knn_exchange *ex, Shard &s, int dim, int kp, const void 
 }
 
 // ---- query, rows in HOST memory (every rank sees the same matrix; each uploads 1/world of every chunk) ----
-int ex_query_host(b200knn_exchange *ex, Shard &s, int dim, int kp, const void *h_query, int dtype, int64_t nq, int64_t ld, int k, unsigned flags,
-                  int32_t *h_out_idx, double *h_out_dist, int *out_kk) {
-    ExCall c;
+// Phase 1 of a host-row query: geometry and EVERY allocation, nothing collective.  A rank that fails here has not touched
+// the protocol yet (a single-process group checks all its ranks before any of them enters phase 2).
+int ex_query_host_prepare(b200knn_exchange *ex, Shard &s, int kp, int64_t nq, int k, unsigned flags, ExCall &c) {
     TRY(ex_begin_query(ex, s, nq, k, flags, c));
-    if (out_kk) *out_kk = c.kk_g;
-    const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
-    const size_t row_bytes = static_cast<size_t>(dim) * esz;
     TRY(ex_chunks(s, nq, kp, std::min<int64_t>(ex->max_nq, QUERY_CHUNK), c.chunks));
     TRY(s.out_idx.ensure(static_cast<size_t>(nq) * c.kk_g));
     TRY(s.out_dist.ensure(static_cast<size_t>(nq) * c.kk_g));
-    const int64_t nchunks = static_cast<int64_t>(c.chunks.size());
     for (auto &ch : c.chunks) TRY(s.reserve_pass(ch.second, kp, c.kk_l, true));       // no (re)allocation once flag-waiting kernels are in flight
     TRY(s.reserve_upload_ring());
+    return B200KNN_OK;
+}
+
+// $B200KNN_VERBOSE: device-side timeline of a call (CUDA events on both streams, printed after the call's synchronisation)
+struct ExTimeline {
+    bool on = false;
+    cudaEvent_t t0 = nullptr;
+    struct Mark { cudaEvent_t ev; const char *what; long long chunk; };
+    std::vector<Mark> marks;
+    std::mutex mu;
+    void begin(cudaStream_t st) {
+        on = getenv("B200KNN_VERBOSE") != nullptr;
+        if (!on) return;
+        cudaEventCreate(&t0);
+        cudaEventRecord(t0, st);
+    }
+    void mark(cudaStream_t st, const char *what, long long chunk) {
+        if (!on) return;
+        Mark m{nullptr, what, chunk};
+        cudaEventCreate(&m.ev);
+        cudaEventRecord(m.ev, st);
+        std::lock_guard<std::mutex> lock(mu);
+        marks.push_back(m);
+    }
+    void print(const b200knn_exchange *ex) {
+        if (!on) return;
+        for (auto &m : marks) {
+            float ms = 0.f;
+            cudaEventSynchronize(m.ev);
+            cudaEventElapsedTime(&ms, t0, m.ev);
+            if (ex->rank == 0 || ex->rank == ex->world - 1) fprintf(stderr, "[b200knn timeline rank %d] %8.3f ms  chunk %lld  %s\n", ex->rank, ms, m.chunk, m.what);
+            cudaEventDestroy(m.ev);
+        }
+        cudaEventDestroy(t0);
+        marks.clear();
+    }
+};
+
+// Phase 2: the pipeline.  h_out_* may be NULL (a rank of a single-process group whose copy of the result nobody needs).
+int ex_query_host_run(b200knn_exchange *ex, Shard &s, int dim, int kp, const void *h_query, int dtype, int64_t nq, int64_t ld, int k, unsigned flags,
+                      int32_t *h_out_idx, double *h_out_dist, ExCall &c) {
+    CU_TRY(cudaSetDevice(s.device));
+    const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
+    const size_t row_bytes = static_cast<size_t>(dim) * esz;
+    const int64_t nchunks = static_cast<int64_t>(c.chunks.size());
     const unsigned int step0 = ex->qstep;
+    ExTimeline tl;
+    tl.begin(s.stream);
     ex->qstep += static_cast<unsigned int>(nchunks);
     const int W = ex->world, R = ex->rank;
     char *lb = ex->local();
@@ -356,7 +439,8 @@ int ex_query_host(b200knn_exchange *ex, Shard &s, int dim, int kp, const void *h
             const unsigned int step = step0 + static_cast<unsigned int>(i) + 1;
             const unsigned par = step & 1u;
             const int64_t q0 = c.chunks[i].first, cq = c.chunks[i].second;
-            const int64_t a = cq * R / W, b = cq * (R + 1) / W;
+            const int64_t slice = (cq + W - 1) / W;                      // rank r uploads rows [r * slice, (r + 1) * slice) of the chunk
+            const int64_t a = std::min(cq, slice * R), b = std::min(cq, slice * (R + 1));
             int rc = B200KNN_OK;
             ex_trace(ex, "uploader: chunk %lld step %u rows [%lld,%lld) slice [%lld,%lld)", (long long)i, step, (long long)q0, (long long)(q0 + cq), (long long)a, (long long)b);
             // the buffers of this parity are free once EVERY rank (this one included) has consumed chunk step-2
@@ -365,37 +449,37 @@ int ex_query_host(b200knn_exchange *ex, Shard &s, int dim, int kp, const void *h
                 if (cudaStreamWaitEvent(up, ex->ev_consumed[par], 0) != cudaSuccess) rc = fail(B200KNN_ECUDA, "cudaStreamWaitEvent failed");
             }
             if (step > 2) wait_flags_kernel<<<1, 32, 0, up>>>(ex->local_flags(F_CONSUMED), W, step - 2, F_CONSUMED);
+            cudaStream_t bc = ex->bc_stream;
             if (b > a && rc == B200KNN_OK) {
                 char *raw = q_raw(lb, par) + static_cast<size_t>(a) * row_bytes;
+                tl.mark(up, "up: start (consumed wait passed)", i);
                 rc = s.upload_rows(raw, static_cast<const char *>(h_query) + static_cast<size_t>(q0 + a) * ld * esz, b - a, row_bytes,
                                    static_cast<size_t>(ld) * esz, up);
+                tl.mark(up, "up: H2D done", i);
                 if (rc == B200KNN_OK)
                     rc = s.launch_convert(raw, dtype, b - a, dim, dim, kp, q_bf(lb, par) + a * kp, q_norm(lb, par) + a, q_err(lb, par) + a,
                                           s.scalars.p + 2, up);
-                // NVLink broadcast by the copy engines: first what the tensor pass needs ...
-                for (int p = 0; p < W && rc == B200KNN_OK; p++) {
-                    if (p == R) continue;
-                    char *pb = static_cast<char *>(ex->peer_base[p]);
-                    if (cudaMemcpyAsync(q_bf(pb, par) + a * kp, q_bf(lb, par) + a * kp, static_cast<size_t>(b - a) * kp * sizeof(__nv_bfloat16), cudaMemcpyDefault, up) != cudaSuccess ||
-                        cudaMemcpyAsync(q_norm(pb, par) + a, q_norm(lb, par) + a, static_cast<size_t>(b - a) * sizeof(float), cudaMemcpyDefault, up) != cudaSuccess ||
-                        cudaMemcpyAsync(q_err(pb, par) + a, q_err(lb, par) + a, static_cast<size_t>(b - a) * sizeof(float), cudaMemcpyDefault, up) != cudaSuccess)
-                        rc = fail(B200KNN_ECUDA, "broadcast of the BF16 query slice failed: %s", cudaGetErrorString(cudaGetLastError()));
-                }
             }
+            // the broadcasts (NVLink copy engines) run on their own stream, so that the next chunk's upload (PCIe) overlaps them
+            if (rc == B200KNN_OK && (cudaEventRecord(ex->ev_conv[par], up) != cudaSuccess || cudaStreamWaitEvent(bc, ex->ev_conv[par], 0) != cudaSuccess))
+                rc = fail(B200KNN_ECUDA, "event hand-over to the broadcast stream failed");
             if (rc == B200KNN_OK) {
-                raise_flags_kernel<<<1, 32, 0, up>>>(ex->peers(), W, ex->off_flags[F_QBF], R, step);
-                if (cudaEventRecord(ex->ev_bf[par], up) != cudaSuccess) rc = fail(B200KNN_ECUDA, "cudaEventRecord failed");
-                // ... then the original rows, which only the exact re-rank reads: this copy hides behind the tensor pass
-                for (int p = 0; p < W && rc == B200KNN_OK && b > a; p++) {
-                    if (p == R) continue;
-                    char *pb = static_cast<char *>(ex->peer_base[p]);
-                    if (cudaMemcpyAsync(q_raw(pb, par) + static_cast<size_t>(a) * row_bytes, q_raw(lb, par) + static_cast<size_t>(a) * row_bytes,
-                                        static_cast<size_t>(b - a) * row_bytes, cudaMemcpyDefault, up) != cudaSuccess)
-                        rc = fail(B200KNN_ECUDA, "broadcast of the original query slice failed: %s", cudaGetErrorString(cudaGetLastError()));
+                // first what the tensor pass needs (BF16 rows, norms, rounding errors) ...
+                if (b > a && W > 1) {
+                    BcastParams bp{};
+                    bp.peers = ex->peers(); bp.world = W; bp.rank = R; bp.nseg = 3;
+                    bp.seg[0] = {static_cast<size_t>(reinterpret_cast<char *>(q_bf(lb, par) + a * kp) - lb), static_cast<size_t>(b - a) * kp * sizeof(__nv_bfloat16)};
+                    bp.seg[1] = {static_cast<size_t>(reinterpret_cast<char *>(q_norm(lb, par) + a) - lb), static_cast<size_t>(b - a) * sizeof(float)};
+                    bp.seg[2] = {static_cast<size_t>(reinterpret_cast<char *>(q_err(lb, par) + a) - lb), static_cast<size_t>(b - a) * sizeof(float)};
+                    const size_t units = bp.seg[0].bytes >> 4;
+                    s.stats.kernel_launches++;
+                    broadcast_segments_kernel<<<static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(32, (units + 2047) / 2048))), 512, 0, bc>>>(bp);
                 }
-                raise_flags_kernel<<<1, 32, 0, up>>>(ex->peers(), W, ex->off_flags[F_QRAW], R, step);
-                if (cudaGetLastError() != cudaSuccess) rc = fail(B200KNN_ECUDA, "flag kernel launch failed");
-                if (rc == B200KNN_OK && cudaEventRecord(ex->ev_raw[par], up) != cudaSuccess) rc = fail(B200KNN_ECUDA, "cudaEventRecord failed");
+                raise_flags_kernel<<<1, 32, 0, bc>>>(ex->peers(), W, ex->off_flags[F_QBF], R, step);
+                if (cudaEventRecord(ex->ev_bf[par], bc) != cudaSuccess) rc = fail(B200KNN_ECUDA, "cudaEventRecord failed");
+                tl.mark(bc, "bc: BF16 slice broadcast", i);
+                if (cudaGetLastError() != cudaSuccess) rc = fail(B200KNN_ECUDA, "broadcast / flag kernel launch failed");
+                // (the original rows stay where they were uploaded: the exact re-rank of any rank reads them from here)
             }
             if (rc != B200KNN_OK) {
                 up_err = g_last_error;      // thread-local in the uploader: hand it over
@@ -419,16 +503,23 @@ int ex_query_host(b200knn_exchange *ex, Shard &s, int dim, int kp, const void *h
         // this rank's slice: event (it has been converted and sent before the spin below starts); the peers': their flags
         if (cudaStreamWaitEvent(s.stream, ex->ev_bf[par], 0) != cudaSuccess) { rc_main = fail(B200KNN_ECUDA, "cudaStreamWaitEvent failed"); break; }
         wait_flags_kernel<<<1, 32, 0, s.stream>>>(ex->local_flags(F_QBF), W, step, F_QBF);      // every rank's BF16 slice is here
+        tl.mark(s.stream, "compute: all BF16 slices here", i);
         const QuerySide pre{q_bf(lb, par), q_norm(lb, par), q_err(lb, par)};
-        const Shard::ShardHook hook = ex_hook(ex, c.kk_g, true, step, ex->ev_raw[par]);
+        Shard::ShardHook hook = ex_hook(ex, c.kk_g);
+        // original rows: read from the rank that uploaded them (its QBF flag also says its slice of them is in place)
+        for (int r = 0; r < W; r++) hook.qpull.base[r] = static_cast<const char *>(ex->peer_base[r]);
+        hook.qpull.off = static_cast<size_t>(q_raw(lb, par) - lb);
+        hook.qpull.slice_rows = static_cast<int>((cq + W - 1) / W);
         s.stats.kernel_launches += 2;
-        if (c.kk_l > 32 || (flags & B200KNN_FLAG_FORCE_SCAN)) {     // the exact scan reads the original rows and has no flag wait of its own
-            cudaStreamWaitEvent(s.stream, ex->ev_raw[par], 0);
-            wait_flags_kernel<<<1, 32, 0, s.stream>>>(ex->local_flags(F_QRAW), W, step, F_QRAW);
+        if (W > 1 && (c.kk_l > 32 || (flags & B200KNN_FLAG_FORCE_SCAN))) {      // the exact scan wants the whole chunk's rows locally: pull them
+            s.stats.kernel_launches++;
+            pull_rows_kernel<<<s.num_sms * 2, 256, 0, s.stream>>>(hook.qpull, R, cq, row_bytes, q_raw(lb, par));
         }
         rc_main = s.query_device(q_raw(lb, par), dtype, cq, dim, dim, kp, k, flags, ex->loc_idx.p + q0 * c.kk_l, ex->loc_dist.p + q0 * c.kk_l, &pre,
                                  static_cast<int>(q0), &hook);
+        tl.mark(s.stream, "compute: tensor pass + re-rank + second pass done", i);
         if (rc_main == B200KNN_OK) rc_main = ex_merge_chunk(ex, s, c, q0, cq, s.out_idx.p, s.out_dist.p, i + 1 == nchunks);
+        tl.mark(s.stream, "compute: lists exchanged + merged", i);
         // every reader of this parity's query buffers (re-rank, second pass) is enqueued before this flag
         raise_flags_kernel<<<1, 32, 0, s.stream>>>(ex->peers(), W, ex->off_flags[F_CONSUMED], R, step);
         if (rc_main == B200KNN_OK && cudaGetLastError() != cudaSuccess) rc_main = fail(B200KNN_ECUDA, "flag kernel launch failed");
@@ -442,6 +533,7 @@ int ex_query_host(b200knn_exchange *ex, Shard &s, int dim, int kp, const void *h
     if (up_rc.load() != B200KNN_OK) return fail(up_rc.load(), "%s", up_err.c_str());
     if (rc_main != B200KNN_OK) return rc_main;
     auto copy_out = [&]() -> int {
+        if (!h_out_idx || !h_out_dist) return B200KNN_OK;
         CU_TRY(cudaMemcpyAsync(h_out_idx, s.out_idx.p, static_cast<size_t>(nq) * c.kk_g * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         CU_TRY(cudaMemcpyAsync(h_out_dist, s.out_dist.p, static_cast<size_t>(nq) * c.kk_g * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         return B200KNN_OK;
@@ -451,6 +543,7 @@ int ex_query_host(b200knn_exchange *ex, Shard &s, int dim, int kp, const void *h
     CU_TRY(cudaMemcpyAsync(ex->h_glovf, ex->gl_overflow.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, s.stream));
     CU_TRY(cudaStreamSynchronize(s.stream));
     ex_trace(ex, "call done: overflow local %d global %u", *s.h_count, *ex->h_glovf);
+    tl.print(ex);
     if (*ex->h_glovf == 0) return B200KNN_OK;
     TRY(ex_finish_query(ex, s, c, s.out_idx.p, s.out_dist.p, [&](int nov) {
         return s.fix_overflow_host(h_query, dtype, ld, nov, dim, c.kk_l, flags, ex->loc_idx.p, ex->loc_dist.p);
@@ -458,6 +551,14 @@ int ex_query_host(b200knn_exchange *ex, Shard &s, int dim, int kp, const void *h
     TRY(copy_out());
     CU_TRY(cudaStreamSynchronize(s.stream));
     return B200KNN_OK;
+}
+
+int ex_query_host(b200knn_exchange *ex, Shard &s, int dim, int kp, const void *h_query, int dtype, int64_t nq, int64_t ld, int k, unsigned flags,
+                  int32_t *h_out_idx, double *h_out_dist, int *out_kk) {
+    ExCall c;
+    TRY(ex_query_host_prepare(ex, s, kp, nq, k, flags, c));
+    if (out_kk) *out_kk = c.kk_g;
+    return ex_query_host_run(ex, s, dim, kp, h_query, dtype, nq, ld, k, flags, h_out_idx, h_out_dist, c);
 }
 
 void ex_destroy(b200knn_exchange *ex) {
@@ -471,9 +572,10 @@ void ex_destroy(b200knn_exchange *ex) {
     if (ex->h_glovf) cudaFreeHost(ex->h_glovf);
     if (ex->h_counts) cudaFreeHost(ex->h_counts);
     if (ex->up_stream) cudaStreamDestroy(ex->up_stream);
+    if (ex->bc_stream) cudaStreamDestroy(ex->bc_stream);
     for (int i = 0; i < 2; i++) {
+        if (ex->ev_conv[i]) cudaEventDestroy(ex->ev_conv[i]);
         if (ex->ev_bf[i]) cudaEventDestroy(ex->ev_bf[i]);
-        if (ex->ev_raw[i]) cudaEventDestroy(ex->ev_raw[i]);
         if (ex->ev_consumed[i]) cudaEventDestroy(ex->ev_consumed[i]);
     }
     if (ex->base) cudaFree(ex->base);

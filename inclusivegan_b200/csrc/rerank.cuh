@@ -86,6 +86,21 @@ __device__ __forceinline__ double canon_d2_warp(const TX *__restrict__ xr, const
     return ((w0 + w1) + w2) + w3;
 }
 
+// Row-sharded pools with host-resident queries: every rank uploads only its slice of a chunk's ORIGINAL query rows; the
+// exact re-rank reads the row of a query straight from its owner's buffer over NVLink (peer loads) — and only for the
+// queries that still have a local survivor after the global pruning, 5x less link traffic than broadcasting the rows.
+// All buffers share one layout, so row q sits at the same offset on whichever rank owns it.
+struct QueryPull {
+    const char *base[16];          // every rank's exchange buffer as mapped here (base[0] == nullptr: rows are local, use qmat)
+    size_t off;                    // byte offset of the chunk's row block in a buffer
+    int slice_rows;                // rows [r * slice_rows, (r + 1) * slice_rows) of the chunk were uploaded by rank r
+};
+template <typename TQ>
+__device__ __forceinline__ const TQ *query_row(const QueryPull &qp, const TQ *qmat, int64_t ld_q, int q) {
+    if (qp.base[0] == nullptr) return qmat + static_cast<int64_t>(q) * ld_q;
+    return reinterpret_cast<const TQ *>(qp.base[q / qp.slice_rows] + qp.off) + static_cast<int64_t>(q) * ld_q;
+}
+
 struct RerankParams {
     const float *cand_s;
     const int *cand_i;
@@ -116,6 +131,8 @@ struct RerankParams {
     const float *ext_bounds;       // nullptr: single shard
     int ext_world;
     int64_t ext_stride;
+    QueryPull qpull;               // where the original query rows live (zero-initialised: in qmat)
+    const float *min_score;        // with ext_bounds: the query's smallest shortlist score (from bound_publish_kernel)
 };
 
 // wait (bounded) until every rank's flag shows `step`; executed by the first `world` threads of a block
@@ -271,6 +288,20 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
     __shared__ int m_s;
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
+    if (p.ext_bounds && p.min_score) {
+        // Row-sharded pools: on most ranks a query has NO candidate that survives the global bound (its neighbour lives on
+        // another shard).  Then nothing is evaluated, the list is empty, and the answer is certified as it stands: every
+        // row of this shard scores at least the shortlist's minimum, whose lower bound already exceeds the global bound.
+        const double u = ext_bound_of(p, q);
+        const float ms = __ldg(p.min_score + q);
+        if (u < DBL_MAX && p.n > C && ms < FLT_MAX && make_err_model(p, q).lower(static_cast<double>(ms)) > u) {     // uniform across the block
+            for (int r = tid; r < p.kk; r += blockDim.x) {
+                p.out_idx[static_cast<int64_t>(q) * p.kk + r] = -1;
+                p.out_dist[static_cast<int64_t>(q) * p.kk + r] = DBL_MAX;
+            }
+            return;
+        }
+    }
     const int total = __ldg(p.slots_per_qtile + q / p.qtile_rows) * C;
     int P = 1;
     while (P < total) P <<= 1;
@@ -324,7 +355,7 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
     // block works on one candidate at a time: every thread owns a strided slice of the dimensions, keeps its slice
     // of the query row in registers across candidates, and issues its loads of the pool row back to back.
     const int warp = tid >> 5, lane = tid & 31;
-    const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
+    const TQ *qr = query_row(p.qpull, qmat, p.ld_q, q);
     if constexpr (NT > 128) {
         // Few queries, many shortlists (the trainer's 24-row calls, config 1): the device is far from full, so the eight
         // 128-thread groups of the block each take a candidate (named barrier per group), every candidate still summed
@@ -435,6 +466,7 @@ struct CollectRerankParams {
     unsigned flags;
     int allow_short;             // row-sharded pool: a list holds every local row within the GLOBAL bound, possibly fewer than kk
     int q_offset;                // first query row of this pass within the call (overflow entries are call-global rows)
+    QueryPull qpull;             // where the original query rows live (zero-initialised: in qmat)
     int32_t *out_idx;
     double *out_dist;
     int *overflow_count;
@@ -462,7 +494,7 @@ rerank_collect_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, con
             }
             continue;
         }
-        const TQ *qr = qmat + static_cast<int64_t>(q) * p.ld_q;
+        const TQ *qr = query_row(p.qpull, qmat, p.ld_q, q);
         for (int c = warp; c < cnt; c += NW) {       // one candidate per warp, canonical summation order
             const int j = p.coll_idx[static_cast<int64_t>(slot) * COLLECT_CAP + c];
             const double a0 = canon_d2_warp(x + static_cast<int64_t>(j) * p.ld_x, qr, p.dim, lane);

@@ -41,7 +41,7 @@ struct Shard {
     DevBuf<__nv_bfloat16> q_bf;
     DevBuf<float> qnorm_bf, q_err;
     DevBuf<__nv_bfloat16> q_bf2;     // second pass: BF16 rows of the uncertified queries
-    DevBuf<float> uncert_thr;
+    DevBuf<float> uncert_thr, min_score;
     DevBuf<int> coll_count, coll_idx, overflow_list;
     DevBuf<WorkItem> sched_items;    // first-pass schedule (cached across calls of the same shape: the trainer's 24-row loop)
     DevBuf<WorkItem> sched_items2;   // second pass / membership schedules
@@ -111,7 +111,7 @@ struct Shard {
         B200_PRELOAD((rerank_kernel<float, double, C, 1024>)); B200_PRELOAD((rerank_kernel<float, float, C, 1024>))
         B200_PRELOAD(colsum_kernel<double>); B200_PRELOAD(colsum_kernel<float>); B200_PRELOAD(scale_kernel);
         B200_PRELOAD(convert_norm_kernel<double>); B200_PRELOAD(convert_norm_kernel<float>);
-        B200_PRELOAD(plan_collect_kernel); B200_PRELOAD(gather_rows_kernel);
+        B200_PRELOAD(plan_pass_kernel); B200_PRELOAD(gather_rows_kernel);
         B200_PRELOAD((dist_topc_kernel<16, false, 1>)); B200_PRELOAD((dist_topc_kernel<32, false, 1>)); B200_PRELOAD((dist_topc_kernel<64, false, 1>));
         B200_PRELOAD((dist_topc_kernel<16, false, 2>)); B200_PRELOAD((dist_topc_kernel<32, false, 2>)); B200_PRELOAD((dist_topc_kernel<64, false, 2>));
         B200_PRELOAD((dist_topc_kernel<16, true, 1>)); B200_PRELOAD((dist_topc_kernel<16, true, 2>));
@@ -120,7 +120,7 @@ struct Shard {
         B200_PRELOAD((rerank_collect_kernel<float, double, 32>)); B200_PRELOAD((rerank_collect_kernel<float, float, 32>));
         B200_PRELOAD_T2(scan_dist_kernel); B200_PRELOAD(scan_select_kernel); B200_PRELOAD(iota_kernel); B200_PRELOAD(scatter_sorted_kernel);
         B200_PRELOAD(merge_topk_kernel); B200_PRELOAD(pad_topk_kernel); B200_PRELOAD(publish_topk_kernel); B200_PRELOAD(merge_wait_kernel);
-        B200_PRELOAD(raise_flags_kernel); B200_PRELOAD(wait_flags_kernel); B200_PRELOAD(bound_publish_kernel);
+        B200_PRELOAD(raise_flags_kernel); B200_PRELOAD(broadcast_segments_kernel); B200_PRELOAD(pull_rows_kernel); B200_PRELOAD(wait_flags_kernel); B200_PRELOAD(bound_publish_kernel);
         B200_PRELOAD(publish_colsum_kernel); B200_PRELOAD(global_mean_kernel);
         B200_PRELOAD(ball_colterm_kernel); B200_PRELOAD(ball_rowthr_kernel); B200_PRELOAD_T2(ball_member_kernel); B200_PRELOAD(scan_member_kernel);
         B200_PRELOAD(project_kernel<double>); B200_PRELOAD(project_kernel<float>);
@@ -221,7 +221,7 @@ struct Shard {
         if (!ready) return;
         clear_pool();
         drain_events();
-        q_bf.release(); qnorm_bf.release(); q_err.release(); q_bf2.release(); uncert_thr.release(); coll_count.release(); coll_idx.release(); overflow_list.release(); sched_items.release(); sched_items2.release(); sched_slots.release(); stream_sync.release(); radius2.release(); colterm.release(); rowthr.release(); member.release(); cand_s.release(); cand_i.release(); uncert_list.release();
+        q_bf.release(); qnorm_bf.release(); q_err.release(); q_bf2.release(); uncert_thr.release(); min_score.release(); coll_count.release(); coll_idx.release(); overflow_list.release(); sched_items.release(); sched_items2.release(); sched_slots.release(); stream_sync.release(); radius2.release(); colterm.release(); rowthr.release(); member.release(); cand_s.release(); cand_i.release(); uncert_list.release();
         scan_d2.release(); scan_d2_sorted.release(); scan_iota.release(); scan_vals_sorted.release(); scan_offsets.release();
         cub_tmp.release(); q_stage.release(); q_stage2.release(); out_idx.release(); out_dist.release(); pad_idx.release(); pad_dist.release(); scalars.release();
         if (h_count) cudaFreeHost(h_count);
@@ -395,12 +395,22 @@ struct Shard {
         // worker count exactly
         const int64_t a_tile_bytes = static_cast<int64_t>(qrows) * kp * 2;
         const int g_cap = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(W, (static_cast<int64_t>(a_budget_mb) << 20) / std::max<int64_t>(a_tile_bytes, 1))));
+        // Cost of a group size g in tile-times per worker: full rounds sweep nt / rc tiles each, the ragged last round has
+        // its own rc.  Within 10 % of the cheapest, the LARGEST group wins: fewer rounds, and fewer pool streams per query
+        // tile means fewer shortlists to publish, sort and bound per query (a 9-tile chunk split 2 x 37 instead of 9 x 8
+        // cost 3x its tensor time in shortlist handling, measured in the multi-GPU chunk pipeline).
         int qg = 1;
-        double best_util = -1.0;
-        for (int g = 1; g <= std::min(g_cap, s.qt); g++) {
-            const int rc = std::min(std::min(W / g, s.nt), max_slots_allowed);
-            const double util = static_cast<double>(g) * rc / W;
-            if (util >= best_util - 1e-12) { best_util = util; qg = g; }   // ties -> larger group (fewer rounds)
+        {
+            auto rc_of = [&](int g) { return std::max(1, std::min(std::min(W / g, s.nt), max_slots_allowed)); };
+            auto cost_of = [&](int g) {
+                double c = static_cast<double>(s.qt / g) * s.nt / rc_of(g);
+                if (s.qt % g) c += static_cast<double>(s.nt) / rc_of(s.qt % g);
+                return c;
+            };
+            double best = 1e300;
+            for (int g = 1; g <= std::min(g_cap, s.qt); g++) best = std::min(best, cost_of(g));
+            for (int g = 1; g <= std::min(g_cap, s.qt); g++)
+                if (cost_of(g) <= best * 1.10 + 1e-9) qg = g;
         }
         // Long K: only a few query tiles fit in L2 and each pool tile would be re-streamed from HBM for every small
         // group.  Alternative: a gs x rc grid of (query tile, pool stream) workers that advance through K together
@@ -657,9 +667,7 @@ struct Shard {
         unsigned int bound_step = 0;
         const char *local_base = nullptr;
         int kk_global = 0;              // neighbours of the GLOBAL answer (a shard with fewer rows publishes +inf)
-        size_t raw_flag_off = 0;        // != 0: the re-rank also waits until every rank's slice of the original query rows has arrived
-        unsigned int raw_step = 0;
-        cudaEvent_t pre_rerank_event = nullptr;   // own upload stream: this rank's slice of the original rows has been sent
+        QueryPull qpull{};              // host-row queries: the original rows are read from their owners' buffers (peer loads)
     };
     // a single-pass call may postpone the second pass until the host has seen the uncertified count at the call's one
     // synchronisation (the common small call has none: nothing is launched for it)
@@ -695,7 +703,7 @@ struct Shard {
     int64_t tmap_q2_rows = -1;
     int tmap_q2_kp = -1;
     int enqueue_second_pass(const void *d_query, int q_dtype, int64_t ld_q, int64_t nq_cap, int dim, int kp, int kk, unsigned flags,
-                            int32_t *d_out_idx, double *d_out_dist, int q_offset, bool allow_short) {
+                            int32_t *d_out_idx, double *d_out_dist, int q_offset, bool allow_short, const QueryPull *qpull = nullptr) {
         TRY(q_bf2.ensure(static_cast<size_t>(nq_cap) * kp));
         TRY(coll_count.ensure(nq_cap));
         TRY(coll_idx.ensure(static_cast<size_t>(nq_cap) * COLLECT_CAP));
@@ -708,17 +716,25 @@ struct Shard {
             tmap_q2_ptr = q_bf2.p; tmap_q2_rows = nq_cap; tmap_q2_kp = kp;
         }
         const int *count_dev = reinterpret_cast<const int *>(scalars.p + 4);
+        TRY(stream_sync.ensure(static_cast<size_t>(max_rounds) * s.workers));
+        PlanParams pp{};
+        pp.count_dev = count_dev;
+        pp.qrows = BM * s.cg; pp.nt = s.nt; pp.workers = s.workers; pp.group = s.qg; pp.max_rounds = max_rounds; pp.wide = s.wide ? 1 : 0;
+        pp.max_slots_cap = 1 << 20;
+        pp.items = sched_items2.p;
+        pp.round_counter = scalars.p + 6;
+        pp.stream_sync = stream_sync.p;
+        pp.sync_entries = max_rounds * s.workers;
+        pp.zero_list = coll_count.p;
+        pp.zero_list_n = static_cast<int>(nq_cap);
+        pp.total_uncertified = scalars.p + 8;
         prof_begin(K_SCAN);
-        plan_collect_kernel<<<1, 256, 0, stream>>>(count_dev, BM * s.cg, s.nt, s.workers, s.qg, max_rounds, s.wide ? 1 : 0, sched_items2.p, scalars.p + 8);
+        plan_pass_kernel<<<1, 256, 0, stream>>>(pp);
         prof_end();
         prof_begin(K_SCAN);
         gather_rows_kernel<<<num_sms * 4, 256, 0, stream>>>(cur_q_bf, uncert_list.p, count_dev, kp, q_bf2.p);
         prof_end();
         CU_TRY(cudaGetLastError());
-        CU_TRY(cudaMemsetAsync(coll_count.p, 0, static_cast<size_t>(nq_cap) * sizeof(int), stream));
-        CU_TRY(cudaMemsetAsync(scalars.p + 6, 0, sizeof(unsigned int), stream));
-        TRY(stream_sync.ensure(static_cast<size_t>(max_rounds) * s.workers));
-        CU_TRY(cudaMemsetAsync(stream_sync.p, 0, static_cast<size_t>(max_rounds) * s.workers * sizeof(unsigned int), stream));
         DistParams dp{};
         dp.xnorm = xnorm_bf.p;
         dp.n = static_cast<int>(n);
@@ -755,6 +771,7 @@ struct Shard {
         cp.flags = flags;
         cp.allow_short = allow_short ? 1 : 0;
         cp.q_offset = q_offset;
+        if (qpull) cp.qpull = *qpull;
         cp.out_idx = d_out_idx;
         cp.out_dist = d_out_dist;
         cp.overflow_count = reinterpret_cast<int *>(scalars.p + 5);
@@ -793,10 +810,27 @@ struct Shard {
         cur_q_bf = qb;
         CUtensorMap tmap_q;
         TRY(make_tmap(&tmap_q, qb, nq, kp, BM));
-        const bool cached = sched1.matches(nq, n, kp, MAX_KEYS / C);
-        if (!cached) TRY(plan(sched1, nq, kp, MAX_KEYS / C));
+        if (!sched1.matches(nq, n, kp, MAX_KEYS / C)) TRY(plan(sched1, nq, kp, MAX_KEYS / C));
         const Sched &s = sched1;
-        TRY(upload_schedule(s, sched_items, true, cached));
+        {   // the schedule is written on the device (and every counter of the pass zeroed) by one tiny kernel: no
+            // host-to-device copy, no memset — nothing of a pass can queue behind a query upload on a copy engine
+            TRY(sched_items.ensure(static_cast<size_t>(s.nrounds) * s.workers));
+            TRY(sched_slots.ensure(s.qt));
+            TRY(stream_sync.ensure(static_cast<size_t>(s.nrounds) * s.max_slots));
+            PlanParams pp{};
+            pp.count = static_cast<int>(nq);
+            pp.qrows = BM * s.cg; pp.nt = s.nt; pp.workers = s.workers; pp.group = s.qg; pp.max_rounds = s.nrounds; pp.wide = s.wide ? 1 : 0;
+            pp.max_slots_cap = MAX_KEYS / C;
+            pp.items = sched_items.p;
+            pp.slots_per_qtile = sched_slots.p;
+            pp.round_counter = scalars.p + 6;
+            pp.stream_sync = stream_sync.p;
+            pp.sync_entries = s.nrounds * s.max_slots;
+            pp.zero_a = scalars.p + 4;
+            stats.kernel_launches++;
+            plan_pass_kernel<<<1, 256, 0, stream>>>(pp);
+            CU_TRY(cudaGetLastError());
+        }
         TRY(cand_s.ensure(static_cast<size_t>(nq) * s.max_slots * C));
         TRY(cand_i.ensure(static_cast<size_t>(nq) * s.max_slots * C));
         DistParams dp = base_dist_params(nq, kp, s, sched_items.p);
@@ -855,6 +889,9 @@ struct Shard {
             bp.stride = hook->bounds_stride;
             bp.step = hook->bound_step;
             bp.done_counter = scalars.p + 9;
+            TRY(min_score.ensure(nq));
+            bp.min_score = min_score.p;
+            rp.min_score = min_score.p;
             prof_begin(K_RERANK);
             bound_publish_kernel<<<static_cast<unsigned>(std::min<int64_t>(num_sms * 4, (nq + 7) / 8)), 256, 0, stream>>>(bp);
             prof_end();
@@ -864,21 +901,15 @@ struct Shard {
                             static_cast<int64_t>(hook->bound_step & 1u) * hook->world * hook->bounds_stride;
             rp.ext_world = hook->world;
             rp.ext_stride = hook->bounds_stride;
-            // dependencies on this device's OTHER stream are taken through events, never through spinning on a flag:
-            // a spinning kernel must only wait for work that is guaranteed to run without it finishing
-            if (hook->pre_rerank_event) CU_TRY(cudaStreamWaitEvent(stream, hook->pre_rerank_event, 0));
-            // the peers' bounds (and, with host rows, their slices of the original query rows) must have arrived: one
-            // tiny spinning block each, so that the skew between ranks is not billed to the re-rank
+            rp.qpull = hook->qpull;
+            // the peers' bounds must have arrived: one tiny spinning block, so that the skew between ranks is not billed
+            // to the re-rank
             prof_begin(K_WAIT);
             wait_flags_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<const unsigned int *>(hook->local_base + hook->bound_flag_off), hook->world,
                                                     hook->bound_step, 101);
-            if (hook->raw_flag_off)
-                wait_flags_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<const unsigned int *>(hook->local_base + hook->raw_flag_off), hook->world,
-                                                        hook->raw_step, 103);
             prof_end();
             CU_TRY(cudaGetLastError());
         }
-        CU_TRY(cudaMemsetAsync(scalars.p + 4, 0, sizeof(unsigned int), stream));
         TRY(launch_rerank<C>(d_query, q_dtype, nq, rp));
         deferred.armed = false;
         if (!(flags & B200KNN_FLAG_NO_CERTIFY)) {
@@ -888,7 +919,8 @@ struct Shard {
                 deferred.kp = kp; deferred.kk = kk; deferred.flags = flags; deferred.out_idx = d_out_idx; deferred.out_dist = d_out_dist;
                 deferred.q_offset = q_offset;
             } else {
-                TRY(enqueue_second_pass(d_query, q_dtype, ld_q, nq, dim, kp, kk, flags, d_out_idx, d_out_dist, q_offset, hook != nullptr));
+                TRY(enqueue_second_pass(d_query, q_dtype, ld_q, nq, dim, kp, kk, flags, d_out_idx, d_out_dist, q_offset, hook != nullptr,
+                                        hook ? &hook->qpull : nullptr));
             }
         }
         return B200KNN_OK;
@@ -1017,6 +1049,7 @@ struct Shard {
         TRY(cand_i.ensure(static_cast<size_t>(nq) * a.max_slots * C));
         TRY(uncert_list.ensure(nq));
         TRY(uncert_thr.ensure(nq));
+        TRY(min_score.ensure(nq));
         TRY(q_bf2.ensure(static_cast<size_t>(nq) * kp));
         TRY(coll_count.ensure(nq));
         TRY(coll_idx.ensure(static_cast<size_t>(nq) * COLLECT_CAP));

@@ -156,7 +156,7 @@ def _protocol_worker(rank, world, port, out_path):
     check("host f32 k=10", gi, gd, pool.astype(np.float64), queries.astype(np.float64), 10)
 
     # ---- case 3: fewer rows per shard than k (lists padded with -1 before the merge) ----
-    n, q, d = 3 * world + 1, 300, 64
+    n, q, d = 4 * world - 1, 300, 64          # every rank holds 3-4 rows
     pool = rng.standard_normal((n, d)); queries = rng.standard_normal((q, d))
     a, b = shard_range(n, world, rank)
     ix4 = DeviceKNN(d, rank); ix4.set_stream(st)

@@ -312,10 +312,39 @@ def test_multi_device_handle_if_available(lib):
     if lib.b200knn_device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     from inclusivegan_b200 import DCI
+    devs = list(range(min(4, lib.b200knn_device_count())))
     x, y = make("gauss", 20000, 300, 256, seed=50)
-    db = DCI(256, devices=list(range(min(4, lib.b200knn_device_count()))))
+    db = DCI(256, devices=devs)
     db.add(x)
     check(db, x, y, 5)
+    # several chunks per call, float32 rows, a common offset (the centring vector is the GLOBAL mean), clustered queries
+    x, y = make("cluster", 60000, 9000, 384, seed=51, dtype=np.float32)
+    x += np.float32(3.0); y += np.float32(3.0)
+    db = DCI(384, devices=devs)
+    db.add(x)
+    i1, d1 = db.query_arrays(y, 3)
+    ri, rd = ko.exact_knn_numpy(x, y, 3)
+    ok, msg = ko.compare_knn(i1, d1, ri, rd, x.astype(np.float64), y.astype(np.float64))
+    assert ok, msg
+    one = DCI(384)                                  # bit-identical to the single-device handle (canonical summation order)
+    one.add(x)
+    i0, d0 = one.query_arrays(y, 3)
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+    # the trainer's 24-row calls through the collective path
+    li, ld = db.query(y[:24], num_neighbours=1)
+    assert np.array_equal(np.array(li)[:, 0], i1[:24, 0])
+    # all neighbours (dci.py:278-279 num_neighbours=-1) of a pool smaller than k per shard: padded shard lists, scan path
+    xs, ys = make("gauss", 50, 40, 32, seed=52)
+    db = DCI(32, devices=devs)
+    db.add(xs)
+    li, ld = db.query(ys)                           # num_neighbours=-1 -> 50 per query
+    ri, rd = ko.exact_knn_c(xs, ys, 50)
+    ok, msg = ko.compare_knn(np.array(li), np.array(ld), ri, rd, xs, ys)
+    assert ok, msg
+    li, ld = db.query(ys, num_neighbours=7)         # k > rows per shard (13 or 12): collective path with padded lists
+    ri, rd = ko.exact_knn_c(xs, ys, 7)
+    ok, msg = ko.compare_knn(np.array(li), np.array(ld), ri, rd, xs, ys)
+    assert ok, msg
 
 
 # ------------------------------------------------------------------------------------------------ full size
