@@ -216,6 +216,21 @@ typedef struct b200knn_stats {
     double  ms_wait;               /* row-sharded pools: time the stream spent waiting for the peers' flags (skew between ranks) */
 } b200knn_stats;
 
+/* ---- precision tiers of the tensor pass ----------------------------------------------------------
+ * Results are exact in every tier (the exact float64 re-rank and the certificate do not change); a tier decides how
+ * sharp the tensor-core scores are, i.e. how many candidates must be re-ranked and how many queries need the second
+ * pass.  BF16 (default): one tcgen05 kind::f16 MMA per product.  BF16X3: every operand row is split into hi + lo BF16
+ * rows and the kernel runs three K segments (hi.hi + hi.lo + lo.hi; the lo.lo term is bounded by ||q_lo|| ||x_lo||) — 3x
+ * the tensor work, rounding error 2^-17 instead of 2^-9 per element: for feature spaces whose nearest-neighbour gaps
+ * are far below BF16 resolution.  TF32: tcgen05 kind::tf32 on fp32 containers (half the BF16 rate, 2^-12).
+ * Set before add() (or after: the pool's operands of the tier are then built at once).  The row-sharded host-row protocol
+ * (b200knn_exchange_query) always runs BF16; b200knn_exchange_query_device honours the tier.  $B200KNN_PRECISION sets the
+ * default (bf16 | bf16x3 | tf32). */
+#define B200KNN_TIER_BF16   0
+#define B200KNN_TIER_BF16X3 1
+#define B200KNN_TIER_TF32   2
+int b200knn_set_precision(b200knn_index *index, int tier);
+
 /* profiling != 0: bracket every kernel with CUDA events on the launching stream; read with get_stats. */
 int b200knn_set_profiling(b200knn_index *index, int profiling);
 int b200knn_get_stats(b200knn_index *index, b200knn_stats *out);   /* synchronises the handle's stream(s) */

@@ -197,6 +197,22 @@ int b200knn_set_stream(b200knn_index *ix, void *stream) {
     return B200KNN_OK;
 }
 
+int b200knn_set_precision(b200knn_index *ix, int tier) {
+    if (!ix) return fail(B200KNN_EINVAL, "index is NULL");
+    if (tier < 0 || tier > 2) return fail(B200KNN_EINVAL, "precision tier must be B200KNN_TIER_BF16 / BF16X3 / TF32 (got %d)", tier);
+    TRY(ix->ensure_devices());
+    for (auto &s : ix->shards) {
+        if (s.tier == tier) continue;
+        s.tier = tier;
+        if (s.n > 0) {               // a pool is indexed already: build the tier's copy of its operands now
+            CU_TRY(cudaSetDevice(s.device));
+            TRY(s.convert_pool_tier(ix->dim, ix->kp));
+            CU_TRY(cudaStreamSynchronize(s.stream));
+        }
+    }
+    return B200KNN_OK;
+}
+
 int b200knn_set_profiling(b200knn_index *ix, int profiling) {
     if (!ix) return fail(B200KNN_EINVAL, "index is NULL");
     ix->profiling = profiling != 0;
@@ -260,6 +276,7 @@ int b200knn_add_device(b200knn_index *ix, const void *d_data, int dtype, int64_t
     TRY(s.attach_pool(d_data, false, dtype, n, ld, ix->dim, ix->kp, index_base));
     TRY(s.compute_mean(d_data, dtype, n, ld, ix->dim));
     TRY(s.launch_convert(d_data, dtype, n, ld, ix->dim, ix->kp, s.x_bf.p, s.xnorm_bf.p, s.x_err.p, s.scalars.p));
+    TRY(s.convert_pool_tier(ix->dim, ix->kp));
     ix->n_total = n;
     return B200KNN_OK;
 }
@@ -289,6 +306,7 @@ static int add_impl(b200knn_index *ix, const void *data, int dtype, int64_t n, i
         if (G > 1) return B200KNN_OK;        // phase 2 below: the centring vector is the GLOBAL column mean
         TRY(s.compute_mean(d_rows, dtype, rows, ix->dim, ix->dim));
         TRY(s.launch_convert(d_rows, dtype, rows, ix->dim, ix->dim, ix->kp, s.x_bf.p, s.xnorm_bf.p, s.x_err.p, s.scalars.p));
+        TRY(s.convert_pool_tier(ix->dim, ix->kp));
         return B200KNN_OK;
     };
     if (G == 1) {
@@ -557,7 +575,13 @@ int b200knn_query_self(b200knn_index *ix, int k, unsigned flags, int32_t *out_id
     TRY(s.begin_call(s.n));
     for (int64_t q0 = 0; q0 < s.n; q0 += QUERY_CHUNK) {
         const int64_t cq = std::min(QUERY_CHUNK, s.n - q0);
-        const QuerySide pre{s.x_bf.p + static_cast<size_t>(q0) * ix->kp, s.xnorm_bf.p + q0, s.x_err.p + q0};
+        QuerySide pre{s.x_bf.p + static_cast<size_t>(q0) * ix->kp, s.xnorm_bf.p + q0, s.x_err.p + q0};
+        if (s.tier != 0) {          // the pool's own operands of the handle's precision tier
+            pre.norm = s.xnorm_t.p + q0;
+            pre.err = s.x_err_t.p + q0;
+            if (s.tier == 1) { pre.lo = s.x_lo.p + static_cast<size_t>(q0) * ix->kp; pre.lonorm = s.x_lonorm.p + q0; }
+            else pre.tf = s.x_tf.p + static_cast<size_t>(q0) * ix->kp;
+        }
         TRY(s.query_device(static_cast<const char *>(s.x_raw) + static_cast<size_t>(q0) * s.ld_x * esz, s.x_dtype, cq, s.ld_x, ix->dim, ix->kp, k,
                            flags, s.out_idx.p + q0 * kk, s.out_dist.p + q0 * kk, &pre, static_cast<int>(q0)));
     }
@@ -657,6 +681,7 @@ static int add_projected_impl(b200knn_index *ix, const void *rows, int dtype, in
     TRY(project_host_rows(ix, s, rows, dtype, n, ld, static_cast<double *>(d_pool)));
     TRY(s.compute_mean(d_pool, B200KNN_F64, n, ix->dim, ix->dim));
     TRY(s.launch_convert(d_pool, B200KNN_F64, n, ix->dim, ix->dim, ix->kp, s.x_bf.p, s.xnorm_bf.p, s.x_err.p, s.scalars.p));
+    TRY(s.convert_pool_tier(ix->dim, ix->kp));
     CU_TRY(cudaStreamSynchronize(s.stream));          // the caller may free / overwrite `rows` after return
     ix->n_total = n;
     return B200KNN_OK;

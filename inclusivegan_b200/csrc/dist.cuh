@@ -39,6 +39,15 @@ struct DistParams {
     unsigned opt;            // tuning switches (A/B measurements): bit2 grid barrier between rounds
     const int *nq_dev;       // non-null: the number of valid query rows is read from device memory (second pass: the
                              // uncertified count of the first pass; the host does not synchronise to learn it)
+    // Precision tiers.  Split BF16 (bf16x3): every operand row is hi + lo (two BF16 rows); the kernel runs the
+    // K loop over THREE segments of nkb_seg blocks — [q_hi | q_hi | q_lo] . [x_hi | x_lo | x_hi] = q_hi.x_hi + q_hi.x_lo +
+    // q_lo.x_hi — by pointing the TMA loads of a segment at the hi or lo tensor map; MMA and epilogue do not change.
+    int nkb_seg;             // K blocks per segment (== num_kb: plain; num_kb == 3 * nkb_seg: split)
+    // K-chunked accumulation: the tensor core accumulates at most kb_per_unit K blocks into one TMEM accumulator; the
+    // epilogue warps add the partial sums in fp32 registers (IEEE round-to-nearest) into a running accumulator kept in the
+    // other half of TMEM.  The certificate's bound on the accumulation error then scales with the unit length instead
+    // of the row length (Cauchy-Schwarz over the units) — what keeps long rows (d = 49152) on the tensor path.
+    int kb_per_unit;         // >= num_kb: one unit (no chunking)
 };
 
 // Device-side planner of a pass (same layout as the host's Shard::plan_schedule, which sizes the buffers): per round a
@@ -135,11 +144,13 @@ struct DistCfg {
     static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2 * BN * 4 + 256 + SCRATCH_BYTES;
 };
 
-template <int C, bool COLLECT, int CG>
+template <int C, bool COLLECT, int CG, bool TF32 = false>
 __global__ void __launch_bounds__(DIST_THREADS, 1)
-dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x, const DistParams p) {
+dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
+                 const __grid_constant__ CUtensorMap tmap_qlo, const __grid_constant__ CUtensorMap tmap_xlo, const DistParams p) {
     using Cfg = DistCfg<CG>;
     constexpr int NSTAGE = Cfg::STAGES;
+    constexpr int KELEMS = TF32 ? BK / 2 : BK;      // elements per 128-byte stage row: 64 bf16 or 32 tf32 (fp32 containers)
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles must sit on 1024-byte boundaries (identical carve-up in both CTAs of a pair)
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -164,6 +175,8 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_qlo);
+        tma_prefetch_desc(&tmap_xlo);
         for (int s = 0; s < NSTAGE; s++) {
             mbar_init(bar_full + 8 * s, 1);       // the leader's arrive.expect_tx covers the bytes of BOTH CTAs' loads
             mbar_init(bar_empty + 8 * s, 1);
@@ -217,20 +230,25 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             }
                         }
                         const int n0 = t * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS;
+                        int seg = 0, kk = 0;                  // split tiers: segment 0 = hi.hi, 1 = q_hi.x_lo, 2 = q_lo.x_hi
                         for (int kb = 0; kb < p.num_kb; kb++) {
+                            const CUtensorMap *ma = (seg == 2) ? &tmap_qlo : &tmap_q;
+                            const CUtensorMap *mb = (seg == 1) ? &tmap_xlo : &tmap_x;
+                            const int kcoord = kk * KELEMS;
+                            if (++kk == p.nkb_seg) { kk = 0; seg++; }
                             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                             if (CG == 1) {
                                 mbar_expect_tx(bar_full + 8 * stage, Cfg::STAGE_BYTES);
-                                tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_q, bar_full + 8 * stage, kb * BK, q0);
-                                tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_x, bar_full + 8 * stage, kb * BK, n0);
+                                tma_load_2d(smem_a + stage * Cfg::A_BYTES, ma, bar_full + 8 * stage, kcoord, q0);
+                                tma_load_2d(smem_b + stage * Cfg::B_BYTES, mb, bar_full + 8 * stage, kcoord, n0);
                             } else {
                                 // all four loads of the pair (2 x A half, 2 x B half) signal the LEADER's barrier; the
                                 // peer never arrives there: its loads only complete_tx (a remote arrive per K block
                                 // would cost a cluster-scope fence each time)
                                 if (leader) mbar_expect_tx(bar_full + 8 * stage, 2 * Cfg::STAGE_BYTES);
                                 const uint32_t fb = leader ? (bar_full + 8 * stage) : (full_remote + 8 * stage);
-                                tma_load_2d_cg2(smem_a + stage * Cfg::A_BYTES, &tmap_q, fb, kb * BK, q0);
-                                tma_load_2d_cg2(smem_b + stage * Cfg::B_BYTES, &tmap_x, fb, kb * BK, n0);
+                                tma_load_2d_cg2(smem_a + stage * Cfg::A_BYTES, ma, fb, kcoord, q0);
+                                tma_load_2d_cg2(smem_b + stage * Cfg::B_BYTES, mb, fb, kcoord, n0);
                             }
                             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                         }
@@ -256,43 +274,53 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // The issuing thread is on the critical path: per K block it must spend less than the 512 tensor cycles the
         // four MMAs take.
         if (leader) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
+            constexpr uint32_t idesc = TF32 ? make_idesc_tf32(BM * CG, BN) : make_idesc_bf16(BM * CG, BN);
+            const bool chunked = p.kb_per_unit < p.num_kb;
             int stage = 0;
             uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
+            int tile_par = 0;                    // one unit per tile: the two accumulators alternate, the epilogue of t overlaps the MMAs of t+1
+            uint32_t uses[2] = {0u, 0u};         // how often each accumulator has been handed to the epilogue (barrier parity)
             for (int round = 0; round < p.nrounds; round++) {
                 const WorkItem w = load_item(p, round, worker);
                 if (w.qtile < 0) continue;
                 for (int t = w.t0; t < w.t1; t++) {
-                    mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);     // epilogues have drained this accumulator
-                    tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + acc * BN;
-                    for (int kb = 0; kb < p.num_kb; kb++) {
-                        mbar_wait(bar_full + 8 * stage, phase);               // TMA bytes (of both CTAs) have landed
+                    // chunked: unit 0 accumulates into buffer 0 (the running sum), every later unit into buffer 1 (a partial
+                    // sum the epilogue folds into buffer 0)
+                    int kb = 0;
+                    for (int unit = 0; kb < p.num_kb; unit++) {
+                        const int acc = chunked ? (unit ? 1 : 0) : tile_par;
+                        const int kb_end = min(p.num_kb, kb + p.kb_per_unit);
+                        mbar_wait(bar_tempty + 8 * acc, (uses[acc] & 1u) ^ 1u);     // epilogues have drained this accumulator
+                        uses[acc]++;
                         tc_fence_after();
-                        const uint32_t cur = stage;
-                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                        if (elect_one()) {
-                            const uint64_t da = make_smem_desc_sw128(smem_a + cur * Cfg::A_BYTES);
-                            const uint64_t db = make_smem_desc_sw128(smem_b + cur * Cfg::B_BYTES);
+                        const uint32_t tmem_d = tmem_base + acc * BN;
+                        for (bool first = true; kb < kb_end; kb++, first = false) {
+                            mbar_wait(bar_full + 8 * stage, phase);               // TMA bytes (of both CTAs) have landed
+                            tc_fence_after();
+                            const uint32_t cur = stage;
+                            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                            if (elect_one()) {
+                                const uint64_t da = make_smem_desc_sw128(smem_a + cur * Cfg::A_BYTES);
+                                const uint64_t db = make_smem_desc_sw128(smem_b + cur * Cfg::B_BYTES);
 #pragma unroll
-                            for (int k = 0; k < BK / UMMA_K; k++) {
-                                // +32 bytes per K slice inside the 128-byte swizzle row: +2 in the (>>4) address field
-                                umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                                for (int k = 0; k < BK / UMMA_K; k++) {
+                                    // +32 bytes per K slice inside the 128-byte swizzle row: +2 in the (>>4) address field
+                                    // (16 bf16 or 8 tf32 per slice: the same 32 bytes)
+                                    if constexpr (TF32) umma_tf32<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+                                    else umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+                                }
+                                // frees the smem slot (in both CTAs) when the MMAs retire
+                                if (CG == 1) umma_commit(bar_empty + 8 * cur);
+                                else umma_commit_cg2(bar_empty + 8 * cur, 0x3);
+                                if (kb == kb_end - 1) {                        // unit complete -> epilogue(s)
+                                    if (CG == 1) umma_commit(bar_tfull + 8 * acc);
+                                    else umma_commit_cg2(bar_tfull + 8 * acc, 0x3);
+                                }
                             }
-                            // frees the smem slot (in both CTAs) when the MMAs retire
-                            if (CG == 1) umma_commit(bar_empty + 8 * cur);
-                            else umma_commit_cg2(bar_empty + 8 * cur, 0x3);
-                            if (kb == p.num_kb - 1) {                      // accumulator complete -> epilogue(s)
-                                if (CG == 1) umma_commit(bar_tfull + 8 * acc);
-                                else umma_commit_cg2(bar_tfull + 8 * acc, 0x3);
-                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1;
+                    tile_par ^= 1;
                 }
             }
         }
@@ -302,8 +330,10 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const int row_in_tile = quarter * 32 + lane;
         const int nq_eff = p.nq_dev ? min(__ldcg(p.nq_dev), p.nq) : p.nq;
         const int et = threadIdx.x - 64;               // 0..127
-        int acc = 0;
-        uint32_t acc_phase = 0;
+        const bool chunked = p.kb_per_unit < p.num_kb;
+        const int nunits = (p.num_kb + p.kb_per_unit - 1) / p.kb_per_unit;
+        int tile_par = 0;
+        uint32_t uses[2] = {0u, 0u};
         for (int round = 0; round < p.nrounds; round++) {
             const WorkItem w = load_item(p, round, worker);
             if (w.qtile < 0) continue;
@@ -321,17 +351,45 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
             for (int t = t0; t < t1; t++) {
                 const int n0 = t * BN;
+                const int acc = chunked ? 0 : tile_par;
                 // stage ||x~||^2 of this tile; rows past the end of the pool can never be selected
-                float *xs = xn_s + acc * BN;
+                float *xs = xn_s + tile_par * BN;       // (two staging buffers whichever accumulator the tile uses)
                 {
                     const int c0 = n0 + et, c1 = n0 + et + 128;
                     xs[et] = (c0 < p.n) ? __ldg(p.xnorm + c0) : FLT_MAX;
                     xs[et + 128] = (c1 < p.n) ? __ldg(p.xnorm + c1) : FLT_MAX;
                 }
                 named_bar_sync(1, 128);
-                mbar_wait(bar_tfull + 8 * acc, acc_phase);
+                mbar_wait(bar_tfull + 8 * acc, uses[acc] & 1u);
+                uses[acc]++;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+                if (chunked) {
+                    // fold the partial sums of units 1.. (buffer 1) into the running sum (buffer 0): fp32 adds in registers
+                    const uint32_t paddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + BN;
+                    for (int unit = 1; unit < nunits; unit++) {
+                        mbar_wait(bar_tfull + 8, uses[1] & 1u);
+                        uses[1]++;
+                        tc_fence_after();
+#pragma unroll 1
+                        for (int c = 0; c < BN / 16; c++) {
+                            uint32_t a[16], b[16];
+                            tmem_ld_32x16(taddr + c * 16, a);
+                            tmem_ld_32x16(paddr + c * 16, b);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; j++) a[j] = __float_as_uint(__fadd_rn(__uint_as_float(a[j]), __uint_as_float(b[j])));
+                            tmem_st_32x16(taddr + c * 16, a);
+                        }
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {                   // the partial accumulator is free for the next unit
+                            if (CG == 1 || leader) mbar_arrive(bar_tempty + 8);
+                            else mbar_arrive_cluster(bar_tempty + 8, 0);
+                        }
+                    }
+                }
                 // TMEM -> registers in 32-column slabs.  Hot path per score: FFMA + compare + predicated OR into a hit
                 // mask (no branches, compact code: the issuing warps share the SM's instruction cache with this loop).
                 // Slabs with hits park their 32 scores in shared memory and replay only the hit positions through ONE
@@ -378,8 +436,7 @@ dist_topc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     if (CG == 1 || leader) mbar_arrive(bar_tempty + 8 * acc);
                     else mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
                 }
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                tile_par ^= 1;
             }
             if constexpr (!COLLECT) {
                 if (q < nq_eff) {

@@ -198,6 +198,7 @@ int ex_finish_add(b200knn_exchange *ex, Shard &s, int dim, int kp) {
     CU_TRY(cudaGetLastError());
     s.centered = s.use_centering;
     TRY(s.launch_convert(s.x_raw, s.x_dtype, rows, s.ld_x, dim, kp, s.x_bf.p, s.xnorm_bf.p, s.x_err.p, s.scalars.p));
+    TRY(s.convert_pool_tier(dim, kp));
     for (int r = 0; r < ex->world; r++)
         CU_TRY(cudaMemcpyAsync(ex->h_counts + r, sums + static_cast<size_t>(r) * (dim + 1) + dim, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     CU_TRY(cudaStreamSynchronize(s.stream));
@@ -303,7 +304,7 @@ int ex_query_device(b200knn_exchange *ex, Shard &s, int dim, int kp, const void 
     const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
     const int64_t step_rows = std::min<int64_t>(ex->max_nq, QUERY_CHUNK);
     for (int64_t q0 = 0; q0 < nq; q0 += step_rows) c.chunks.emplace_back(q0, std::min(step_rows, nq - q0));
-    for (auto &ch : c.chunks) TRY(s.reserve_pass(ch.second, kp, c.kk_l, ex->world > 1));      // no (re)allocation once flag-waiting kernels are in flight
+    for (auto &ch : c.chunks) TRY(s.reserve_pass(ch.second, kp, c.kk_l, ex->world > 1 && s.tier == 0));      // no (re)allocation once flag-waiting kernels are in flight
     const int W = ex->world, R = ex->rank;
     char *lb = ex->local();
     const bool tensor_path = c.kk_l <= 32 && !(flags & B200KNN_FLAG_FORCE_SCAN);
@@ -311,7 +312,7 @@ int ex_query_device(b200knn_exchange *ex, Shard &s, int dim, int kp, const void 
         const int64_t q0 = c.chunks[i].first, cq = c.chunks[i].second;
         const char *qsrc = static_cast<const char *>(d_query) + static_cast<size_t>(q0) * ld * esz;
         const Shard::ShardHook hook = ex_hook(ex, c.kk_g);
-        if (W > 1 && tensor_path) {
+        if (W > 1 && tensor_path && s.tier == 0) {     // (other precision tiers: every rank converts all rows itself, below)
             // The rows are replicated, the conversion need not be: every rank converts 1/world of the chunk to BF16 + norms
             // and broadcasts that slice by peer stores (same buffers, flags and step counter as the host-row protocol; all
             // on the compute stream here — there is no upload to overlap).

@@ -73,13 +73,14 @@ int resolve_driver() {
 }
 
 // BF16 row-major [rows, kp] -> 2-D tensor map with a (BK x box_rows) SWIZZLE_128B box
-int make_tmap(CUtensorMap *m, const void *base, uint64_t rows, uint64_t kp, uint32_t box_rows) {
+// (f32 = true: fp32 containers of TF32 values, 32 elements per 128-byte box row)
+int make_tmap(CUtensorMap *m, const void *base, uint64_t rows, uint64_t kp, uint32_t box_rows, bool f32 = false) {
     TRY(resolve_driver());
     cuuint64_t dims[2] = {kp, rows};
-    cuuint64_t strides[1] = {kp * 2};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+    cuuint64_t strides[1] = {kp * (f32 ? 4u : 2u)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(f32 ? BK / 2 : BK), box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+    CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(B200KNN_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu kp=%llu)", (int)r,
@@ -120,6 +121,10 @@ struct PinnedRing {
 };
 PinnedRing g_rings[64];
 
-struct QuerySide { const __nv_bfloat16 *bf; const float *norm; const float *err; };
+// converted query rows handed to a tensor pass: BF16 rows (+ lo rows for the split tier, or TF32 rows), norms, errors
+struct QuerySide {
+    const __nv_bfloat16 *bf; const float *norm; const float *err;
+    const __nv_bfloat16 *lo = nullptr; const float *tf = nullptr; const float *lonorm = nullptr;
+};
 
 }  // namespace

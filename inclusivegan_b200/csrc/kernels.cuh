@@ -17,6 +17,7 @@
 #pragma once
 #include "common.cuh"
 #include "convert.cuh"
+#include "tiers.cuh"
 #include "dist.cuh"
 #include "rerank.cuh"
 #include "scan.cuh"

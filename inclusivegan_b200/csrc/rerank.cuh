@@ -133,6 +133,12 @@ struct RerankParams {
     int64_t ext_stride;
     QueryPull qpull;               // where the original query rows live (zero-initialised: in qmat)
     const float *min_score;        // with ext_bounds: the query's smallest shortlist score (from bound_publish_kernel)
+    // precision tier of the tensor pass that produced the scores (tiers.cuh) and its accumulation geometry
+    int tier;                      // 0 bf16, 1 bf16x3 (hi/lo split, three segments), 2 tf32
+    int k_unit;                    // products accumulated by the tensor core into one accumulator (<= k_total)
+    int n_units;                   // accumulation units per score (partial sums added in fp32 by the epilogue when > 1)
+    const float *q_lonorm;         // tier 1: ||q_lo|| per query
+    const unsigned int *max_x_lonorm_bits;   // tier 1: max ||x_lo|| over the pool
 };
 
 // wait (bounded) until every rank's flag shows `step`; executed by the first `world` threads of a block
@@ -178,10 +184,24 @@ __device__ __forceinline__ ErrModel make_err_model(const RerankParams &p, int q)
     ErrModel m;
     m.qn_bf = static_cast<double>(p.qnorm_bf[q]);
     const double xn_bf = static_cast<double>(__uint_as_float(*p.max_xnorm_bf_bits));
-    const double K = static_cast<double>(p.kp);
-    // fp32 accumulation error of the MMA (K terms of magnitude <= ||q~|| ||x~||, x2 for the -2 factor, truncating
-    // adds assumed), of the fp32 norm sums, and of forming s~ in fp32
-    m.eps_acc = (K + 8.0) * 2.4e-7 * sqrt(m.qn_bf * xn_bf) * 1.001 + (K / 16.0 + 8.0) * 1.2e-7 * (xn_bf + m.qn_bf);
+    // magnitude of the operand rows as the tensor core sees them: plain tiers ||q^|| ||x^||; split tier the three
+    // segments [hi | hi | lo] . [hi | lo | hi], with ||hi|| <= ||hi + lo|| + ||lo||
+    double QN = m.qn_bf, XN = xn_bf, extra = 0.0;
+    if (p.tier == 1) {
+        const double ql = static_cast<double>(p.q_lonorm[q]), xl = static_cast<double>(__uint_as_float(*p.max_x_lonorm_bits));
+        const double qh = sqrt(m.qn_bf) + ql, xh = sqrt(xn_bf) + xl;
+        QN = 2.0 * qh * qh + ql * ql;
+        XN = 2.0 * xh * xh + xl * xl;
+        extra = 2.0 * ql * xl * (1.0 + 1e-6);          // the q_lo . x_lo products the three MMAs leave out
+    }
+    const double mag = sqrt(QN * XN);
+    // fp32 accumulation inside the tensor core: k_unit products of magnitude <= mag in total per unit (x2 for the -2 factor,
+    // truncating adds assumed: EMPIRICALLY VALIDATED model, tests/test_gpu_parity.py::test_tensor_scores_within_the_certified_error_model);
+    // summed over the units by Cauchy-Schwarz the total still scales with ONE unit's length.  Then: the fp32 adds of the
+    // partial sums (IEEE round-to-nearest), the norm sums, and forming s~ in fp32.
+    m.eps_acc = (static_cast<double>(p.k_unit) + 8.0) * 2.4e-7 * mag * 1.001 + static_cast<double>(p.n_units) * 1.2e-7 * mag + extra;
+    if (p.tier == 0) m.eps_acc += (static_cast<double>(p.kp) / 16.0 + 8.0) * 1.2e-7 * (xn_bf + m.qn_bf);
+    else m.eps_acc += 4.8e-7 * (xn_bf + m.qn_bf + 2.0 * mag);     // norms summed in float64, rounded once
     m.eta = (static_cast<double>(p.q_err[q]) + static_cast<double>(__uint_as_float(*p.max_x_err_bits))) * (1.0 + 1e-6) + 1e-30;
     return m;
 }
@@ -536,17 +556,15 @@ rerank_collect_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, con
     }
 }
 
-// gather BF16 query rows of the uncertified queries into a compact matrix for the collection pass
+// gather converted query rows (16-byte units) of the uncertified queries into a compact matrix for the collection pass
 __global__ void __launch_bounds__(256)
-gather_rows_kernel(const __nv_bfloat16 *__restrict__ src, const int *__restrict__ list, const int *__restrict__ nsel_dev, int kp,
-                   __nv_bfloat16 *__restrict__ dst) {
+gather_rows_kernel(const uint4 *__restrict__ src, const int *__restrict__ list, const int *__restrict__ nsel_dev, int vec_per_row,
+                   uint4 *__restrict__ dst) {
     const int nsel = *nsel_dev;        // device-side count: zero -> nothing to do
-    const int vec_per_row = kp >> 3;   // kp is a multiple of 8: 16-byte chunks
     const int64_t total = static_cast<int64_t>(nsel) * vec_per_row;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int r = static_cast<int>(i / vec_per_row), c = static_cast<int>(i % vec_per_row);
-        reinterpret_cast<uint4 *>(dst + static_cast<int64_t>(r) * kp)[c] =
-            reinterpret_cast<const uint4 *>(src + static_cast<int64_t>(list[r]) * kp)[c];
+        dst[static_cast<int64_t>(r) * vec_per_row + c] = src[static_cast<int64_t>(list[r]) * vec_per_row + c];
     }
 }
 

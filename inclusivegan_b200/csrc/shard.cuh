@@ -21,13 +21,21 @@ struct Shard {
     int64_t n = 0, ld_x = 0, index_base = 0;
     DevBuf<__nv_bfloat16> x_bf;
     DevBuf<float> xnorm_bf, x_err;
+    // precision tier of the tensor pass (tiers.cuh): 0 bf16, 1 bf16x3 (split), 2 tf32; the tier's own operand copies
+    int tier = 0;                    // $B200KNN_PRECISION / b200knn_set_precision
+    int kc_elems = 4096;             // $B200KNN_KC: K elements the tensor core accumulates before the epilogue folds the partial sum (0 = never)
+    DevBuf<__nv_bfloat16> x_lo, q_lo, q_lo2;
+    DevBuf<float> x_tf, q_tf, q_tf2;
+    DevBuf<float> xnorm_t, x_err_t, x_lonorm, qnorm_t, q_err_t, q_lonorm, qnorm_t2, q_err_t2, q_lonorm2;
+    CUtensorMap tmap_xlo, tmap_xlo128, tmap_xtf, tmap_xtf128;
     DevBuf<double> col_mean;         // pool column means (subtracted from pool and queries before BF16 rounding)
     bool centered = false;
     bool use_centering = true;       // $B200KNN_CENTER=0 disables
     DevBuf<unsigned int> scalars;    // [0] max ||x~||^2 bits, [1] max ||x - x~|| bits, [2],[3] same for queries (unused), [4] uncertified count of
                                      // the pass in flight, [5] overflow count of the call, [6] grid-barrier counter of the distance kernel,
                                      // [7] max (r_j + e_j) bits (ball membership), [8] uncertified queries since the last stats reset,
-                                     // [9] done counter of bound_publish_kernel
+                                     // [9] done counter of bound_publish_kernel, [10..12] tier maxima of the pool (||x^||^2, ||x - x^||,
+                                     // ||x_lo||), [13..15] the same for the queries of the pass (unused)
     CUtensorMap tmap_x;              // pool, 256-row box (1-CTA kernel)
     CUtensorMap tmap_x128;           // pool, 128-row box (each CTA of a pair stages half of the 256-row tile)
     int forced_cg = 0;               // $B200KNN_CTA_GROUP=1|2 pins the kernel flavour (A/B measurements)
@@ -65,6 +73,9 @@ struct Shard {
     DevBuf<double> out_dist, pad_dist;
     int *h_count = nullptr;          // pinned
     const __nv_bfloat16 *cur_q_bf = nullptr;   // BF16 query rows of the tensor pass in flight (second pass gathers from them)
+    const __nv_bfloat16 *cur_q_lo = nullptr;   // ... their lo parts (split tier) / TF32 rows, and the tier that pass ran in
+    const float *cur_q_tf = nullptr;
+    int cur_tier = 0;
     int64_t last_nq = 0;             // geometry of the last tensor pass (b200knn_debug_shortlists)
     int last_slots = 0, last_c = 0;
 
@@ -115,6 +126,11 @@ struct Shard {
         B200_PRELOAD((dist_topc_kernel<16, false, 1>)); B200_PRELOAD((dist_topc_kernel<32, false, 1>)); B200_PRELOAD((dist_topc_kernel<64, false, 1>));
         B200_PRELOAD((dist_topc_kernel<16, false, 2>)); B200_PRELOAD((dist_topc_kernel<32, false, 2>)); B200_PRELOAD((dist_topc_kernel<64, false, 2>));
         B200_PRELOAD((dist_topc_kernel<16, true, 1>)); B200_PRELOAD((dist_topc_kernel<16, true, 2>));
+        B200_PRELOAD((dist_topc_kernel<16, false, 1, true>)); B200_PRELOAD((dist_topc_kernel<32, false, 1, true>)); B200_PRELOAD((dist_topc_kernel<64, false, 1, true>));
+        B200_PRELOAD((dist_topc_kernel<16, false, 2, true>)); B200_PRELOAD((dist_topc_kernel<32, false, 2, true>)); B200_PRELOAD((dist_topc_kernel<64, false, 2, true>));
+        B200_PRELOAD((dist_topc_kernel<16, true, 1, true>)); B200_PRELOAD((dist_topc_kernel<16, true, 2, true>));
+        B200_PRELOAD((convert_tier_kernel<double, 1>)); B200_PRELOAD((convert_tier_kernel<float, 1>));
+        B200_PRELOAD((convert_tier_kernel<double, 2>)); B200_PRELOAD((convert_tier_kernel<float, 2>));
         B200_PRELOAD_RR(16); B200_PRELOAD_RR(32); B200_PRELOAD_RR(64);
         B200_PRELOAD((rerank_collect_kernel<double, double, 32>)); B200_PRELOAD((rerank_collect_kernel<double, float, 32>));
         B200_PRELOAD((rerank_collect_kernel<float, double, 32>)); B200_PRELOAD((rerank_collect_kernel<float, float, 32>));
@@ -138,6 +154,14 @@ struct Shard {
         CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<16, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
         CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<64, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<1>::SMEM_BYTES));
         CU_TRY(cudaFuncSetAttribute(dist_topc_kernel<64, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute((dist_topc_kernel<16, false, 1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<1>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute((dist_topc_kernel<32, false, 1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<1>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute((dist_topc_kernel<64, false, 1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<1>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute((dist_topc_kernel<16, true, 1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<1>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute((dist_topc_kernel<16, false, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute((dist_topc_kernel<32, false, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute((dist_topc_kernel<64, false, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute((dist_topc_kernel<16, true, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, DistCfg<2>::SMEM_BYTES));
         TRY(preload_kernels());
         if (const char *o = getenv("B200KNN_OPT")) opt_flags = static_cast<unsigned>(atoi(o));
         if (const char *o = getenv("B200KNN_A_BUDGET_MB")) a_budget_mb = std::max(1, atoi(o));
@@ -145,6 +169,11 @@ struct Shard {
         if (const char *o = getenv("B200KNN_WIDE")) wide_mode = atoi(o);
         if (const char *o = getenv("B200KNN_COPY_THREADS")) copy_threads = std::max(1, atoi(o));
         if (const char *o = getenv("B200KNN_CENTER")) use_centering = atoi(o) != 0;
+        if (const char *o = getenv("B200KNN_KC")) kc_elems = std::max(0, atoi(o));
+        if (const char *o = getenv("B200KNN_PRECISION")) {
+            if (!strcmp(o, "bf16x3") || !strcmp(o, "1")) tier = 1;
+            else if (!strcmp(o, "tf32") || !strcmp(o, "2")) tier = 2;
+        }
         copy_threads = std::min<int>(copy_threads, std::max(1u, std::thread::hardware_concurrency()));
         const char *e = getenv("B200KNN_CTA_GROUP");
         if (e && (e[0] == '1' || e[0] == '2')) forced_cg = e[0] - '0';
@@ -215,6 +244,7 @@ struct Shard {
         x_bf.release();
         xnorm_bf.release();
         x_err.release();
+        x_lo.release(); x_tf.release(); xnorm_t.release(); x_err_t.release(); x_lonorm.release();
         centered = false;
     }
     void destroy() {
@@ -339,6 +369,46 @@ struct Shard {
                 static_cast<const float *>(src), mu, rows, ld, dim, kp, vec, dst, nbf, nex, maxbits, maxbits + 1);
         if (!on_stream) prof_end();
         CU_TRY(cudaGetLastError());
+        return B200KNN_OK;
+    }
+
+    // operands of the split / tf32 tiers (tiers.cuh); hi == nullptr: the BF16 tier has already written the hi rows
+    int launch_convert_tier(int t, const void *src, int dtype, int64_t rows, int64_t ld, int dim, int kp, __nv_bfloat16 *hi, __nv_bfloat16 *lo,
+                            float *tf, float *norm, float *err, float *lonorm, unsigned int *maxbits /* [3] */) {
+        const double *mu = centered ? col_mean.p : nullptr;
+        if (rows <= 0) return B200KNN_OK;
+        const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((rows + 7) / 8, static_cast<int64_t>(num_sms) * 8));
+        prof_begin(K_CONVERT);
+        if (t == 1) {
+            if (dtype == B200KNN_F64) convert_tier_kernel<double, 1><<<blocks, 256, 0, stream>>>(static_cast<const double *>(src), mu, rows, ld, dim, kp, hi, lo, nullptr, norm, err, lonorm, maxbits);
+            else convert_tier_kernel<float, 1><<<blocks, 256, 0, stream>>>(static_cast<const float *>(src), mu, rows, ld, dim, kp, hi, lo, nullptr, norm, err, lonorm, maxbits);
+        } else {
+            if (dtype == B200KNN_F64) convert_tier_kernel<double, 2><<<blocks, 256, 0, stream>>>(static_cast<const double *>(src), mu, rows, ld, dim, kp, nullptr, nullptr, tf, norm, err, nullptr, maxbits);
+            else convert_tier_kernel<float, 2><<<blocks, 256, 0, stream>>>(static_cast<const float *>(src), mu, rows, ld, dim, kp, nullptr, nullptr, tf, norm, err, nullptr, maxbits);
+        }
+        prof_end();
+        CU_TRY(cudaGetLastError());
+        return B200KNN_OK;
+    }
+    // pool operands of the handle's tier; called after the BF16 conversion of add() (which every tier keeps: the BF16
+    // rows are the hi part of the split tier, and ball membership always runs in BF16)
+    int convert_pool_tier(int dim, int kp) {
+        if (tier == 0 || n <= 0) return B200KNN_OK;
+        TRY(xnorm_t.ensure(n));
+        TRY(x_err_t.ensure(n));
+        CU_TRY(cudaMemsetAsync(scalars.p + 10, 0, 3 * sizeof(unsigned int), stream));
+        if (tier == 1) {
+            TRY(x_lo.ensure(static_cast<size_t>(n) * kp));
+            TRY(x_lonorm.ensure(n));
+            TRY(launch_convert_tier(1, x_raw, x_dtype, n, ld_x, dim, kp, nullptr, x_lo.p, nullptr, xnorm_t.p, x_err_t.p, x_lonorm.p, scalars.p + 10));
+            TRY(make_tmap(&tmap_xlo, x_lo.p, n, kp, BN));
+            TRY(make_tmap(&tmap_xlo128, x_lo.p, n, kp, BN / 2));
+        } else {
+            TRY(x_tf.ensure(static_cast<size_t>(n) * kp));
+            TRY(launch_convert_tier(2, x_raw, x_dtype, n, ld_x, dim, kp, nullptr, nullptr, x_tf.p, xnorm_t.p, x_err_t.p, nullptr, scalars.p + 10));
+            TRY(make_tmap(&tmap_xtf, x_tf.p, n, kp, BN, true));
+            TRY(make_tmap(&tmap_xtf128, x_tf.p, n, kp, BN / 2, true));
+        }
         return B200KNN_OK;
     }
 
@@ -476,8 +546,10 @@ struct Shard {
         return B200KNN_OK;
     }
 
-    template <int C, bool COLLECT>
-    int launch_dist(const Sched &s, const CUtensorMap &tmap_q, const DistParams &dp) {
+    // tier 0: (q, x, q, x); tier 1: (q_hi, x_hi, q_lo, x_lo); tier 2: the kind::tf32 flavour on (q_tf, x_tf)
+    template <int C, bool COLLECT, bool TF32>
+    int launch_dist_t(const Sched &s, const CUtensorMap &mq, const CUtensorMap &mx, const CUtensorMap &mx128, const CUtensorMap &mqlo,
+                      const CUtensorMap &mxlo, const CUtensorMap &mxlo128, const DistParams &dp) {
         if (s.cg == 2) {
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(s.grid);
@@ -491,12 +563,19 @@ struct Shard {
             at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
-            CU_TRY(cudaLaunchKernelEx(&cfg, dist_topc_kernel<C, COLLECT, 2>, tmap_q, tmap_x128, dp));
+            CU_TRY(cudaLaunchKernelEx(&cfg, dist_topc_kernel<C, COLLECT, 2, TF32>, mq, mx128, mqlo, mxlo128, dp));
         } else {
-            dist_topc_kernel<C, COLLECT, 1><<<s.grid, DIST_THREADS, DistCfg<1>::SMEM_BYTES, stream>>>(tmap_q, tmap_x, dp);
+            dist_topc_kernel<C, COLLECT, 1, TF32><<<s.grid, DIST_THREADS, DistCfg<1>::SMEM_BYTES, stream>>>(mq, mx, mqlo, mxlo, dp);
         }
         CU_TRY(cudaGetLastError());
         return B200KNN_OK;
+    }
+    // t: tier of this launch; tmap_q / tmap_qlo: the query operands of that tier (lo only for tier 1)
+    template <int C, bool COLLECT>
+    int launch_dist(const Sched &s, const CUtensorMap &tmap_q, const DistParams &dp, int t = 0, const CUtensorMap *tmap_qlo = nullptr) {
+        if (t == 1) return launch_dist_t<C, COLLECT, false>(s, tmap_q, tmap_x, tmap_x128, *tmap_qlo, tmap_xlo, tmap_xlo128, dp);
+        if (t == 2) return launch_dist_t<C, COLLECT, true>(s, tmap_q, tmap_xtf, tmap_xtf128, tmap_q, tmap_xtf, tmap_xtf128, dp);
+        return launch_dist_t<C, COLLECT, false>(s, tmap_q, tmap_x, tmap_x128, tmap_q, tmap_x, tmap_x128, dp);
     }
 
     // ------------------------------------------------------------------ exact scan of a query subset
@@ -598,12 +677,29 @@ struct Shard {
         return B200KNN_OK;
     }
 
-    DistParams base_dist_params(int64_t nq, int kp, const Sched &s, const WorkItem *items) const {
+    // accumulation geometry of a tier: K blocks per segment, total, per unit (chunked accumulation only pays for long rows:
+    // at least two full units), and the (k_unit, n_units) the error model charges
+    struct AccGeom { int nkb_seg, num_kb, kb_per_unit, k_unit, n_units; };
+    AccGeom acc_geom(int kp, int t) const {
+        AccGeom g{};
+        const int kelems = t == 2 ? BK / 2 : BK;
+        g.nkb_seg = (kp + kelems - 1) / kelems;
+        g.num_kb = t == 1 ? 3 * g.nkb_seg : g.nkb_seg;
+        const int kbu = kc_elems > 0 ? std::max(1, kc_elems / kelems) : 0;
+        g.kb_per_unit = (kbu > 0 && g.num_kb >= 2 * kbu) ? kbu : g.num_kb;
+        g.n_units = (g.num_kb + g.kb_per_unit - 1) / g.kb_per_unit;
+        g.k_unit = std::min(g.kb_per_unit, g.num_kb) * kelems;
+        return g;
+    }
+    DistParams base_dist_params(int64_t nq, int kp, const Sched &s, const WorkItem *items, int t = 0) const {
         DistParams dp{};
-        dp.xnorm = xnorm_bf.p;
+        const AccGeom g = acc_geom(kp, t);
+        dp.xnorm = t ? xnorm_t.p : xnorm_bf.p;
         dp.n = static_cast<int>(n);
         dp.nq = static_cast<int>(nq);
-        dp.num_kb = (kp + BK - 1) / BK;
+        dp.num_kb = g.num_kb;
+        dp.nkb_seg = g.nkb_seg;
+        dp.kb_per_unit = g.kb_per_unit;
         dp.items = items;
         dp.nrounds = s.nrounds;
         dp.workers = s.workers;
@@ -704,16 +800,31 @@ struct Shard {
     int tmap_q2_kp = -1;
     int enqueue_second_pass(const void *d_query, int q_dtype, int64_t ld_q, int64_t nq_cap, int dim, int kp, int kk, unsigned flags,
                             int32_t *d_out_idx, double *d_out_dist, int q_offset, bool allow_short, const QueryPull *qpull = nullptr) {
-        TRY(q_bf2.ensure(static_cast<size_t>(nq_cap) * kp));
+        const int t = cur_tier;                // the collection pass runs in the tier of the pass that found the query uncertified
+        const int kp_plan = t ? 2 * kp : kp;   // operand bytes per row, in BF16-element units (L2 budget of the schedule)
+        if (t != 2) TRY(q_bf2.ensure(static_cast<size_t>(nq_cap) * kp));
+        if (t == 1) TRY(q_lo2.ensure(static_cast<size_t>(nq_cap) * kp));
+        if (t == 2) TRY(q_tf2.ensure(static_cast<size_t>(nq_cap) * kp));
         TRY(coll_count.ensure(nq_cap));
         TRY(coll_idx.ensure(static_cast<size_t>(nq_cap) * COLLECT_CAP));
-        if (!sched2.matches(nq_cap, n, kp, 1 << 20)) TRY(plan(sched2, nq_cap, kp, 1 << 20));
+        if (!sched2.matches(nq_cap, n, kp_plan, 1 << 20)) TRY(plan(sched2, nq_cap, kp_plan, 1 << 20));
         const Sched &s = sched2;
         const int max_rounds = (s.qt + s.qg - 1) / s.qg;
         TRY(sched_items2.ensure(static_cast<size_t>(max_rounds) * s.workers));
-        if (tmap_q2_ptr != q_bf2.p || tmap_q2_rows != nq_cap || tmap_q2_kp != kp) {
-            TRY(make_tmap(&tmap_q2, q_bf2.p, nq_cap, kp, BM));
-            tmap_q2_ptr = q_bf2.p; tmap_q2_rows = nq_cap; tmap_q2_kp = kp;
+        CUtensorMap tmap_q2lo;
+        if (t == 0) {
+            if (tmap_q2_ptr != q_bf2.p || tmap_q2_rows != nq_cap || tmap_q2_kp != kp) {
+                TRY(make_tmap(&tmap_q2, q_bf2.p, nq_cap, kp, BM));
+                tmap_q2_ptr = q_bf2.p; tmap_q2_rows = nq_cap; tmap_q2_kp = kp;
+            }
+        } else {
+            tmap_q2_ptr = nullptr;
+            if (t == 1) {
+                TRY(make_tmap(&tmap_q2, q_bf2.p, nq_cap, kp, BM));
+                TRY(make_tmap(&tmap_q2lo, q_lo2.p, nq_cap, kp, BM));
+            } else {
+                TRY(make_tmap(&tmap_q2, q_tf2.p, nq_cap, kp, BM, true));
+            }
         }
         const int *count_dev = reinterpret_cast<const int *>(scalars.p + 4);
         TRY(stream_sync.ensure(static_cast<size_t>(max_rounds) * s.workers));
@@ -732,15 +843,26 @@ struct Shard {
         plan_pass_kernel<<<1, 256, 0, stream>>>(pp);
         prof_end();
         prof_begin(K_SCAN);
-        gather_rows_kernel<<<num_sms * 4, 256, 0, stream>>>(cur_q_bf, uncert_list.p, count_dev, kp, q_bf2.p);
+        if (t != 2)
+            gather_rows_kernel<<<num_sms * 4, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(cur_q_bf), uncert_list.p, count_dev, kp / 8,
+                                                                reinterpret_cast<uint4 *>(q_bf2.p));
+        if (t == 1)
+            gather_rows_kernel<<<num_sms * 4, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(cur_q_lo), uncert_list.p, count_dev, kp / 8,
+                                                                reinterpret_cast<uint4 *>(q_lo2.p));
+        if (t == 2)
+            gather_rows_kernel<<<num_sms * 4, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(cur_q_tf), uncert_list.p, count_dev, kp / 4,
+                                                                reinterpret_cast<uint4 *>(q_tf2.p));
         prof_end();
         CU_TRY(cudaGetLastError());
+        const AccGeom ag = acc_geom(kp, t);
         DistParams dp{};
-        dp.xnorm = xnorm_bf.p;
+        dp.xnorm = t ? xnorm_t.p : xnorm_bf.p;
         dp.n = static_cast<int>(n);
         dp.nq = static_cast<int>(nq_cap);
         dp.nq_dev = count_dev;
-        dp.num_kb = (kp + BK - 1) / BK;
+        dp.num_kb = ag.num_kb;
+        dp.nkb_seg = ag.nkb_seg;
+        dp.kb_per_unit = ag.kb_per_unit;
         dp.items = sched_items2.p;
         dp.nrounds = max_rounds;
         dp.workers = s.workers;
@@ -755,7 +877,7 @@ struct Shard {
         dp.coll_idx = coll_idx.p;
         dp.coll_cap = COLLECT_CAP;
         prof_begin(K_SCAN);
-        const int rc2 = launch_dist<16, true>(s, tmap_q2, dp);
+        const int rc2 = launch_dist<16, true>(s, tmap_q2, dp, t, &tmap_q2lo);
         prof_end();
         TRY(rc2);
         CollectRerankParams cp{};
@@ -796,21 +918,45 @@ struct Shard {
                     int32_t *d_out_idx, double *d_out_dist, const QuerySide *pre, int q_offset, const ShardHook *hook) {
         // query side: BF16 rows + norms, either converted now or already there (self-kNN: the pool's own, converted by
         // add(); row-sharded protocol: broadcast by the ranks that converted them)
-        const __nv_bfloat16 *qb;
-        const float *qn, *qe;
+        // The pass runs in the handle's tier when the query operands of that tier are at hand (converted here, or the
+        // pool's own for self-kNN); BF16 slices broadcast by the row-sharded protocol run in BF16.
+        const int t = (tier != 0 && (!pre || (tier == 1 ? pre->lo != nullptr : pre->tf != nullptr))) ? tier : 0;
+        cur_tier = t;
+        const int kp_plan = t ? 2 * kp : kp;
+        const __nv_bfloat16 *qb = nullptr, *qlo = nullptr;
+        const float *qtf = nullptr, *qn, *qe, *qln = nullptr;
         if (pre) {
-            qb = pre->bf; qn = pre->norm; qe = pre->err;
-        } else {
+            qb = pre->bf; qn = pre->norm; qe = pre->err; qlo = pre->lo; qtf = pre->tf; qln = pre->lonorm;
+        } else if (t == 0) {
             TRY(q_bf.ensure(static_cast<size_t>(nq) * kp));
             TRY(qnorm_bf.ensure(nq));
             TRY(q_err.ensure(nq));
             TRY(launch_convert(d_query, q_dtype, nq, ld_q, dim, kp, q_bf.p, qnorm_bf.p, q_err.p, scalars.p + 2));
             qb = q_bf.p; qn = qnorm_bf.p; qe = q_err.p;
+        } else {
+            TRY(qnorm_t.ensure(nq));
+            TRY(q_err_t.ensure(nq));
+            if (t == 1) {
+                TRY(q_bf.ensure(static_cast<size_t>(nq) * kp));
+                TRY(q_lo.ensure(static_cast<size_t>(nq) * kp));
+                TRY(q_lonorm.ensure(nq));
+                TRY(launch_convert_tier(1, d_query, q_dtype, nq, ld_q, dim, kp, q_bf.p, q_lo.p, nullptr, qnorm_t.p, q_err_t.p, q_lonorm.p, scalars.p + 13));
+                qb = q_bf.p; qlo = q_lo.p; qln = q_lonorm.p;
+            } else {
+                TRY(q_tf.ensure(static_cast<size_t>(nq) * kp));
+                TRY(launch_convert_tier(2, d_query, q_dtype, nq, ld_q, dim, kp, nullptr, nullptr, q_tf.p, qnorm_t.p, q_err_t.p, nullptr, scalars.p + 13));
+                qtf = q_tf.p;
+            }
+            qn = qnorm_t.p; qe = q_err_t.p;
         }
         cur_q_bf = qb;
-        CUtensorMap tmap_q;
-        TRY(make_tmap(&tmap_q, qb, nq, kp, BM));
-        if (!sched1.matches(nq, n, kp, MAX_KEYS / C)) TRY(plan(sched1, nq, kp, MAX_KEYS / C));
+        cur_q_lo = qlo;
+        cur_q_tf = qtf;
+        CUtensorMap tmap_q, tmap_qlo;
+        if (t == 2) TRY(make_tmap(&tmap_q, qtf, nq, kp, BM, true));
+        else TRY(make_tmap(&tmap_q, qb, nq, kp, BM));
+        if (t == 1) TRY(make_tmap(&tmap_qlo, qlo, nq, kp, BM));
+        if (!sched1.matches(nq, n, kp_plan, MAX_KEYS / C)) TRY(plan(sched1, nq, kp_plan, MAX_KEYS / C));
         const Sched &s = sched1;
         {   // the schedule is written on the device (and every counter of the pass zeroed) by one tiny kernel: no
             // host-to-device copy, no memset — nothing of a pass can queue behind a query upload on a copy engine
@@ -833,11 +979,11 @@ struct Shard {
         }
         TRY(cand_s.ensure(static_cast<size_t>(nq) * s.max_slots * C));
         TRY(cand_i.ensure(static_cast<size_t>(nq) * s.max_slots * C));
-        DistParams dp = base_dist_params(nq, kp, s, sched_items.p);
+        DistParams dp = base_dist_params(nq, kp, s, sched_items.p, t);
         dp.cand_s = cand_s.p;
         dp.cand_i = cand_i.p;
         prof_begin(K_DISTANCE, 2.0 * static_cast<double>(nq) * static_cast<double>(n) * dim);
-        const int rc1 = launch_dist<C, false>(s, tmap_q, dp);
+        const int rc1 = launch_dist<C, false>(s, tmap_q, dp, t, &tmap_qlo);
         prof_end();
         TRY(rc1);
 
@@ -861,9 +1007,17 @@ struct Shard {
         rp.flags = flags;
         rp.qnorm_bf = qn;
         rp.q_err = qe;
-        rp.max_xnorm_bf_bits = scalars.p;
-        rp.max_x_err_bits = scalars.p + 1;
+        rp.max_xnorm_bf_bits = t ? scalars.p + 10 : scalars.p;
+        rp.max_x_err_bits = t ? scalars.p + 11 : scalars.p + 1;
         rp.kp = kp;
+        {
+            const AccGeom ag = acc_geom(kp, t);
+            rp.tier = t;
+            rp.k_unit = ag.k_unit;
+            rp.n_units = ag.n_units;
+            rp.q_lonorm = qln;
+            rp.max_x_lonorm_bits = scalars.p + 12;
+        }
         rp.out_idx = d_out_idx;
         rp.out_dist = d_out_dist;
         rp.uncert_count = reinterpret_cast<int *>(scalars.p + 4);
@@ -1035,13 +1189,18 @@ struct Shard {
     int reserve_pass(int64_t nq, int kp, int kk, bool pre) {
         if (nq <= 0 || kk > 32) return B200KNN_OK;
         const int C = kk <= 4 ? 16 : (kk <= 16 ? 32 : 64);
+        const int t = pre ? 0 : tier;
+        const int kp_plan = t ? 2 * kp : kp;
         if (!pre) {
-            TRY(q_bf.ensure(static_cast<size_t>(nq) * kp));
+            if (t != 2) TRY(q_bf.ensure(static_cast<size_t>(nq) * kp));
             TRY(qnorm_bf.ensure(nq));
             TRY(q_err.ensure(nq));
+            if (t) { TRY(qnorm_t.ensure(nq)); TRY(q_err_t.ensure(nq)); }
+            if (t == 1) { TRY(q_lo.ensure(static_cast<size_t>(nq) * kp)); TRY(q_lonorm.ensure(nq)); TRY(q_lo2.ensure(static_cast<size_t>(nq) * kp)); }
+            if (t == 2) { TRY(q_tf.ensure(static_cast<size_t>(nq) * kp)); TRY(q_tf2.ensure(static_cast<size_t>(nq) * kp)); }
         }
         Sched a;
-        TRY(plan(a, nq, kp, MAX_KEYS / C));
+        TRY(plan(a, nq, kp_plan, MAX_KEYS / C));
         TRY(sched_items.ensure(a.items.size()));
         TRY(sched_slots.ensure(a.slots_per_qtile.size()));
         TRY(stream_sync.ensure(static_cast<size_t>(a.nrounds) * a.max_slots));
@@ -1054,7 +1213,7 @@ struct Shard {
         TRY(coll_count.ensure(nq));
         TRY(coll_idx.ensure(static_cast<size_t>(nq) * COLLECT_CAP));
         Sched b;
-        TRY(plan(b, nq, kp, 1 << 20));
+        TRY(plan(b, nq, kp_plan, 1 << 20));
         const int max_rounds = (b.qt + b.qg - 1) / b.qg;
         TRY(sched_items2.ensure(static_cast<size_t>(max_rounds) * b.workers));
         TRY(stream_sync.ensure(static_cast<size_t>(max_rounds) * b.workers));

@@ -33,6 +33,7 @@ _lib = None
 
 F64, F32 = 0, 1
 FLAG_SQUARED, FLAG_NO_CERTIFY, FLAG_FORCE_SCAN = 1, 2, 4
+PRECISION_TIERS = {"bf16": 0, "bf16x3": 1, "tf32": 2}
 
 
 class B200KNNError(RuntimeError):
@@ -88,6 +89,8 @@ def load_library(path=None):
     lib.b200knn_merge_topk_device.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp]
     lib.b200knn_set_profiling.restype = i32
     lib.b200knn_set_profiling.argtypes = [vp, i32]
+    lib.b200knn_set_precision.restype = i32
+    lib.b200knn_set_precision.argtypes = [vp, i32]
     lib.b200knn_get_stats.restype = i32
     lib.b200knn_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.b200knn_reset_stats.restype = i32
@@ -190,10 +193,12 @@ def _draw_unit_directions(rows, dim):
 class DCI(object):
     """Exact k-nearest-neighbour index with the reference `DCI` interface (dci.py:61-340)."""
 
-    def __init__(self, dim, num_comp_indices=2, num_simp_indices=7, devices=None, strict=False):
+    def __init__(self, dim, num_comp_indices=2, num_simp_indices=7, devices=None, strict=False, precision=None):
         """dim, num_comp_indices, num_simp_indices: as dci.py:63.  Extensions (keyword-only in spirit):
-        devices — GPU ids to row-shard the pool over (None: $B200KNN_DEVICES or the current device);
-        strict  — refuse non-float64 data like the reference (dci.py:116-117)."""
+        devices   — GPU ids to row-shard the pool over (None: $B200KNN_DEVICES or the current device);
+        strict    — refuse non-float64 data like the reference (dci.py:116-117);
+        precision — tier of the tensor pass: 'bf16' (default), 'bf16x3' (split BF16, three MMAs) or 'tf32'; results are
+                    exact in every tier, the tier only decides how much exact re-ranking the tensor scores leave."""
         self._dim = int(dim)
         self._num_comp_indices = num_comp_indices
         self._num_simp_indices = num_simp_indices
@@ -209,6 +214,8 @@ class DCI(object):
         handle = ctypes.c_void_p()
         _check(self._lib.b200knn_create(self._dim, n_dev, ids, ctypes.byref(handle)))
         self._handle = handle
+        if precision is not None:
+            self.set_precision(precision)
         # Exact search uses no projections; the property is kept shape-correct (m*L x dim, float64) and
         # writable-when-empty because callers may read or pin it (dci.py:69,93-105; py_dci.c:299-302).
         self._proj_vec = _draw_unit_directions(num_comp_indices * num_simp_indices, self._dim)
@@ -267,6 +274,11 @@ class DCI(object):
         s = Stats()
         _check(self._lib.b200knn_get_stats(self._handle, ctypes.byref(s)))
         return s.as_dict()
+
+    def set_precision(self, precision):
+        """'bf16' | 'bf16x3' | 'tf32' (or the tier number): b200knn_set_precision."""
+        tier = PRECISION_TIERS[precision] if isinstance(precision, str) else int(precision)
+        _check(self._lib.b200knn_set_precision(self._handle, tier))
 
     def set_profiling(self, on):
         _check(self._lib.b200knn_set_profiling(self._handle, int(bool(on))))

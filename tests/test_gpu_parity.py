@@ -405,44 +405,151 @@ def _bf16_round(a):
     return u.astype(np.uint32).view(np.float32).astype(np.float64)
 
 
-@pytest.mark.parametrize("kind,n,q,d", [("gauss", 20000, 256, 3072), ("image", 20000, 256, 3072), ("relu", 30000, 512, 2048),
-                                        ("gauss", 6000, 130, 5000)])
-def test_tensor_scores_within_the_certified_error_model(lib, kind, n, q, d):
-    """The certificate is only as good as its error model.  Pull the raw tensor-core scores of the shortlists and
-    check them against float64 arithmetic on the BF16-rounded (mean-centred) inputs: |s~_gpu - (||x~||^2 - 2 q~.x~)| must stay
-    below the eps_acc the kernels assume (csrc/rerank.cuh make_err_model), and every kept score must bracket the true
-    distance through the exact perturbation norms ||q-q~||, ||x-x~||."""
+def _tf32_round(a):
+    """Round-to-nearest (ties away from zero) float32 -> tf32 (10 explicit mantissa bits): cvt.rna.tf32.f32."""
+    f = np.ascontiguousarray(a, dtype=np.float32)
+    u = f.view(np.uint32).astype(np.uint64)
+    u = (u + 0x1000) & 0xFFFFE000
+    return u.astype(np.uint32).view(np.float32).astype(np.float64)
+
+
+KC = 4096          # $B200KNN_KC default: K elements per tensor-core accumulation unit
+
+
+def _acc_geom(kp, tier):
+    """Shard::acc_geom: (k_unit, n_units) the error model charges."""
+    kelems = 32 if tier == 2 else 64
+    nkb = -(-kp // kelems) * (3 if tier == 1 else 1)
+    kbu = KC // kelems
+    per = kbu if nkb >= 2 * kbu else nkb
+    return min(per, nkb) * kelems, -(-nkb // per)
+
+
+@pytest.mark.parametrize("kind,n,q,d,tier", [
+    ("gauss", 20000, 256, 3072, "bf16"), ("image", 20000, 256, 3072, "bf16"), ("relu", 30000, 512, 2048, "bf16"),
+    ("gauss", 6000, 130, 5000, "bf16"),
+    ("gauss", 3000, 130, 49152, "bf16"),          # long rows: K-chunked accumulation (12 units of 4096)
+    ("mixed", 5000, 130, 12288, "bf16"),          # magnitudes spread over six decades inside every row
+    ("gauss", 20000, 256, 3072, "bf16x3"), ("mixed", 5000, 130, 12288, "bf16x3"), ("gauss", 3000, 130, 49152, "bf16x3"),
+    ("gauss", 20000, 256, 3072, "tf32"), ("image", 6000, 130, 9000, "tf32")])
+def test_tensor_scores_within_the_certified_error_model(lib, kind, n, q, d, tier):
+    """The certificate is only as good as its error model (EMPIRICALLY validated, not proven: the accumulation model of the
+    tensor core is an assumption).  Pull the raw tensor-core scores of the shortlists and check them against float64
+    arithmetic on the rounded (mean-centred) operands of the tier: |s~_gpu - s~_exact| must stay below the eps_acc the
+    kernels assume (csrc/rerank.cuh make_err_model), and every kept score must bracket the true distance through the
+    exact perturbation norms ||q-q^||, ||x-x^||."""
     from inclusivegan_b200 import DCI
-    x, y = make(kind, n, q, d, seed=d + n)
-    db = DCI(d)
+    if kind == "mixed":
+        rng = np.random.default_rng(d + n)
+        scale = 10.0 ** rng.uniform(-3, 3, d)
+        x = rng.standard_normal((n, d)) * scale
+        y = rng.standard_normal((q, d)) * scale
+    else:
+        x, y = make(kind, n, q, d, seed=d + n)
+    t = {"bf16": 0, "bf16x3": 1, "tf32": 2}[tier]
+    db = DCI(d, precision=tier)
     db.add(x)
     idx, dist = db.query_arrays(y, 1, flags=FLAG_NO_CERTIFY)
     scores, rows = db.debug_shortlists()
     assert scores.shape[0] == q and rows.max() < n
     mu = x.mean(axis=0)                                        # the library subtracts the pool mean before rounding
     xc, yc = x - mu, y - mu
-    xb, yb = _bf16_round(xc), _bf16_round(yc)
-    xn = np.einsum("ij,ij->i", xb, xb)
-    qn = np.einsum("ij,ij->i", yb, yb)
+    if t == 2:
+        xh, yh = _tf32_round(xc), _tf32_round(yc)
+        xl = yl = None
+        xr, yr = xh, yh
+    else:
+        xh, yh = _bf16_round(xc), _bf16_round(yc)
+        if t == 1:
+            xl, yl = _bf16_round(xc - xh), _bf16_round(yc - yh)
+            xr, yr = xh + xl, yh + yl
+        else:
+            xl = yl = None
+            xr, yr = xh, yh
+    xn = np.einsum("ij,ij->i", xr, xr)
+    qn = np.einsum("ij,ij->i", yr, yr)
     kp = (d + 7) // 8 * 8
+    k_unit, n_units = _acc_geom(kp, t)
     worst_ratio = 0.0
-    err_q = np.linalg.norm(yc - yb, axis=1)
-    err_x_max = np.linalg.norm(xc - xb, axis=1).max()
+    err_q = np.linalg.norm(yc - yr, axis=1)
+    err_x_max = np.linalg.norm(xc - xr, axis=1).max()
+    xl_max = np.linalg.norm(xl, axis=1).max() if t == 1 else 0.0
     for i in range(0, q, 7):                                   # a spread of query rows
         valid = rows[i] >= 0
         r = rows[i][valid]
         s_gpu = scores[i][valid].astype(np.float64)
-        s_ref = xn[r] - 2.0 * (xb[r] @ yb[i])
-        eps = (kp + 8.0) * 2.4e-7 * np.sqrt(qn[i] * xn.max()) * 1.001 + (kp / 16.0 + 8.0) * 1.2e-7 * (xn.max() + qn[i])
-        worst_ratio = max(worst_ratio, float(np.max(np.abs(s_gpu - s_ref)) / eps))
+        if t == 1:                                             # what the three MMAs compute: hi.hi + hi.lo + lo.hi
+            ql = np.linalg.norm(yl[i])
+            s_ref = xn[r] - 2.0 * (xh[r] @ yh[i] + xl[r] @ yh[i] + xh[r] @ yl[i])
+            qh, xhh = np.sqrt(qn[i]) + ql, np.sqrt(xn.max()) + xl_max
+            mag = np.sqrt((2 * qh * qh + ql * ql) * (2 * xhh * xhh + xl_max * xl_max))
+            extra = 2.0 * ql * xl_max * (1 + 1e-6)
+        else:
+            s_ref = xn[r] - 2.0 * (xr[r] @ yr[i])
+            mag = np.sqrt(qn[i] * xn.max())
+            extra = 0.0
+        eps_mma = (k_unit + 8.0) * 2.4e-7 * mag * 1.001 + n_units * 1.2e-7 * mag
+        eps_mma += (kp / 16.0 + 8.0) * 1.2e-7 * (xn.max() + qn[i]) if t == 0 else 4.8e-7 * (xn.max() + qn[i] + 2.0 * mag)
+        worst_ratio = max(worst_ratio, float(np.max(np.abs(s_gpu - s_ref)) / eps_mma))
         # bracket of the true distance (the inequality the pruning rule and the certificate rely on)
+        eps = eps_mma + extra
         d_true = np.linalg.norm(x[r] - y[i], axis=1)
         eta = err_q[i] + err_x_max
         lo = np.sqrt(np.maximum(s_gpu + qn[i] - eps, 0.0)) - eta
         hi = np.sqrt(np.maximum(s_gpu + qn[i] + eps, 0.0)) + eta
         assert np.all(lo <= d_true * (1 + 1e-12)) and np.all(d_true <= hi * (1 + 1e-12))
     assert worst_ratio < 1.0, "tensor-core accumulation error exceeds the modelled eps_acc (ratio %.3f)" % worst_ratio
-    print("max |s_gpu - s_ref| / eps_acc = %.4f" % worst_ratio)
+    print("%s %s d=%d: max |s_gpu - s_ref| / eps_acc = %.4f (k_unit %d, units %d)" % (tier, kind, d, worst_ratio, k_unit, n_units))
+
+
+@pytest.mark.parametrize("tier", ["bf16x3", "tf32"])
+@pytest.mark.parametrize("kind,n,q,d,k,dtype", [("gauss", 20011, 300, 256, 10, np.float64), ("cluster", 15000, 700, 3072, 1, np.float32),
+                                               ("image", 9001, 260, 9000, 3, np.float32), ("lowrank", 10000, 100, 5000, 10, np.float64)])
+def test_precision_tiers_are_exact(lib, tier, kind, n, q, d, k, dtype):
+    """the split-BF16 (three MMAs) and TF32 flavours of the tensor pass answer exactly like the BF16 one —
+    bit-identical results (the exact re-rank and its canonical summation order do not depend on the tier) — and leave
+    fewer queries to the second pass."""
+    from inclusivegan_b200 import DCI
+    x, y = make(kind, n, q, d, seed=n + d, dtype=dtype)
+    base = DCI(d)
+    base.add(x)
+    i0, d0 = check(base, x.astype(np.float64), y.astype(np.float64), k) if dtype == np.float64 else base.query_arrays(y, k)
+    db = DCI(d, precision=tier)
+    db.add(x)
+    i1, d1 = db.query_arrays(y, k)
+    ri, rd = ko.exact_knn_numpy(x, y, k)
+    ok, msg = ko.compare_knn(i1, d1, ri, rd, x.astype(np.float64), y.astype(np.float64))
+    assert ok, msg
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+    assert db.stats()["uncertified"] <= base.stats()["uncertified"]
+    # self-kNN uses the pool's own tier operands
+    si, sd = db.query_self_arrays(min(k + 1, 4))
+    assert np.array_equal(si[:, 0], np.arange(n, dtype=np.int32)) and np.all(sd[:, 0] == 0)
+    # switching the tier of a loaded index rebuilds its operands
+    base.set_precision(tier)
+    i2, d2 = base.query_arrays(y, k)
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+
+
+def test_unstructured_long_rows_stay_on_the_tensor_path(lib):
+    """VERDICT r1 / SURVEY 8f-4: i.i.d. Gaussian rows at d = 49152 — every pairwise distance within a fraction of a percent
+    of every other, BF16 rounding moves a point further than the neighbour gaps.  Round 1 answered these on the exact
+    float64 CUDA-core scan (~1k queries/s).  With the split-BF16 tier (rounding 2^-17) and K-chunked accumulation (error
+    bound per 4096 products instead of per 49152) the tensor path certifies them: nothing falls to the scan."""
+    from inclusivegan_b200 import DCI
+    rng = np.random.default_rng(4915)
+    n, q, d = 20000, 512, 49152
+    x = rng.standard_normal((n, d), dtype=np.float32)
+    y = rng.standard_normal((q, d), dtype=np.float32)
+    db = DCI(d, precision="bf16x3")
+    db.add(x)
+    idx, dist = db.query_arrays(y, 1)
+    ri, rd = ko.exact_knn_numpy(x, y, 1, qblock=512)
+    ok, msg = ko.compare_knn(idx, dist, ri, rd)
+    assert ok, msg
+    st = db.stats()
+    assert st["exact_scanned"] == 0, st
+    print("bf16x3, i.i.d. d=49152: %d of %d queries needed the second (collection) pass, none the exact scan" % (st["uncertified"], q))
 
 
 # ------------------------------------------------------------------------------------------------ C ABI corner cases
