@@ -23,6 +23,23 @@ __device__ __forceinline__ void load8<float>(const float *p, double (&d)[8]) {
     d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w; d[4] = v1.x; d[5] = v1.y; d[6] = v1.z; d[7] = v1.w;
 }
 
+// 256-bit flavours (LDG.256, sm_100): one full 32-byte sector per lane and request — rows must be 32-byte aligned
+template <typename T>
+__device__ __forceinline__ void load8_wide(const T *p, double (&d)[8]);
+template <>
+__device__ __forceinline__ void load8_wide<double>(const double *p, double (&d)[8]) {
+    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(d[0]), "=d"(d[1]), "=d"(d[2]), "=d"(d[3]) : "l"(p));
+    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(d[4]), "=d"(d[5]), "=d"(d[6]), "=d"(d[7]) : "l"(p + 4));
+}
+template <>
+__device__ __forceinline__ void load8_wide<float>(const float *p, double (&d)[8]) {
+    float f[8];
+    asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "l"(p));
+#pragma unroll
+    for (int i = 0; i < 8; i++) d[i] = f[i];
+}
+
 // 8 doubles through the read-only cached path (the column means: 8*dim bytes, L1/L2 resident)
 __device__ __forceinline__ void load8_cached(const double *p, double (&d)[8]) {
     const double2 *p2 = reinterpret_cast<const double2 *>(p);
@@ -60,7 +77,7 @@ __global__ void scale_kernel(double *__restrict__ v, int dim, double f) {
 // rounded values) and err = ||(x - mu) - x~|| rounded up - the EXACT size of the rounding perturbation, which is what
 // the exactness certificate needs (a worst-case 2^-9 ||x|| bound is ~2.5x looser).  Grid-wide maxima of both are kept
 // as float bit patterns (non-negative floats order like unsigned ints).
-// vec != 0 requires: dim % 8 == 0 (so kp == dim), src rows 16-byte aligned.
+// vec != 0 requires: dim % 8 == 0 (so kp == dim), src rows 16-byte aligned; vec == 2: 32-byte aligned (256-bit loads).
 template <typename T>
 __global__ void __launch_bounds__(256)
 convert_norm_kernel(const T *__restrict__ src, const double *__restrict__ mu, int64_t n, int64_t ld, int dim, int kp, int vec,
@@ -76,24 +93,30 @@ convert_norm_kernel(const T *__restrict__ src, const double *__restrict__ mu, in
         double er = 0.0;      // sum of squares of (x - x~)
         if (vec) {
             const int groups = dim >> 3;
-            // two 8-element groups per lane per step: all loads of a step are issued before the first use
+            // NG 8-element groups per lane per step: all loads of a step are issued before the first use (NG x 64 bytes of a
+            // float64 row in flight per lane; the means come from L1/L2)
+            constexpr int NG = sizeof(T) == 8 ? 3 : 2;      // (float rows: three groups cost a third resident block, ncu: 65 % vs 85 % of copy peak)
             int g = lane;
-            for (; g + 32 < groups; g += 64) {
-                double v[2][8];
-                load8<T>(s + (g << 3), v[0]);
-                load8<T>(s + ((g + 32) << 3), v[1]);
-                if (mu) {
-                    double m0[8], m1[8];
-                    load8_cached(mu + (g << 3), m0);
-                    load8_cached(mu + ((g + 32) << 3), m1);
+            for (; g + 32 * (NG - 1) < groups; g += 32 * NG) {
+                double v[NG][8];
+                if (vec == 2) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        v[0][i] -= m0[i];
-                        v[1][i] -= m1[i];
+                    for (int h = 0; h < NG; h++) load8_wide<T>(s + ((g + 32 * h) << 3), v[h]);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < NG; h++) load8<T>(s + ((g + 32 * h) << 3), v[h]);
+                }
+                if (mu) {
+#pragma unroll
+                    for (int h = 0; h < NG; h++) {
+                        double m0[8];
+                        load8_cached(mu + ((g + 32 * h) << 3), m0);
+#pragma unroll
+                        for (int i = 0; i < 8; i++) v[h][i] -= m0[i];
                     }
                 }
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
+                for (int h = 0; h < NG; h++) {
                     __nv_bfloat162 b[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
@@ -163,8 +186,10 @@ convert_norm_kernel(const T *__restrict__ src, const double *__restrict__ mu, in
         mx_er = fmaxf(mx_er, erf);
     }
     if (lane == 0) {
-        if (mx_bf > 0.f) atomicMax(max_norm_bf_bits, __float_as_uint(mx_bf));
-        if (mx_er > 0.f) atomicMax(max_err_bits, __float_as_uint(mx_er));
+        // (read first: after the first wave almost every warp finds a larger maximum already there and skips the atomic —
+        // tens of thousands of same-address atomics would otherwise serialise at the end of a short launch)
+        if (mx_bf > 0.f && __float_as_uint(mx_bf) > *reinterpret_cast<volatile unsigned int *>(max_norm_bf_bits)) atomicMax(max_norm_bf_bits, __float_as_uint(mx_bf));
+        if (mx_er > 0.f && __float_as_uint(mx_er) > *reinterpret_cast<volatile unsigned int *>(max_err_bits)) atomicMax(max_err_bits, __float_as_uint(mx_er));
     }
 }
 
