@@ -297,8 +297,8 @@ static int add_impl(b200knn_index *ix, const void *data, int dtype, int64_t n, i
         const int64_t rows = r1 - r0;
         if (rows <= 0) { s.n = 0; return B200KNN_OK; }
         CU_TRY(cudaSetDevice(s.device));
-        void *d_rows = nullptr;
-        CU_TRY(cudaMalloc(&d_rows, static_cast<size_t>(rows) * ix->dim * esz));
+        TRY(s.x_store.ensure(static_cast<size_t>(rows) * ix->dim * esz));
+        void *d_rows = s.x_store.p;
         int r = s.attach_pool(d_rows, true, dtype, rows, ix->dim, ix->dim, ix->kp, r0);
         if (r != B200KNN_OK) return r;
         const char *src = static_cast<const char *>(data) + static_cast<size_t>(r0) * ld * esz;
@@ -497,8 +497,8 @@ int b200knn_exchange_add(b200knn_exchange *ex, b200knn_index *ix, const void *da
     Shard &s = ix->shards[0];
     CU_TRY(cudaSetDevice(s.device));
     const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
-    void *d_rows = nullptr;
-    CU_TRY(cudaMalloc(&d_rows, static_cast<size_t>(n) * ix->dim * esz));
+    TRY(s.x_store.ensure(static_cast<size_t>(n) * ix->dim * esz));
+    void *d_rows = s.x_store.p;
     int rc = s.attach_pool(d_rows, true, dtype, n, ix->dim, ix->dim, ix->kp, index_base);      // the shard owns d_rows from here
     if (rc == B200KNN_OK) rc = s.upload_rows(d_rows, static_cast<const char *>(data), n, ix->dim * esz, ld * esz, s.stream);
     if (rc == B200KNN_OK) rc = ex_finish_add(ex, s, ix->dim, ix->kp);
@@ -674,8 +674,8 @@ static int add_projected_impl(b200knn_index *ix, const void *rows, int dtype, in
     if (n == 0) return B200KNN_OK;
     Shard &s = ix->shards[0];
     CU_TRY(cudaSetDevice(s.device));
-    void *d_pool = nullptr;
-    CU_TRY(cudaMalloc(&d_pool, static_cast<size_t>(n) * ix->dim * sizeof(double)));
+    TRY(s.x_store.ensure(static_cast<size_t>(n) * ix->dim * sizeof(double)));
+    void *d_pool = s.x_store.p;
     int r = s.attach_pool(d_pool, true, B200KNN_F64, n, ix->dim, ix->dim, ix->kp, 0);   // the shard owns d_pool from here
     if (r != B200KNN_OK) return r;
     TRY(project_host_rows(ix, s, rows, dtype, n, ld, static_cast<double *>(d_pool)));

@@ -40,6 +40,33 @@ __device__ __forceinline__ void load8_wide<float>(const float *p, double (&d)[8]
     for (int i = 0; i < 8; i++) d[i] = f[i];
 }
 
+// raw 8-element group of a row (no conversion: a float->double conversion right behind its load would make the in-order
+// warp wait for that load before issuing the next one)
+template <typename T>
+__device__ __forceinline__ void load8_raw(const T *p, T (&r)[8], bool wide);
+template <>
+__device__ __forceinline__ void load8_raw<double>(const double *p, double (&r)[8], bool wide) {
+    if (wide) {
+        asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r[0]), "=d"(r[1]), "=d"(r[2]), "=d"(r[3]) : "l"(p));
+        asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r[4]), "=d"(r[5]), "=d"(r[6]), "=d"(r[7]) : "l"(p + 4));
+    } else {
+        const double2 *p2 = reinterpret_cast<const double2 *>(p);
+        const double2 v0 = __ldcs(p2), v1 = __ldcs(p2 + 1), v2 = __ldcs(p2 + 2), v3 = __ldcs(p2 + 3);
+        r[0] = v0.x; r[1] = v0.y; r[2] = v1.x; r[3] = v1.y; r[4] = v2.x; r[5] = v2.y; r[6] = v3.x; r[7] = v3.y;
+    }
+}
+template <>
+__device__ __forceinline__ void load8_raw<float>(const float *p, float (&r)[8], bool wide) {
+    if (wide) {
+        asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p));
+    } else {
+        const float4 *p4 = reinterpret_cast<const float4 *>(p);
+        const float4 v0 = __ldcs(p4), v1 = __ldcs(p4 + 1);
+        r[0] = v0.x; r[1] = v0.y; r[2] = v0.z; r[3] = v0.w; r[4] = v1.x; r[5] = v1.y; r[6] = v1.z; r[7] = v1.w;
+    }
+}
+
 // 8 doubles through the read-only cached path (the column means: 8*dim bytes, L1/L2 resident)
 __device__ __forceinline__ void load8_cached(const double *p, double (&d)[8]) {
     const double2 *p2 = reinterpret_cast<const double2 *>(p);
@@ -95,36 +122,38 @@ convert_norm_kernel(const T *__restrict__ src, const double *__restrict__ mu, in
             const int groups = dim >> 3;
             // NG 8-element groups per lane per step: all loads of a step are issued before the first use (NG x 64 bytes of a
             // float64 row in flight per lane; the means come from L1/L2)
-            constexpr int NG = sizeof(T) == 8 ? 3 : 2;      // (float rows: three groups cost a third resident block, ncu: 65 % vs 85 % of copy peak)
+            constexpr int NG = sizeof(T) == 8 ? 3 : 4;      // 192 / 128 bytes of the row in flight per lane
             int g = lane;
             for (; g + 32 * (NG - 1) < groups; g += 32 * NG) {
-                double v[NG][8];
-                if (vec == 2) {
+                T raw[NG][8];
 #pragma unroll
-                    for (int h = 0; h < NG; h++) load8_wide<T>(s + ((g + 32 * h) << 3), v[h]);
-                } else {
+                for (int h = 0; h < NG; h++) load8_raw<T>(s + ((g + 32 * h) << 3), raw[h], vec == 2);
+                if constexpr (sizeof(T) == 4) {
 #pragma unroll
-                    for (int h = 0; h < NG; h++) load8<T>(s + ((g + 32 * h) << 3), v[h]);
+                    for (int h = 0; h < NG; h++)
+#pragma unroll
+                        for (int i = 0; i < 8; i++) keep(raw[h][i]);      // every load issued before the first conversion
                 }
-                if (mu) {
+                // one group at a time from here on (the raw values of the others wait in registers)
 #pragma unroll
-                    for (int h = 0; h < NG; h++) {
+                for (int h = 0; h < NG; h++) {
+                    double v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[i] = static_cast<double>(raw[h][i]);
+                    if (mu) {
                         double m0[8];
                         load8_cached(mu + ((g + 32 * h) << 3), m0);
 #pragma unroll
-                        for (int i = 0; i < 8; i++) v[h][i] -= m0[i];
+                        for (int i = 0; i < 8; i++) v[i] -= m0[i];
                     }
-                }
-#pragma unroll
-                for (int h = 0; h < NG; h++) {
                     __nv_bfloat162 b[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        b[i] = __floats2bfloat162_rn(static_cast<float>(v[h][2 * i]), static_cast<float>(v[h][2 * i + 1]));
+                        b[i] = __floats2bfloat162_rn(static_cast<float>(v[2 * i]), static_cast<float>(v[2 * i + 1]));
                         const float lo = __low2float(b[i]), hi = __high2float(b[i]);
                         acc = fmaf(lo, lo, acc);
                         acc = fmaf(hi, hi, acc);
-                        const double e0 = v[h][2 * i] - static_cast<double>(lo), e1 = v[h][2 * i + 1] - static_cast<double>(hi);
+                        const double e0 = v[2 * i] - static_cast<double>(lo), e1 = v[2 * i + 1] - static_cast<double>(hi);
                         er = fma(e0, e0, er);
                         er = fma(e1, e1, er);
                     }

@@ -215,6 +215,10 @@ int ex_chunks(const Shard &s, int64_t nq, int kp, int64_t cap_rows, std::vector<
     int64_t group_rows = static_cast<int64_t>(sch.qg) * BM * sch.cg;
     cap_rows = std::max<int64_t>(BM * 2, cap_rows / (BM * 2) * (BM * 2));
     group_rows = std::max<int64_t>(BM * 2, std::min(group_rows, cap_rows));
+    // Every chunk ends in two rank-wide exchanges (bounds, lists), i.e. it costs the skew between the ranks twice.  Long rows
+    // have small groups (8 query tiles at d = 49152: 15 chunks of 19 ms each, ~2 ms of skew per exchange measured at 8 GPUs):
+    // a chunk is then several groups, about a quarter of the call.
+    if (nq / 4 > group_rows) group_rows = std::min(cap_rows / group_rows * group_rows, (nq / 4 + group_rows - 1) / group_rows * group_rows);
     if (nq <= std::min(cap_rows, group_rows + group_rows / 4)) {
         chunks.emplace_back(0, nq);
         return B200KNN_OK;

@@ -17,6 +17,9 @@ struct Shard {
     // ---- pool ----
     const void *x_raw = nullptr;     // original rows (f64 or f32), ld_x elements apart
     void *x_owned = nullptr;         // set when the library owns the copy
+    DevBuf<unsigned char> x_store;   // the library's copy of the original rows: kept across clear() (the trainer re-adds a pool of
+                                     // the same size at every refresh; freeing and re-allocating GBs costs tens of ms), freed by destroy()
+    bool release_on_clear = false;   // $B200KNN_RELEASE_ON_CLEAR=1: give the memory back at clear()/reset()
     int x_dtype = B200KNN_F64;
     int64_t n = 0, ld_x = 0, index_base = 0;
     DevBuf<__nv_bfloat16> x_bf;
@@ -169,6 +172,7 @@ struct Shard {
         if (const char *o = getenv("B200KNN_WIDE")) wide_mode = atoi(o);
         if (const char *o = getenv("B200KNN_COPY_THREADS")) copy_threads = std::max(1, atoi(o));
         if (const char *o = getenv("B200KNN_CENTER")) use_centering = atoi(o) != 0;
+        if (const char *o = getenv("B200KNN_RELEASE_ON_CLEAR")) release_on_clear = atoi(o) != 0;
         if (const char *o = getenv("B200KNN_KC")) kc_elems = std::max(0, atoi(o));
         if (const char *o = getenv("B200KNN_PRECISION")) {
             if (!strcmp(o, "bf16x3") || !strcmp(o, "1")) tier = 1;
@@ -235,20 +239,26 @@ struct Shard {
         if (!ready) return;
         cudaSetDevice(device);
         cudaStreamSynchronize(stream);
-        if (x_owned) cudaFree(x_owned);
+        if (x_owned && x_owned != x_store.p) cudaFree(x_owned);
         x_owned = nullptr;
         x_raw = nullptr;
         n = 0;
         sched1.key_nq = -1;
         sched2.key_nq = -1;
-        x_bf.release();
-        xnorm_bf.release();
-        x_err.release();
-        x_lo.release(); x_tf.release(); xnorm_t.release(); x_err_t.release(); x_lonorm.release();
+        tmap_q2_ptr = nullptr;
+        if (release_on_clear || final_release) {       // (grow-only buffers otherwise: the next add() reuses them)
+            x_store.release();
+            x_bf.release();
+            xnorm_bf.release();
+            x_err.release();
+            x_lo.release(); x_tf.release(); xnorm_t.release(); x_err_t.release(); x_lonorm.release();
+        }
         centered = false;
     }
+    bool final_release = false;
     void destroy() {
         if (!ready) return;
+        final_release = true;
         clear_pool();
         drain_events();
         q_bf.release(); qnorm_bf.release(); q_err.release(); q_bf2.release(); uncert_thr.release(); min_score.release(); coll_count.release(); coll_idx.release(); overflow_list.release(); sched_items.release(); sched_items2.release(); sched_slots.release(); stream_sync.release(); radius2.release(); colterm.release(); rowthr.release(); member.release(); cand_s.release(); cand_i.release(); uncert_list.release();
