@@ -66,6 +66,29 @@ def test_no_cpu_fallback(native_lib):
     assert db.num_points == 0
 
 
+def test_collective_and_tier_entry_points_fail_loudly_without_a_gpu(native_lib):
+    """The round-2 entry points (precision tiers, the multi-GPU collective protocol) validate their arguments and, like
+    everything else, refuse to do anything without a device."""
+    from inclusivegan_b200 import dci as mod
+    assert mod.PRECISION_TIERS == {"bf16": 0, "bf16x3": 1, "tf32": 2}
+    h = ctypes.c_void_p()
+    assert native_lib.b200knn_create(8, 0, None, ctypes.byref(h)) == 0
+    assert native_lib.b200knn_set_precision(h, 7) == -1 and b"tier" in native_lib.b200knn_last_error()
+    assert native_lib.b200knn_set_precision(None, 1) == -1
+    ex = ctypes.c_void_p()
+    assert native_lib.b200knn_exchange_create_for_queries(0, 0, 1, 0, 256, 1, ctypes.byref(ex)) == -1       # dim must be positive
+    assert native_lib.b200knn_exchange_create_for_queries(0, 3, 2, 8, 256, 1, ctypes.byref(ex)) == -1       # rank >= world
+    if native_lib.b200knn_device_count() == 0:
+        assert native_lib.b200knn_set_precision(h, 1) == -3
+        assert native_lib.b200knn_exchange_create_for_queries(0, 0, 1, 8, 256, 1, ctypes.byref(ex)) in (-3, -4)
+        assert ex.value is None
+    x = np.zeros((4, 8))
+    assert native_lib.b200knn_exchange_add(None, h, x.ctypes.data, 0, 4, 8, 0) == -1                       # NULL exchange
+    idx = np.zeros((4, 1), np.int32); dist = np.zeros((4, 1))
+    assert native_lib.b200knn_exchange_query(None, h, x.ctypes.data, 0, 4, 8, 1, 0, idx.ctypes.data, dist.ctypes.data, None) == -1
+    native_lib.b200knn_destroy(h)
+
+
 def test_missing_library_fails_loudly(tmp_path):
     from inclusivegan_b200 import dci as mod
     with pytest.raises(RuntimeError) as ei:
