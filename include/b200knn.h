@@ -245,6 +245,11 @@ int b200knn_reset_stats(b200knn_index *index);
 int b200knn_debug_plan(int64_t n, int64_t nq, int kp, int num_sms, int cta_group, int max_slots, int a_budget_mb, int wide_mode,
                        int32_t *items, int64_t capacity, int32_t *geometry);
 
+/* Test hook (pure host code): how a host-row collective query of nq rows (b200knn_exchange_query) is cut into chunks on a rank
+ * holding n pool rows, and which rows of every chunk each of `world` ranks uploads.  out receives, per chunk,
+ * {first row, rows, then per rank: slice begin, slice end (chunk-relative)}; *count = number of chunks. */
+int b200knn_debug_chunks(int64_t n, int64_t nq, int kp, int num_sms, int64_t cap_rows, int world, int64_t *out, int64_t capacity, int64_t *count);
+
 /* Test hook: copy out the BF16-pass shortlists of the LAST tensor pass of a single-device handle (the last query
  * chunk): scores[nq][slots][C] (s~ = ||x~||^2 - 2 q~.x~ as computed on the tensor cores) and rows[nq][slots][C]
  * (shard-local pool row, -1 = empty).  *nq, *slots, *c receive the geometry; the HOST buffers must hold `capacity`

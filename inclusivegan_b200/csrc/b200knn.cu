@@ -375,6 +375,29 @@ int b200knn_debug_plan(int64_t n, int64_t nq, int kp, int num_sms, int cta_group
     return B200KNN_OK;
 }
 
+int b200knn_debug_chunks(int64_t n, int64_t nq, int kp, int num_sms, int64_t cap_rows, int world, int64_t *out, int64_t capacity, int64_t *count) {
+    if (n <= 0 || nq <= 0 || kp <= 0 || num_sms <= 0 || cap_rows <= 0 || world <= 0 || !count) return fail(B200KNN_EINVAL, "chunk arguments must be positive");
+    Shard::Sched sch;
+    TRY(Shard::plan_schedule(sch, n, nq, kp, 64, 0, std::max(1, num_sms / 2), num_sms, 64, 1));
+    std::vector<std::pair<int64_t, int64_t>> chunks;
+    TRY(ex_chunks_from_group(nq, static_cast<int64_t>(sch.qg) * BM * sch.cg, cap_rows, chunks));
+    *count = static_cast<int64_t>(chunks.size());
+    if (out) {
+        if (capacity < *count * (2 + 2 * world)) return fail(B200KNN_EINVAL, "capacity too small");
+        int64_t *o = out;
+        for (auto &c : chunks) {
+            *o++ = c.first;
+            *o++ = c.second;
+            const int64_t slice = (c.second + world - 1) / world;          // the rule of ex_query_host_run / ex_query_device
+            for (int r = 0; r < world; r++) {
+                *o++ = std::min(c.second, slice * r);
+                *o++ = std::min(c.second, slice * (r + 1));
+            }
+        }
+    }
+    return B200KNN_OK;
+}
+
 int b200knn_debug_shortlists(b200knn_index *ix, float *scores, int32_t *rows, int64_t capacity, int64_t *nq, int *slots, int *c) {
     if (!ix || !scores || !rows || !nq || !slots || !c) return fail(B200KNN_EINVAL, "NULL argument");
     if (ix->shards.size() != 1 || !ix->shards[0].ready) return fail(B200KNN_ESTATE, "needs a single-device handle that has answered a query");

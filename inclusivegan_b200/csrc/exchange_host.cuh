@@ -209,10 +209,14 @@ int ex_finish_add(b200knn_exchange *ex, Shard &s, int dim, int kp) {
 
 // chunks of a call: (first row, rows); one chunk = one group of query tiles of the per-shard kernel (a round that keeps
 // every SM busy), bounded by the exchange's capacity; the ragged remainder goes FIRST (the only upload nothing hides)
+int ex_chunks_from_group(int64_t nq, int64_t group_rows, int64_t cap_rows, std::vector<std::pair<int64_t, int64_t>> &chunks);
 int ex_chunks(const Shard &s, int64_t nq, int kp, int64_t cap_rows, std::vector<std::pair<int64_t, int64_t>> &chunks) {
     Shard::Sched sch;
     TRY(s.plan(sch, nq, kp, 64));
-    int64_t group_rows = static_cast<int64_t>(sch.qg) * BM * sch.cg;
+    return ex_chunks_from_group(nq, static_cast<int64_t>(sch.qg) * BM * sch.cg, cap_rows, chunks);
+}
+// pure host arithmetic (also reachable through b200knn_debug_chunks for the CPU tests)
+int ex_chunks_from_group(int64_t nq, int64_t group_rows, int64_t cap_rows, std::vector<std::pair<int64_t, int64_t>> &chunks) {
     cap_rows = std::max<int64_t>(BM * 2, cap_rows / (BM * 2) * (BM * 2));
     group_rows = std::max<int64_t>(BM * 2, std::min(group_rows, cap_rows));
     // Every chunk ends in two rank-wide exchanges (bounds, lists), i.e. it costs the skew between the ranks twice.  Long rows

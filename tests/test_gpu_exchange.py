@@ -171,8 +171,29 @@ def _protocol_worker(rank, world, port, out_path):
         msgs.append("k > N: shape %r" % (gi.shape,))
     else:
         check("tiny pool k>N", gi, gd, pool, queries, n + 1)
+    # ---- case 4: second-pass lists overflow on every rank (two tight clusters, noise far below BF16 resolution): every
+    # rank answers its overflowed queries by the exact scan and the list exchange is repeated, collectively ----
+    n, q, d = 4000 * world, 64, 256
+    sign = np.where(np.arange(n) % 2 == 0, 1.0, -1.0)[:, None]
+    pool = np.ascontiguousarray(40.0 * sign + 1e-3 * rng.standard_normal((n, d)))
+    queries = np.ascontiguousarray(40.0 * np.where(np.arange(q) % 2 == 0, 1.0, -1.0)[:, None] + 1e-3 * rng.standard_normal((q, d)))
+    a, b = shard_range(n, world, rank)
+    ix5 = DeviceKNN(d, rank); ix5.set_stream(st)
+    ex5 = PeerExchange(rank, rank, world, 512, 8, dim=d)
+    connect(ex5)
+    ex5.add(ix5, pool[a:b], index_base=a)
+    gi, gd = ex5.query(ix5, queries, 3)
+    check("overflow -> collective scan fix-up (host rows)", gi, gd, pool, queries, 3)
+    tq5 = torch.from_numpy(queries).to(dev)
+    oi5 = torch.empty(q, 3, dtype=torch.int32, device=dev); od5 = torch.empty(q, 3, dtype=torch.float64, device=dev)
+    ex5.query_device(ix5, tq5.data_ptr(), F64, q, 3, oi5.data_ptr(), od5.data_ptr())
+    torch.cuda.synchronize()
+    check("overflow -> collective scan fix-up (device rows)", oi5.cpu().numpy(), od5.cpu().numpy(), pool, queries, 3)
+    if ix5.stats()["exact_scanned"] == 0:
+        ok = False
+        msgs.append("case 4 did not reach the exact scan")
     _finish(dist, torch, rank, ok, msgs, out_path)
-    for e in (ex, ex2, ex3, ex4):
+    for e in (ex, ex2, ex3, ex4, ex5):
         e.close()
     dist.destroy_process_group()
 

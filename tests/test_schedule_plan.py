@@ -74,3 +74,36 @@ def test_headline_shapes(native_lib):
 def test_every_tile_pair_is_scheduled_exactly_once(native_lib, n, nq, kp, num_sms, cg, max_slots, budget, wide):
     g, items = plan(native_lib, n, nq, kp, num_sms, cg, max_slots, budget, wide)
     check_invariants(g, items, n, nq, max_slots)
+
+
+# ------------------------------------------------------------------------------------------------ multi-GPU host logic
+@settings(max_examples=120, deadline=None)
+@given(n=st.integers(1, 400000), nq=st.integers(1, 70000), kp=st.sampled_from([64, 512, 3072, 5000, 49152]),
+       cap=st.sampled_from([256, 1000, 4096, 30000, 32768]), world=st.integers(1, 16))
+def test_collective_query_chunks_and_slices(native_lib, n, nq, kp, cap, world):
+    """b200knn_exchange_query: the chunks tile the query rows in order, none exceeds the exchange's capacity, and the
+    per-rank upload slices tile every chunk (the exact re-rank finds the owner of row q as q // slice)."""
+    native_lib.b200knn_debug_chunks.restype = ctypes.c_int
+    native_lib.b200knn_debug_chunks.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
+                                                ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
+    count = ctypes.c_int64(0)
+    assert native_lib.b200knn_debug_chunks(n, nq, kp, 148, cap, world, None, 0, ctypes.byref(count)) == 0
+    per = 2 + 2 * world
+    out = np.zeros(count.value * per, dtype=np.int64)
+    assert native_lib.b200knn_debug_chunks(n, nq, kp, 148, cap, world, out.ctypes.data, out.size, ctypes.byref(count)) == 0
+    rows = out.reshape(count.value, per)
+    cap_eff = max(256, cap // 256 * 256)
+    pos = 0
+    for r in rows:
+        first, cnt = int(r[0]), int(r[1])
+        assert first == pos and 0 < cnt <= cap_eff
+        sl = r[2:].reshape(world, 2)
+        assert sl[0, 0] == 0 and sl[-1, 1] == cnt and np.all(sl[1:, 0] == sl[:-1, 1]) and np.all(sl[:, 1] >= sl[:, 0])
+        slice_rows = -(-cnt // world)
+        for q in (0, cnt // 2, cnt - 1):                       # owner lookup of the re-rank
+            owner = q // slice_rows
+            assert sl[owner, 0] <= q < sl[owner, 1]
+        pos += cnt
+    assert pos == nq
+    if count.value > 1:                                        # the ragged remainder goes first, the rest are equal
+        assert len({int(c) for c in rows[1:, 1]}) == 1 and rows[0, 1] <= rows[1, 1]
