@@ -428,51 +428,32 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
 #pragma unroll
         for (int i = 0; i < RQ; i++) qreg[i] = static_cast<double>(qraw[i]);
     }
-    // float32 pool rows: two candidates per step (twice the bytes in flight per block for 24 more registers — the sweep
-    // is latency-bound: ncu 35 % of DRAM throughput at 22 % occupancy); float64 rows: one (the registers are not there).
-    // One barrier per step: the per-warp partial sums are double-buffered by step parity.
-    constexpr bool PAIRS = sizeof(TX) == 4;
-    __shared__ double partial2[2][2][4];
-    int par = 0;
-    for (int c = 0; c < C;) {
+    // (Tried in round 2 and dropped: two candidates per step for float32 pools — 164 registers cost a resident block and the
+    // config-4 re-rank went from 3.3 to 4.1 ms.  ncu: the kernel is latency-bound per block (sort, prune, one candidate
+    // after the other), not DRAM-bound: 4 % of DRAM throughput at config 4, 35 % at config 3.)
+    for (int c = 0; c < C; c++) {
         if (c == p.kk && c < m) m = tighten_survivors(p, q, keys, d2s, m, &m_s, warp, lane, u_ext);   // uniform across the block
         const unsigned long long key = keys[c];
         if (c >= m || key == ~0ull) {           // uniform across the block
             if (tid == 0) d2s[c] = DBL_MAX;
-            c++;
             continue;
         }
         const TX *xr = x + static_cast<int64_t>(static_cast<uint32_t>(key)) * p.ld_x;
         if (!fits) {
             const double tot = canon_d2(xr, qr, p.dim, tid, partial);
             if (tid == 0) d2s[c] = tot;
-            c++;
             continue;
         }
-        // a second candidate rides along when it is a survivor too and the pruning point (c == kk) is not between them
-        const bool pair = PAIRS && (c + 1 < C) && (c + 1 < m) && (c + 1 != p.kk) && keys[c + 1] != ~0ull;      // uniform
         if (act) {                               // same order as canon_d2, query slice already in registers
-            TX xraw[RQ], yraw[PAIRS ? RQ : 1];
+            double a0 = 0.0, a1 = 0.0;
+            TX xraw[RQ];
 #pragma unroll
             for (int i = 0; i < RQ; i++) {
                 const int e = tid + i * nth;
                 xraw[i] = (e < p.dim) ? xr[e] : TX(0);
             }
-            if constexpr (PAIRS) {
-                if (pair) {
-                    const TX *yr = x + static_cast<int64_t>(static_cast<uint32_t>(keys[c + 1])) * p.ld_x;
-#pragma unroll
-                    for (int i = 0; i < RQ; i++) {
-                        const int e = tid + i * nth;
-                        yraw[i] = (e < p.dim) ? yr[e] : TX(0);
-                    }
-#pragma unroll
-                    for (int i = 0; i < RQ; i++) keep(yraw[i]);
-                }
-            }
 #pragma unroll
             for (int i = 0; i < RQ; i++) keep(xraw[i]);
-            double a0 = 0.0, a1 = 0.0;
 #pragma unroll
             for (int i = 0; i < RQ; i += 2) {
                 const double d0 = qreg[i] - static_cast<double>(xraw[i]), d1 = qreg[i + 1] - static_cast<double>(xraw[i + 1]);
@@ -480,29 +461,11 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
                 a1 = fma(d1, d1, a1);
             }
             const double w = warp_sum(a0 + a1);
-            if (lane == 0) partial2[par][0][warp] = w;
-            if constexpr (PAIRS) {
-                if (pair) {
-                    double b0 = 0.0, b1 = 0.0;
-#pragma unroll
-                    for (int i = 0; i < RQ; i += 2) {
-                        const double d0 = qreg[i] - static_cast<double>(yraw[i]), d1 = qreg[i + 1] - static_cast<double>(yraw[i + 1]);
-                        b0 = fma(d0, d0, b0);
-                        b1 = fma(d1, d1, b1);
-                    }
-                    const double w1 = warp_sum(b0 + b1);
-                    if (lane == 0) partial2[par][1][warp] = w1;
-                }
-            }
+            if (lane == 0) partial[warp] = w;
         }
         __syncthreads();
-        if (tid == 0) {
-            d2s[c] = ((partial2[par][0][0] + partial2[par][0][1]) + partial2[par][0][2]) + partial2[par][0][3];
-            if (pair) d2s[c + 1] = ((partial2[par][1][0] + partial2[par][1][1]) + partial2[par][1][2]) + partial2[par][1][3];
-        }
-        par ^= 1;          // the next step writes the other buffer: no second barrier (thread 0 has read this one before it
-                           // reaches the barrier of the step after next)
-        c += pair ? 2 : 1;
+        if (tid == 0) d2s[c] = ((partial[0] + partial[1]) + partial[2]) + partial[3];
+        __syncthreads();
     }
     __syncthreads();
     if (warp == 0) rerank_finish<C>(p, q, keys, d2s, lane, u_ext);

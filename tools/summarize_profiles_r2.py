@@ -57,12 +57,16 @@ launch_list('gpurun_out/launches_r2.csv', 'profiles/launches_r2_c3.txt',
 tr = summary('gpurun_out/prof_dist_r2.ncu-rep', 'profiles/dist_kernel_ncu_r2_c3.txt',
              ["# ncu --set full --clock-control none --import-source on -k regex:dist_topc -s 2 -c 1  python bench.py --steps 1 --warmup 3 (workload c3), round 2",
               "# one launch of the dominant kernel: 30000 queries x 300000 pool rows x 3072 dims; 2*Q*N*d = 5.53e13 FLOP"])
-summary('gpurun_out/prof_convert_r2.ncu-rep', 'profiles/convert_kernel_ncu_r2.txt',
+summary('gpurun_out/prof_convert_r2c.ncu-rep', 'profiles/convert_kernel_ncu_r2.txt',
         ["# ncu --set full --clock-control none -k regex:convert_norm -c 4  python tools/ncu_convert_target.py, round 2",
-         "# launches: float64 pool 300000 x 3072, float64 queries 30000 x 3072, float32 pool, float32 queries (three 8-element groups per lane in flight,",
-         "# 256-bit loads).  algorithmic bytes per row: d * (sizeof(T) + 2) + 8.  (bench.py's event-timed `convert` figure also contains the",
+         "# launches: float64 pool 300000 x 3072, float64 queries 30000 x 3072, float32 pool, float32 queries (three float64 / four float32 8-element",
+         "# groups per lane in flight, 256-bit loads, raw loads issued before any conversion).  algorithmic bytes per row: d * (sizeof(T) + 2) + 8.  (bench.py's event-timed `convert` figure also contains the",
          "# launch latency after the host synchronisation that ends the previous step: ~0.1 ms on a 0.16 ms kernel.)"],
         algo_bytes=[300000 * (3072 * 10 + 8), 30000 * (3072 * 10 + 8), 300000 * (3072 * 6 + 8), 30000 * (3072 * 6 + 8)])
+summary('gpurun_out/prof_rerank_r2c.ncu-rep', 'profiles/rerank_kernel_ncu_r2_c4.txt',
+        ["# ncu --set full --clock-control none -k regex:rerank_kernel -s 2 -c 1  python bench.py --workload c4 --steps 1 --warmup 3, round 2",
+         "# one launch: 32768 rows of a 50000 x 2048 float32 self-kNN (k = 4), with the two-candidates-per-step variant that was dropped afterwards",
+         "# (164 registers, 3 resident blocks): 4 % of DRAM throughput — the kernel is latency-bound per block, not DRAM-bound"])
 summary('gpurun_out/prof_rerank_r2.ncu-rep', 'profiles/rerank_kernel_ncu_r2_c3.txt',
         ["# ncu --set full --clock-control none -k regex:rerank_kernel -s 2 -c 1  python bench.py --steps 1 --warmup 3 (workload c3), round 2",
          "# one launch: 30000 queries, shortlists of 2-10 pool streams x 16, exact float64 re-rank of the survivors (gather of 24 KB rows)"])
