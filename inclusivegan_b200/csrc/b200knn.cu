@@ -571,11 +571,16 @@ int b200knn_query_device(b200knn_index *ix, const void *d_query, int dtype, int6
     const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
     if (nq == 0) return B200KNN_OK;
     TRY(s.begin_call(nq));
+    const bool whole = nq > QUERY_CHUNK;       // several passes: one second pass for all of them, at the end
+    s.accum = Shard::CallAccum{};
     for (int64_t q0 = 0; q0 < nq; q0 += QUERY_CHUNK) {
         const int64_t cq = std::min(QUERY_CHUNK, nq - q0);
-        TRY(s.query_device(static_cast<const char *>(d_query) + static_cast<size_t>(q0) * ld * esz, dtype, cq, ld, ix->dim, ix->kp, k, flags,
-                           d_out_idx + q0 * kk, d_out_dist + q0 * kk, nullptr, static_cast<int>(q0)));
+        if (whole) { s.accum.on = true; s.accum.rows = nq; s.accum.off = q0; }
+        const int rc = s.query_device(static_cast<const char *>(d_query) + static_cast<size_t>(q0) * ld * esz, dtype, cq, ld, ix->dim, ix->kp, k, flags,
+                                      d_out_idx + q0 * kk, d_out_dist + q0 * kk, nullptr, static_cast<int>(q0));
+        if (rc != B200KNN_OK) { s.accum = Shard::CallAccum{}; return rc; }
     }
+    if (whole) TRY(s.finish_accumulated_call(d_query, dtype, ld, ix->dim, ix->kp, kk, flags, d_out_idx, d_out_dist));
     // one synchronisation per call: did any second-pass list overflow?  (then: exact scan of those queries)
     TRY(s.enqueue_overflow_readback());
     CU_TRY(cudaStreamSynchronize(s.stream));
@@ -596,18 +601,28 @@ int b200knn_query_self(b200knn_index *ix, int k, unsigned flags, int32_t *out_id
     TRY(s.out_dist.ensure(static_cast<size_t>(s.n) * kk));
     const size_t esz = s.x_dtype == B200KNN_F64 ? 8 : 4;
     TRY(s.begin_call(s.n));
-    for (int64_t q0 = 0; q0 < s.n; q0 += QUERY_CHUNK) {
-        const int64_t cq = std::min(QUERY_CHUNK, s.n - q0);
+    auto pool_side = [&](int64_t q0) {       // the pool's own operands (of the handle's precision tier) from row q0 on
         QuerySide pre{s.x_bf.p + static_cast<size_t>(q0) * ix->kp, s.xnorm_bf.p + q0, s.x_err.p + q0};
-        if (s.tier != 0) {          // the pool's own operands of the handle's precision tier
+        if (s.tier != 0) {
             pre.norm = s.xnorm_t.p + q0;
             pre.err = s.x_err_t.p + q0;
             if (s.tier == 1) { pre.lo = s.x_lo.p + static_cast<size_t>(q0) * ix->kp; pre.lonorm = s.x_lonorm.p + q0; }
             else pre.tf = s.x_tf.p + static_cast<size_t>(q0) * ix->kp;
         }
-        TRY(s.query_device(static_cast<const char *>(s.x_raw) + static_cast<size_t>(q0) * s.ld_x * esz, s.x_dtype, cq, s.ld_x, ix->dim, ix->kp, k,
-                           flags, s.out_idx.p + q0 * kk, s.out_dist.p + q0 * kk, &pre, static_cast<int>(q0)));
+        return pre;
+    };
+    const QuerySide base = pool_side(0);
+    const bool whole = s.n > QUERY_CHUNK;       // several passes: one second pass for all of them, at the end
+    s.accum = Shard::CallAccum{};
+    for (int64_t q0 = 0; q0 < s.n; q0 += QUERY_CHUNK) {
+        const int64_t cq = std::min(QUERY_CHUNK, s.n - q0);
+        const QuerySide pre = pool_side(q0);
+        if (whole) { s.accum.on = true; s.accum.rows = s.n; s.accum.off = q0; s.accum.pre_base = &base; }
+        const int rc = s.query_device(static_cast<const char *>(s.x_raw) + static_cast<size_t>(q0) * s.ld_x * esz, s.x_dtype, cq, s.ld_x, ix->dim, ix->kp, k,
+                                      flags, s.out_idx.p + q0 * kk, s.out_dist.p + q0 * kk, &pre, static_cast<int>(q0));
+        if (rc != B200KNN_OK) { s.accum = Shard::CallAccum{}; return rc; }
     }
+    if (whole) TRY(s.finish_accumulated_call(s.x_raw, s.x_dtype, s.ld_x, ix->dim, ix->kp, kk, flags, s.out_idx.p, s.out_dist.p));
     auto copy_out = [&]() -> int {
         CU_TRY(cudaMemcpyAsync(out_idx, s.out_idx.p, static_cast<size_t>(s.n) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         CU_TRY(cudaMemcpyAsync(out_dist, s.out_dist.p, static_cast<size_t>(s.n) * kk * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
@@ -822,11 +837,22 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
         int64_t max_rows = 0;
         for (auto &c : chunks) max_rows = std::max(max_rows, c.second);
         const int64_t nchunks = static_cast<int64_t>(chunks.size());
-        TRY(s.q_stage.ensure(static_cast<size_t>(max_rows) * dim * esz));
-        if (nchunks > 1) TRY(s.q_stage2.ensure(static_cast<size_t>(max_rows) * dim * esz));
+        // Whole-call mode: when the call's query rows fit a device buffer ($B200KNN_CALL_BUFFER_MB, default 4096) every
+        // chunk is uploaded into its own slice of it — no stage buffer is recycled, so no upload ever waits for a compute
+        // pass — and the call runs ONE second pass at its end instead of one per chunk (Shard::CallAccum).
+        static const int64_t call_buffer_mb = []() { const char *e = getenv("B200KNN_CALL_BUFFER_MB"); return e ? std::max<int64_t>(0, atoll(e)) : 4096ll; }();
+        const bool whole = nchunks > 1 && kk <= 32 && !(flags & B200KNN_FLAG_FORCE_SCAN) &&
+                           static_cast<int64_t>(nq) * dim * static_cast<int64_t>(esz) <= (call_buffer_mb << 20);
+        if (whole) {
+            TRY(s.q_stage.ensure(static_cast<size_t>(nq) * dim * esz));
+        } else {
+            TRY(s.q_stage.ensure(static_cast<size_t>(max_rows) * dim * esz));
+            if (nchunks > 1) TRY(s.q_stage2.ensure(static_cast<size_t>(max_rows) * dim * esz));
+        }
         TRY(s.out_idx.ensure(static_cast<size_t>(nq) * kk));
         TRY(s.out_dist.ensure(static_cast<size_t>(nq) * kk));
         unsigned char *stage[2] = {s.q_stage.p, s.q_stage2.p};
+        auto stage_of = [&](int64_t c) { return whole ? s.q_stage.p + static_cast<size_t>(chunks[c].first) * dim * esz : stage[c & 1]; };
         const char *src = static_cast<const char *>(query);
         TRY(s.begin_call(nq));
         auto copy_out = [&]() -> int {
@@ -839,7 +865,8 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
         auto finish = [&](Shard &sh) -> int {
             const int nov = *sh.h_count;
             if (nov <= 0) return B200KNN_OK;
-            TRY(sh.fix_overflow_host(query, dtype, ld, nov, dim, kk, flags, sh.out_idx.p, sh.out_dist.p));
+            if (whole) TRY(sh.fix_overflow_device(sh.q_stage.p, dtype, dim, nov, dim, kk, flags, sh.out_idx.p, sh.out_dist.p));
+            else TRY(sh.fix_overflow_host(query, dtype, ld, nov, dim, kk, flags, sh.out_idx.p, sh.out_dist.p));
             TRY(copy_out());
             CU_TRY(cudaStreamSynchronize(sh.stream));
             return B200KNN_OK;
@@ -874,10 +901,11 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
             for (int64_t c = 0; c < nchunks; c++) {
                 const int b = static_cast<int>(c & 1);
                 if (c >= 2) {
-                    while (consumed.load(std::memory_order_acquire) < c - 1) std::this_thread::yield();   // chunk c-2 enqueued
-                    cudaStreamWaitEvent(s.copy_stream, s.ev_consumed[b], 0);
+                    // chunk c-2 enqueued: its wait on ev_copied[b] is in the stream, the event may be recorded again
+                    while (consumed.load(std::memory_order_acquire) < c - 1) std::this_thread::yield();
+                    if (!whole) cudaStreamWaitEvent(s.copy_stream, s.ev_consumed[b], 0);      // (whole-call mode recycles no buffer)
                 }
-                int rc = upload(s, stage[b], src + static_cast<size_t>(chunks[c].first) * ld * esz, chunks[c].second, s.copy_stream);
+                int rc = upload(s, stage_of(c), src + static_cast<size_t>(chunks[c].first) * ld * esz, chunks[c].second, s.copy_stream);
                 if (rc == B200KNN_OK && cudaEventRecord(s.ev_copied[b], s.copy_stream) != cudaSuccess) rc = B200KNN_ECUDA;
                 if (rc != B200KNN_OK) {
                     up_err = g_last_error;      // thread-local in the uploader: hand it over
@@ -889,20 +917,24 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
             }
         });
         int rc_main = B200KNN_OK;
+        s.accum = Shard::CallAccum{};
         for (int64_t c = 0; c < nchunks && rc_main == B200KNN_OK; c++) {
             const int b = static_cast<int>(c & 1);
             const int64_t q0 = chunks[c].first, cq = chunks[c].second;
             while (uploaded.load(std::memory_order_acquire) < c + 1) std::this_thread::yield();
             if (up_rc.load() != B200KNN_OK) break;
             if (cudaStreamWaitEvent(s.stream, s.ev_copied[b], 0) != cudaSuccess) { rc_main = fail(B200KNN_ECUDA, "cudaStreamWaitEvent failed"); break; }
-            rc_main = s.query_device(stage[b], dtype, cq, dim, dim, ix->kp, k, flags, s.out_idx.p + q0 * kk, s.out_dist.p + q0 * kk, nullptr, static_cast<int>(q0));
+            if (whole) { s.accum.on = true; s.accum.rows = nq; s.accum.off = q0; }
+            rc_main = s.query_device(stage_of(c), dtype, cq, dim, dim, ix->kp, k, flags, s.out_idx.p + q0 * kk, s.out_dist.p + q0 * kk, nullptr, static_cast<int>(q0));
             if (rc_main == B200KNN_OK && cudaEventRecord(s.ev_consumed[b], s.stream) != cudaSuccess) rc_main = fail(B200KNN_ECUDA, "cudaEventRecord failed");
             consumed.store(c + 1, std::memory_order_release);
         }
         consumed.store(nchunks + 2, std::memory_order_release);   // never leave the uploader waiting
         uploader.join();
+        if (up_rc.load() != B200KNN_OK || rc_main != B200KNN_OK) s.accum = Shard::CallAccum{};
         if (up_rc.load() != B200KNN_OK) return fail(up_rc.load(), "%s", up_err.c_str());
         if (rc_main != B200KNN_OK) return rc_main;
+        if (whole) TRY(s.finish_accumulated_call(s.q_stage.p, dtype, dim, dim, ix->kp, kk, flags, s.out_idx.p, s.out_dist.p));
         TRY(copy_out());
         TRY(s.enqueue_overflow_readback());
         CU_TRY(cudaStreamSynchronize(s.stream));

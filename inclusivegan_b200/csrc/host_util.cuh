@@ -19,8 +19,6 @@
 #include <utility>
 #include <vector>
 
-#include <cub/device/device_segmented_radix_sort.cuh>
-
 #include "../../include/b200knn.h"
 #include "kernels.cuh"
 

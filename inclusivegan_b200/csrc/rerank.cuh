@@ -123,6 +123,7 @@ struct RerankParams {
     int *uncert_count;             // number of uncertified queries
     int *uncert_list;              // their row numbers
     float *uncert_thr;             // score threshold for the collection pass, per list slot
+    int uncert_q_base;             // added to the row numbers queued in uncert_list (a call that runs one second pass over all its chunks)
     // Row-sharded pools (one rank per GPU): ext_bounds[r * ext_stride + q] is rank r's upper bound on the distance of
     // its kk-th nearest row to query q (+inf if it has fewer than kk rows), written into this rank's buffer by the
     // peers' bound_publish_kernel.  The global kk-th distance is at most their minimum, so a local candidate whose
@@ -266,7 +267,7 @@ __device__ __forceinline__ void rerank_finish(const RerankParams &p, int q, cons
             // ||q~ - x~|| <= dk + eta, i.e. s~ <= (dk + eta)^2 - ||q~||^2 + eps_acc.
             const double t = (dk + em.eta) * (dk + em.eta) - em.qn_bf + em.eps_acc;
             const int slot = atomicAdd(p.uncert_count, 1);
-            p.uncert_list[slot] = q;
+            p.uncert_list[slot] = q + p.uncert_q_base;
             p.uncert_thr[slot] = __double2float_ru(t + 1e-6 * fabs(t));
         }
     }
@@ -469,6 +470,110 @@ rerank_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const Reran
     }
     __syncthreads();
     if (warp == 0) rerank_finish<C>(p, q, keys, d2s, lane, u_ext);
+}
+
+// The same re-rank with ONE WARP per query (throughput flavour, many queries).  The block flavour above keeps one query
+// per 128 threads and 124-157 registers: 3-4 queries resident per SM, each a chain of dependent latencies (sort, prune,
+// one candidate after the other) — ncu: 22 % occupancy, 35 % (config 3) / 4 % (config 4) of DRAM throughput.  Here a
+// query costs one warp and ~70 registers, so 24 queries are resident per SM and their latency chains overlap; a
+// candidate row is streamed by canon_d2_warp (sixteen 8-byte loads in flight per lane, bit-identical to the block
+// flavour's sum).  Same pruning, tightening, certificate and output code: results are bit-identical to rerank_kernel.
+__device__ __forceinline__ int tighten_survivors_warp(const RerankParams &p, int q, const unsigned long long *keys, const double *d2s, int m,
+                                                      int lane, double u_ext) {
+    __syncwarp();
+    double mx = 0.0;
+    for (int i = lane; i < p.kk; i += 32) mx = fmax(mx, d2s[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    int cnt = 0;
+    if (mx < DBL_MAX) {
+        const ErrModel em = make_err_model(p, q);
+        const double dk = fmin(sqrt(mx), u_ext);
+        for (int i = p.kk + lane; i < m; i += 32)
+            cnt += (keys[i] != ~0ull && em.lower(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(keys[i] >> 32)))) <= dk) ? 1 : 0;
+    } else {
+        cnt = (lane == 0) ? m - p.kk : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    return p.kk + cnt;
+}
+
+template <typename TX, typename TQ, int C, int WPB>
+__global__ void __launch_bounds__(WPB * 32, 3)
+rerank_warp_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const RerankParams p, int nq, int P /* pow2 >= max_slots * C */) {
+    extern __shared__ unsigned long long keys_all[];   // [WPB][P]
+    __shared__ double d2s_all[WPB][C];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * WPB + warp;
+    if (q >= nq) return;                               // (the warps of a block never meet at a barrier)
+    unsigned long long *keys = keys_all + static_cast<size_t>(warp) * P;
+    double *d2s = d2s_all[warp];
+    if (p.ext_bounds && p.min_score) {                 // row-sharded pools: no candidate survives the global bound (see rerank_kernel)
+        const double u = ext_bound_of(p, q);
+        const float ms = __ldg(p.min_score + q);
+        if (u < DBL_MAX && p.n > C && ms < FLT_MAX && make_err_model(p, q).lower(static_cast<double>(ms)) > u) {
+            for (int r = lane; r < p.kk; r += 32) {
+                p.out_idx[static_cast<int64_t>(q) * p.kk + r] = -1;
+                p.out_dist[static_cast<int64_t>(q) * p.kk + r] = DBL_MAX;
+            }
+            return;
+        }
+    }
+    const int total = __ldg(p.slots_per_qtile + q / p.qtile_rows) * C;
+    int Pq = 1;
+    while (Pq < total) Pq <<= 1;
+    for (int i = lane; i < Pq; i += 32) {
+        unsigned long long key = ~0ull;
+        if (i < total) {
+            const int64_t o = static_cast<int64_t>(q) * p.max_slots * C + i;
+            const int idx = p.cand_i[o];
+            if (idx >= 0) key = (static_cast<unsigned long long>(float_order_bits(p.cand_s[o])) << 32) | static_cast<uint32_t>(idx);
+        }
+        keys[i] = key;
+    }
+    for (int c = lane; c < C; c += 32) d2s[c] = DBL_MAX;
+    __syncwarp();
+    for (int k2 = 2; k2 <= Pq; k2 <<= 1) {             // bitonic sort, ascending by (score, index)
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < Pq; i += 32) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long a = keys[i], b = keys[l];
+                    const bool up = (i & k2) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[l] = a; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    const double u_ext = ext_bound_of(p, q);
+    int m = 0;
+    if (lane == 0) {                                   // the pruning rule of rerank_kernel, word for word
+        const ErrModel em = make_err_model(p, q);
+        double u = u_ext;
+        if (keys[p.kk - 1] != ~0ull)
+            u = fmin(u, em.upper(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(keys[p.kk - 1] >> 32)))));
+        if (u < DBL_MAX) {
+            while (m < C && keys[m] != ~0ull &&
+                   em.lower(static_cast<double>(float_from_order_bits(static_cast<uint32_t>(keys[m] >> 32)))) <= u) m++;
+        } else {
+            m = C;
+        }
+        if (!p.ext_bounds) m = max(m, min(C, p.kk));
+    }
+    m = __shfl_sync(0xffffffffu, m, 0);
+    const TQ *qr = query_row(p.qpull, qmat, p.ld_q, q);
+    for (int c = 0; c < m; c++) {
+        if (c == p.kk) m = tighten_survivors_warp(p, q, keys, d2s, m, lane, u_ext);
+        if (c >= m) break;
+        const unsigned long long key = keys[c];
+        if (key == ~0ull) continue;                    // (d2s[c] stays DBL_MAX)
+        const double d2 = canon_d2_warp(x + static_cast<int64_t>(static_cast<uint32_t>(key)) * p.ld_x, qr, p.dim, lane);
+        if (lane == 0) d2s[c] = d2;
+    }
+    __syncwarp();
+    rerank_finish<C>(p, q, keys, d2s, lane, u_ext);
 }
 
 // Second pass, part 2: exact re-rank of the collected lists.  The number of lists is read from device memory (the

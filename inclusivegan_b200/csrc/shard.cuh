@@ -47,6 +47,7 @@ struct Shard {
     int wide_mode = 1;               // $B200KNN_WIDE: 0 never, 1 when cheaper in HBM traffic, 2 always (A/B measurements)
     int sync_tiles = -1;             // $B200KNN_SYNC_TILES: lockstep interval of the workers sharing a pool-tile stream (-1: by tile length)
     int max_pairs = 74;              // CTA pairs that can be co-resident (cudaOccupancyMaxActiveClusters)
+    int rerank_warp_mode = 1;        // $B200KNN_RERANK_WARP: 0 block per query always, 1 warp per query for >= 2048 queries, 2 always
 
     // ---- query workspace ----
     DevBuf<__nv_bfloat16> q_bf;
@@ -64,9 +65,9 @@ struct Shard {
     DevBuf<float> cand_s;
     DevBuf<int> cand_i;
     DevBuf<int> uncert_list;
-    DevBuf<double> scan_d2, scan_d2_sorted;
-    DevBuf<int> scan_iota, scan_vals_sorted, scan_offsets;
-    DevBuf<unsigned char> cub_tmp;
+    DevBuf<double> scan_d2;
+    DevBuf<unsigned long long> scan_key;   // k > 32: (key, index) scratch of scan_topk_kernel, [queries][2][kk]
+    DevBuf<int> scan_idx;
     DevBuf<unsigned char> q_stage;   // host API: device copy of the caller's query rows
     DevBuf<unsigned char> q_stage2;  // second buffer: the upload of chunk i+1 overlaps the compute of chunk i
     cudaStream_t copy_stream = nullptr;
@@ -123,6 +124,8 @@ struct Shard {
         B200_PRELOAD((rerank_kernel<float, double, C, 128>)); B200_PRELOAD((rerank_kernel<float, float, C, 128>));                       \
         B200_PRELOAD((rerank_kernel<double, double, C, 1024>)); B200_PRELOAD((rerank_kernel<double, float, C, 1024>));                   \
         B200_PRELOAD((rerank_kernel<float, double, C, 1024>)); B200_PRELOAD((rerank_kernel<float, float, C, 1024>))
+#define B200_PRELOAD_RW(C) B200_PRELOAD((rerank_warp_kernel<double, double, C, RR_WPB>)); B200_PRELOAD((rerank_warp_kernel<double, float, C, RR_WPB>)); \
+        B200_PRELOAD((rerank_warp_kernel<float, double, C, RR_WPB>)); B200_PRELOAD((rerank_warp_kernel<float, float, C, RR_WPB>))
         B200_PRELOAD(colsum_kernel<double>); B200_PRELOAD(colsum_kernel<float>); B200_PRELOAD(scale_kernel);
         B200_PRELOAD(convert_norm_kernel<double>); B200_PRELOAD(convert_norm_kernel<float>);
         B200_PRELOAD(plan_pass_kernel); B200_PRELOAD(gather_rows_kernel);
@@ -135,15 +138,17 @@ struct Shard {
         B200_PRELOAD((convert_tier_kernel<double, 1>)); B200_PRELOAD((convert_tier_kernel<float, 1>));
         B200_PRELOAD((convert_tier_kernel<double, 2>)); B200_PRELOAD((convert_tier_kernel<float, 2>));
         B200_PRELOAD_RR(16); B200_PRELOAD_RR(32); B200_PRELOAD_RR(64);
+        B200_PRELOAD_RW(16); B200_PRELOAD_RW(32); B200_PRELOAD_RW(64);
         B200_PRELOAD((rerank_collect_kernel<double, double, 32>)); B200_PRELOAD((rerank_collect_kernel<double, float, 32>));
         B200_PRELOAD((rerank_collect_kernel<float, double, 32>)); B200_PRELOAD((rerank_collect_kernel<float, float, 32>));
-        B200_PRELOAD_T2(scan_dist_kernel); B200_PRELOAD(scan_select_kernel); B200_PRELOAD(iota_kernel); B200_PRELOAD(scatter_sorted_kernel);
+        B200_PRELOAD_T2(scan_dist_kernel); B200_PRELOAD(scan_select_kernel); B200_PRELOAD(scan_topk_kernel);
         B200_PRELOAD(merge_topk_kernel); B200_PRELOAD(pad_topk_kernel); B200_PRELOAD(publish_topk_kernel); B200_PRELOAD(merge_wait_kernel);
         B200_PRELOAD(raise_flags_kernel); B200_PRELOAD(broadcast_segments_kernel); B200_PRELOAD(pull_rows_kernel); B200_PRELOAD(wait_flags_kernel); B200_PRELOAD(bound_publish_kernel);
         B200_PRELOAD(publish_colsum_kernel); B200_PRELOAD(global_mean_kernel);
         B200_PRELOAD(ball_colterm_kernel); B200_PRELOAD(ball_rowthr_kernel); B200_PRELOAD_T2(ball_member_kernel); B200_PRELOAD(scan_member_kernel);
         B200_PRELOAD(project_kernel<double>); B200_PRELOAD(project_kernel<float>);
 #undef B200_PRELOAD_RR
+#undef B200_PRELOAD_RW
 #undef B200_PRELOAD_T2
 #undef B200_PRELOAD
         return B200KNN_OK;
@@ -174,6 +179,7 @@ struct Shard {
         if (const char *o = getenv("B200KNN_CENTER")) use_centering = atoi(o) != 0;
         if (const char *o = getenv("B200KNN_RELEASE_ON_CLEAR")) release_on_clear = atoi(o) != 0;
         if (const char *o = getenv("B200KNN_KC")) kc_elems = std::max(0, atoi(o));
+        if (const char *o = getenv("B200KNN_RERANK_WARP")) rerank_warp_mode = std::max(0, std::min(2, atoi(o)));
         if (const char *o = getenv("B200KNN_PRECISION")) {
             if (!strcmp(o, "bf16x3") || !strcmp(o, "1")) tier = 1;
             else if (!strcmp(o, "tf32") || !strcmp(o, "2")) tier = 2;
@@ -262,8 +268,8 @@ struct Shard {
         clear_pool();
         drain_events();
         q_bf.release(); qnorm_bf.release(); q_err.release(); q_bf2.release(); uncert_thr.release(); min_score.release(); coll_count.release(); coll_idx.release(); overflow_list.release(); sched_items.release(); sched_items2.release(); sched_slots.release(); stream_sync.release(); radius2.release(); colterm.release(); rowthr.release(); member.release(); cand_s.release(); cand_i.release(); uncert_list.release();
-        scan_d2.release(); scan_d2_sorted.release(); scan_iota.release(); scan_vals_sorted.release(); scan_offsets.release();
-        cub_tmp.release(); q_stage.release(); q_stage2.release(); out_idx.release(); out_dist.release(); pad_idx.release(); pad_dist.release(); scalars.release();
+        scan_d2.release(); scan_key.release(); scan_idx.release();
+        q_stage.release(); q_stage2.release(); out_idx.release(); out_dist.release(); pad_idx.release(); pad_dist.release(); scalars.release();
         if (h_count) cudaFreeHost(h_count);
         if (own_stream) cudaStreamDestroy(own_stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -599,7 +605,7 @@ struct Shard {
                    int32_t *d_out_idx, double *d_out_dist) {
         const TX *x = static_cast<const TX *>(x_raw);
         // sub-batches bounded to ~1.5 GB of scratch
-        int64_t per_q = n * (kk > 32 ? 24 : 8);
+        int64_t per_q = n * 8 + (kk > 32 ? static_cast<int64_t>(kk) * 24 : 0);
         int batch = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nsub, (1536ll << 20) / std::max<int64_t>(per_q, 1))));
         batch = std::max(1, std::min(batch, 4096));
         TRY(scan_d2.ensure(static_cast<size_t>(batch) * n));
@@ -621,30 +627,11 @@ struct Shard {
                 prof_end();
                 CU_TRY(cudaGetLastError());
             } else {
-                const int64_t total = static_cast<int64_t>(ns) * n;
-                TRY(scan_d2_sorted.ensure(total));
-                TRY(scan_iota.ensure(total));
-                TRY(scan_vals_sorted.ensure(total));
-                TRY(scan_offsets.ensure(ns + 1));
-                std::vector<int> off(ns + 1);
-                for (int i = 0; i <= ns; i++) off[i] = static_cast<int>(static_cast<int64_t>(i) * n);
-                if (total > 0x7fffffffll) return fail(B200KNN_EINVAL, "scan batch too large");
-                CU_TRY(cudaMemcpyAsync(scan_offsets.p, off.data(), (ns + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
-                CU_TRY(cudaStreamSynchronize(stream));   // `off` is a stack-lifetime host buffer
+                // kk > 32 / all points: radix select + stable radix sort of the kk selected, one block per scanned query
+                TRY(scan_key.ensure(static_cast<size_t>(ns) * 2 * kk));
+                TRY(scan_idx.ensure(static_cast<size_t>(ns) * 2 * kk));
                 prof_begin(K_SCAN);
-                iota_kernel<<<num_sms * 4, 256, 0, stream>>>(scan_iota.p, total, static_cast<int>(n));
-                prof_end();
-                size_t tmp_bytes = 0;
-                cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp_bytes, scan_d2.p, scan_d2_sorted.p, scan_iota.p, scan_vals_sorted.p,
-                                                         static_cast<int>(total), ns, scan_offsets.p, scan_offsets.p + 1, 0, 64, stream);
-                TRY(cub_tmp.ensure(tmp_bytes));
-                stats.kernel_launches++;
-                CU_TRY(cub::DeviceSegmentedRadixSort::SortPairs(cub_tmp.p, tmp_bytes, scan_d2.p, scan_d2_sorted.p, scan_iota.p,
-                                                                scan_vals_sorted.p, static_cast<int>(total), ns, scan_offsets.p,
-                                                                scan_offsets.p + 1, 0, 64, stream));
-                prof_begin(K_SCAN);
-                scatter_sorted_kernel<<<num_sms * 4, 256, 0, stream>>>(scan_d2_sorted.p, scan_vals_sorted.p, static_cast<int>(n), ql, ns, kk,
-                                                                      index_base, flags, oi, od);
+                scan_topk_kernel<<<ns, TOPK_THREADS, 0, stream>>>(scan_d2.p, static_cast<int>(n), ql, kk, index_base, flags, scan_key.p, scan_idx.p, oi, od);
                 prof_end();
                 CU_TRY(cudaGetLastError());
             }
@@ -674,6 +661,22 @@ struct Shard {
         else
             rerank_kernel<float, float, C, NT><<<g, NT, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), rp);
     }
+    // throughput flavour: one warp per query, RR_WPB queries per block (rerank.cuh)
+    static constexpr int RR_WPB = 8;
+    template <int C>
+    void launch_rerank_warp(const void *d_query, int q_dtype, int64_t nq, int pk, const RerankParams &rp) {
+        const unsigned g = static_cast<unsigned>((nq + RR_WPB - 1) / RR_WPB);
+        const size_t sm = static_cast<size_t>(RR_WPB) * pk * sizeof(unsigned long long);
+        const int inq = static_cast<int>(nq);
+        if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
+            rerank_warp_kernel<double, double, C, RR_WPB><<<g, RR_WPB * 32, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), rp, inq, pk);
+        else if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
+            rerank_warp_kernel<double, float, C, RR_WPB><<<g, RR_WPB * 32, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), rp, inq, pk);
+        else if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
+            rerank_warp_kernel<float, double, C, RR_WPB><<<g, RR_WPB * 32, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), rp, inq, pk);
+        else
+            rerank_warp_kernel<float, float, C, RR_WPB><<<g, RR_WPB * 32, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), rp, inq, pk);
+    }
     template <int C>
     int launch_rerank(const void *d_query, int q_dtype, int64_t nq, const RerankParams &rp) {
         prof_begin(K_RERANK);
@@ -681,9 +684,12 @@ struct Shard {
         int pk = 1;
         while (pk < rp.max_slots * C) pk <<= 1;
         const size_t sm = static_cast<size_t>(pk) * sizeof(unsigned long long);
-        // merging many shortlists for few queries (many pool streams) is a latency-bound sort: give it 32 warps; with
-        // many queries the device is full anyway and the exact sweep (128 lanes per query) is what matters
-        if (pk >= 1024 && nq <= 4096) launch_rerank_nt<C, 1024>(d_query, q_dtype, g, sm, rp);
+        // Three flavours, bit-identical results.  Many queries: one warp per query (24 resident per SM, their latency
+        // chains overlap).  Few queries: a block per query (128 lanes stream a candidate row at once: lowest latency) —
+        // and when those few queries merge many shortlists (many pool streams), a latency-bound sort, 32 warps per query.
+        const bool warp_flavour = rerank_warp_mode == 2 || (rerank_warp_mode == 1 && nq >= 2048);
+        if (warp_flavour && pk <= 512) launch_rerank_warp<C>(d_query, q_dtype, nq, pk, rp);
+        else if (pk >= 1024 && nq <= 4096) launch_rerank_nt<C, 1024>(d_query, q_dtype, g, sm, rp);
         else launch_rerank_nt<C, 128>(d_query, q_dtype, g, sm, rp);
         prof_end();
         CU_TRY(cudaGetLastError());
@@ -790,6 +796,24 @@ struct Shard {
         double *out_dist = nullptr;
     } deferred;
     bool defer_second_pass = false;     // set by the caller around query_device()
+    // A call whose chunks all stay in HBM (b200knn_query on one device: the query rows of the whole call fit a device
+    // buffer) runs ONE second pass at its end instead of one per chunk: every collection pass sweeps the whole BF16 shard
+    // (0.26-0.44 ms at config 3) whether it serves 10 uncertified queries or 10 000.  The re-rank of every chunk appends to
+    // the same queue (call-global row numbers); the converted rows of all chunks are kept (whole-call buffers).
+    struct CallAccum {
+        bool on = false, first = true;
+        int64_t rows = 0;               // query rows of the call
+        int64_t off = 0;                // first row of the chunk being enqueued
+        const QuerySide *pre_base = nullptr;   // converted rows handed in by the caller (self-kNN): row 0 of the call
+    } accum;
+    // the call's one second pass; d_query_all / outputs: whole-call arrays
+    int finish_accumulated_call(const void *d_query_all, int q_dtype, int64_t ld_q, int dim, int kp, int kk, unsigned flags,
+                                int32_t *d_out_idx_all, double *d_out_dist_all) {
+        const int64_t rows = accum.rows;
+        accum = CallAccum{};
+        if (kk > 32 || (flags & (B200KNN_FLAG_FORCE_SCAN | B200KNN_FLAG_NO_CERTIFY)) || rows <= 0) return B200KNN_OK;
+        return enqueue_second_pass(d_query_all, q_dtype, ld_q, rows, dim, kp, kk, flags, d_out_idx_all, d_out_dist_all, 0, false);
+    }
     int enqueue_uncertified_readback() {     // h_count[1] <- uncertified count of the last pass
         CU_TRY(cudaMemcpyAsync(h_count + 1, scalars.p + 4, sizeof(int), cudaMemcpyDeviceToHost, stream));
         return B200KNN_OK;
@@ -938,33 +962,45 @@ struct Shard {
         const int kp_plan = t ? 2 * kp : kp;
         const __nv_bfloat16 *qb = nullptr, *qlo = nullptr;
         const float *qtf = nullptr, *qn, *qe, *qln = nullptr;
+        // (a call that postpones its second pass keeps the converted rows of ALL its chunks: whole-call buffers, this
+        // chunk's rows at row `off`)
+        const bool acc = accum.on && !hook && (!pre || accum.pre_base);
+        const int64_t cap = acc ? accum.rows : nq, off = acc ? accum.off : 0;
         if (pre) {
             qb = pre->bf; qn = pre->norm; qe = pre->err; qlo = pre->lo; qtf = pre->tf; qln = pre->lonorm;
         } else if (t == 0) {
-            TRY(q_bf.ensure(static_cast<size_t>(nq) * kp));
-            TRY(qnorm_bf.ensure(nq));
-            TRY(q_err.ensure(nq));
-            TRY(launch_convert(d_query, q_dtype, nq, ld_q, dim, kp, q_bf.p, qnorm_bf.p, q_err.p, scalars.p + 2));
-            qb = q_bf.p; qn = qnorm_bf.p; qe = q_err.p;
+            TRY(q_bf.ensure(static_cast<size_t>(cap) * kp));
+            TRY(qnorm_bf.ensure(cap));
+            TRY(q_err.ensure(cap));
+            qb = q_bf.p + static_cast<size_t>(off) * kp; qn = qnorm_bf.p + off; qe = q_err.p + off;
+            TRY(launch_convert(d_query, q_dtype, nq, ld_q, dim, kp, q_bf.p + static_cast<size_t>(off) * kp, qnorm_bf.p + off, q_err.p + off, scalars.p + 2));
         } else {
-            TRY(qnorm_t.ensure(nq));
-            TRY(q_err_t.ensure(nq));
+            TRY(qnorm_t.ensure(cap));
+            TRY(q_err_t.ensure(cap));
             if (t == 1) {
-                TRY(q_bf.ensure(static_cast<size_t>(nq) * kp));
-                TRY(q_lo.ensure(static_cast<size_t>(nq) * kp));
-                TRY(q_lonorm.ensure(nq));
-                TRY(launch_convert_tier(1, d_query, q_dtype, nq, ld_q, dim, kp, q_bf.p, q_lo.p, nullptr, qnorm_t.p, q_err_t.p, q_lonorm.p, scalars.p + 13));
-                qb = q_bf.p; qlo = q_lo.p; qln = q_lonorm.p;
+                TRY(q_bf.ensure(static_cast<size_t>(cap) * kp));
+                TRY(q_lo.ensure(static_cast<size_t>(cap) * kp));
+                TRY(q_lonorm.ensure(cap));
+                TRY(launch_convert_tier(1, d_query, q_dtype, nq, ld_q, dim, kp, q_bf.p + static_cast<size_t>(off) * kp, q_lo.p + static_cast<size_t>(off) * kp, nullptr,
+                                        qnorm_t.p + off, q_err_t.p + off, q_lonorm.p + off, scalars.p + 13));
+                qb = q_bf.p + static_cast<size_t>(off) * kp; qlo = q_lo.p + static_cast<size_t>(off) * kp; qln = q_lonorm.p + off;
             } else {
-                TRY(q_tf.ensure(static_cast<size_t>(nq) * kp));
-                TRY(launch_convert_tier(2, d_query, q_dtype, nq, ld_q, dim, kp, nullptr, nullptr, q_tf.p, qnorm_t.p, q_err_t.p, nullptr, scalars.p + 13));
-                qtf = q_tf.p;
+                TRY(q_tf.ensure(static_cast<size_t>(cap) * kp));
+                TRY(launch_convert_tier(2, d_query, q_dtype, nq, ld_q, dim, kp, nullptr, nullptr, q_tf.p + static_cast<size_t>(off) * kp, qnorm_t.p + off, q_err_t.p + off,
+                                        nullptr, scalars.p + 13));
+                qtf = q_tf.p + static_cast<size_t>(off) * kp;
             }
-            qn = qnorm_t.p; qe = q_err_t.p;
+            qn = qnorm_t.p + off; qe = q_err_t.p + off;
         }
-        cur_q_bf = qb;
-        cur_q_lo = qlo;
-        cur_q_tf = qtf;
+        // what the second pass gathers from: rows are addressed by the numbers the re-rank queues (chunk-local, or
+        // call-global when the pass is postponed to the end of the call)
+        if (acc && pre) {
+            cur_q_bf = accum.pre_base->bf; cur_q_lo = accum.pre_base->lo; cur_q_tf = accum.pre_base->tf;
+        } else {
+            cur_q_bf = acc ? (qb ? q_bf.p : nullptr) : qb;
+            cur_q_lo = acc ? (qlo ? q_lo.p : nullptr) : qlo;
+            cur_q_tf = acc ? (qtf ? q_tf.p : nullptr) : qtf;
+        }
         CUtensorMap tmap_q, tmap_qlo;
         if (t == 2) TRY(make_tmap(&tmap_q, qtf, nq, kp, BM, true));
         else TRY(make_tmap(&tmap_q, qb, nq, kp, BM));
@@ -985,7 +1021,7 @@ struct Shard {
             pp.round_counter = scalars.p + 6;
             pp.stream_sync = stream_sync.p;
             pp.sync_entries = s.nrounds * s.max_slots;
-            pp.zero_a = scalars.p + 4;
+            pp.zero_a = (acc && !accum.first) ? nullptr : scalars.p + 4;      // (postponed second pass: the queue grows over the chunks)
             stats.kernel_launches++;
             plan_pass_kernel<<<1, 256, 0, stream>>>(pp);
             CU_TRY(cudaGetLastError());
@@ -1003,9 +1039,10 @@ struct Shard {
         last_nq = nq;
         last_slots = s.max_slots;
         last_c = C;
-        TRY(uncert_list.ensure(nq));
-        TRY(uncert_thr.ensure(nq));
+        TRY(uncert_list.ensure(cap));
+        TRY(uncert_thr.ensure(cap));
         RerankParams rp{};
+        rp.uncert_q_base = static_cast<int>(off);
         rp.cand_s = cand_s.p;
         rp.cand_i = cand_i.p;
         rp.max_slots = s.max_slots;
@@ -1079,6 +1116,10 @@ struct Shard {
         }
         TRY(launch_rerank<C>(d_query, q_dtype, nq, rp));
         deferred.armed = false;
+        if (acc) {                   // the caller enqueues ONE second pass for the whole call (finish_accumulated_call)
+            accum.first = false;
+            return B200KNN_OK;
+        }
         if (!(flags & B200KNN_FLAG_NO_CERTIFY)) {
             if (defer_second_pass && !hook) {
                 deferred.armed = true;

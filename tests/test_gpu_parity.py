@@ -217,6 +217,39 @@ def test_all_neighbours_when_k_negative(lib):
     assert ok, msg
 
 
+@pytest.mark.parametrize("n,q,d,k,dtype", [(5000, 70, 96, 100, np.float64),       # select 100 of 5000 (several 1024-key chunks per row)
+                                           (3000, 40, 64, 3000, np.float64),      # k = n > one chunk: sort only
+                                           (70000, 33, 32, 2500, np.float32),     # long rows of keys, float32 pool
+                                           (2049, 10, 16, 2048, np.float64)])     # k = n - 1: the last key is dropped
+def test_large_k_select_and_sort(lib, n, q, d, k, dtype):
+    """k > 32 runs the exact scan + scan_topk_kernel (radix select, index-ordered compaction, stable radix sort)."""
+    from inclusivegan_b200 import DCI
+    x, y = make("gauss", n, q, d, seed=n + k, dtype=dtype)
+    db = DCI(d)
+    db.add(x)
+    idx, dist = check(db, x, y, k)
+    assert all(len(set(r)) == k for r in idx.tolist())
+    assert np.all(np.diff(dist, axis=1) >= 0)
+
+
+def test_large_k_ties_come_out_in_index_order(lib):
+    """Equal distances (duplicated pool rows, lattice points) must come out by ascending index — also across the
+    selection threshold, where only the lowest-indexed of the tied keys belong to the answer."""
+    from inclusivegan_b200 import DCI
+    rng = np.random.default_rng(12)
+    base = rng.integers(-3, 4, size=(400, 12)).astype(np.float64)          # small integer lattice: many exact ties
+    x = np.ascontiguousarray(np.concatenate([base, base[::-1], base, base[:123]]))      # every row 3-4 times
+    y = np.ascontiguousarray(rng.integers(-3, 4, size=(25, 12)).astype(np.float64))
+    db = DCI(12)
+    db.add(x)
+    d2 = ((y[:, None, :] - x[None, :, :]) ** 2).sum(-1)                      # exact in float64 (small integers)
+    for k in (40, 700, x.shape[0]):
+        idx, dist = db.query_arrays(y, k, squared=True)
+        order = np.lexsort((np.broadcast_to(np.arange(x.shape[0]), d2.shape), d2), axis=1)[:, :k]
+        assert np.array_equal(idx, order.astype(np.int32)), k
+        assert np.array_equal(dist, np.take_along_axis(d2, order, axis=1)), k
+
+
 def test_non_contiguous_and_mixed_dtype_queries(lib):
     from inclusivegan_b200 import DCI
     x, y = make("gauss", 3000, 64, 128, seed=33)
@@ -624,6 +657,25 @@ def test_results_do_not_depend_on_batching_or_path(lib):
     certified_rows = np.all(i_nc == i_all, axis=1)
     assert certified_rows.mean() > 0.2
     assert np.array_equal(d_nc[certified_rows], d_all[certified_rows])
+
+
+@pytest.mark.parametrize("kind,n,q,d,k,dtype", [("cluster", 30000, 2500, 384, 1, np.float64), ("relu", 9000, 2100, 2048, 4, np.float32),
+                                                ("gauss", 6000, 2200, 520, 20, np.float64)])
+def test_rerank_flavours_are_bit_identical(lib, kind, n, q, d, k, dtype, monkeypatch):
+    """The re-rank has a block-per-query flavour (few queries: lowest latency) and a warp-per-query flavour (many queries:
+    24 resident per SM).  Same pruning, same canonical summation order: outputs must be bit-identical, and exact."""
+    from inclusivegan_b200 import DCI
+    x, y = make(kind, n, q, d, seed=n + k, dtype=dtype)
+    out = {}
+    for mode in ("0", "2"):
+        monkeypatch.setenv("B200KNN_RERANK_WARP", mode)          # read when the handle's device state is created
+        db = DCI(d)
+        db.add(x)
+        out[mode] = check(db, x, y, k)
+        small = db.query_arrays(y[:40], k)                        # 40 rows: auto mode would take the block flavour
+        assert np.array_equal(small[0], out[mode][0][:40]) and np.array_equal(small[1], out[mode][1][:40])
+        db.clear()
+    assert np.array_equal(out["0"][0], out["2"][0]) and np.array_equal(out["0"][1], out["2"][1])
 
 
 @pytest.mark.parametrize("cg", ["1", "2"])

@@ -51,3 +51,13 @@ def test_exact_paths_are_float64(sass):
     dfma = functions(sass, "DFMA")
     for name in ("rerank_kernel", "rerank_collect_kernel", "scan_dist_kernel", "project_kernel", "ball_member_kernel"):
         assert any(name in f for f in dfma), name
+
+
+def test_every_kernel_is_the_repos_own(sass):
+    """No library kernel (cub / thrust / cuBLAS device code) is linked into the product: every SASS function belongs to
+    namespace b200 (csrc/*.cuh).  Round 1 sorted k > 32 results with cub::DeviceSegmentedRadixSort."""
+    names = {l.split(":", 1)[1].strip() for l in sass.splitlines() if l.strip().startswith("Function :")}
+    assert names
+    foreign = sorted(n for n in names if not n.startswith("_ZN4b200"))
+    assert not foreign, foreign[:5]
+    assert any("scan_topk_kernel" in n for n in names) and any("rerank_warp_kernel" in n for n in names)
