@@ -98,7 +98,10 @@ int b200knn_query(b200knn_index *index, const void *query, int dtype, int64_t nq
 /* Self-kNN: every pool row queried against the pool it belongs to (row i's own entry, distance 0, comes first unless
  * duplicates tie).  The reference's precision/recall metric does exactly this to get the k-th neighbour radii
  * (metrics/precision_recall.py:74-90); the rows, their BF16 copies and norms are already on the device from add(), so
- * nothing is uploaded or converted.  out_idx / out_dist: HOST, num_points x kk.  Single-device handles. */
+ * nothing is uploaded or converted.  out_idx / out_dist: HOST, num_points x kk.
+ * Multi-device handles (k <= 32): the rows of every shard, chunk by chunk, are the queries of one collective call — the
+ * chunk's original rows are replicated to the other shards over NVLink, every shard converts 1/G of them, broadcasts the
+ * BF16 slice and answers against its own rows; bit-identical to a single-device handle. */
 int b200knn_query_self(b200knn_index *index, int k, unsigned flags, int32_t *out_idx, double *out_dist, int *out_kk);
 
 /* Ball membership for the k-NN precision/recall metric (reference metrics/precision_recall.py:96-134, the
@@ -109,7 +112,7 @@ int b200knn_query_self(b200knn_index *index, int k, unsigned flags, int32_t *out
 int b200knn_ball_membership(b200knn_index *index, const void *query, int dtype, int64_t nq, int64_t ld, const double *radius2,
                             unsigned char *out_member);
 
-/* ---- random projection on the device (single-device handles) ----
+/* ---- random projection on the device ----
  * The trainer's optional `--init-proj-dim` path multiplies every 256-row chunk of generated images and every 24-row
  * chunk of real images by a fixed Gaussian matrix in NumPy float64 on the host before handing them to DCI
  * (training/training_loop.py:205-212 builds `projector`, :362-365 and :379-381 do `np.matmul(rows.astype(float64),
@@ -117,7 +120,10 @@ int b200knn_ball_membership(b200knn_index *index, const void *query, int dtype, 
  * do that product on the device in float64 (one sequential FMA chain per output element: independent of chunking),
  * so neither the float64 blow-up of the images nor the projected matrix crosses PCIe.
  * projector: HOST float64 [in_dim][dim] row-major (leading dimension ld), dim = the handle's dim; may be replaced at
- * any time, applies to later calls.  rows: HOST [n][in_dim].  Results exactly as add() / query() on the projected rows. */
+ * any time, applies to later calls.  rows: HOST [n][in_dim].  Results exactly as add() / query() on the projected rows.
+ * Multi-device handles: every device keeps a copy of the projector; add_projected projects each shard's slice of the rows
+ * on that shard's device (its own PCIe link), query_projected projects on the first device and feeds the row-sharded
+ * collective query. */
 int b200knn_set_projector(b200knn_index *index, const double *projector, int64_t in_dim, int64_t ld);
 int b200knn_add_projected(b200knn_index *index, const void *rows, int dtype, int64_t n, int64_t ld);
 int b200knn_query_projected(b200knn_index *index, const void *rows, int dtype, int64_t nq, int64_t ld, int k, unsigned flags,
@@ -125,7 +131,7 @@ int b200knn_query_projected(b200knn_index *index, const void *rows, int dtype, i
 /* Debug / parity: the projected rows themselves.  out: HOST float64 [n][dim]. */
 int b200knn_project_rows(b200knn_index *index, const void *rows, int dtype, int64_t n, int64_t ld, double *out);
 
-/* ---- device-buffer entry points (inputs already resident in HBM; single-device handles) ---- */
+/* ---- device-buffer entry points (inputs already resident in HBM) ---- */
 
 /* Launch all work of this handle on `stream` (a cudaStream_t passed as void*, NULL = the
  * library's own stream).  Lets a host that owns streams (e.g. torch) time and order the work. */
@@ -134,12 +140,14 @@ int b200knn_set_stream(b200knn_index *index, void *stream);
 /* As b200knn_add, but `data` is a DEVICE pointer on the handle's device; the rows are NOT copied:
  * the index borrows the buffer until clear/destroy (the reference's ownership model, dci.h:78).
  * index_base is added to every returned index (row offset of this shard in a pool that is
- * row-sharded across processes; py_dci.c:185's data_idx_offset). */
+ * row-sharded across processes; py_dci.c:185's data_idx_offset).
+ * Multi-device handles: d_data may live on any device of the process (peer access); the handle shards the rows itself,
+ * COPYING each slice into its shard over NVLink (index_base must be 0), then indexes them like b200knn_add. */
 int b200knn_add_device(b200knn_index *index, const void *d_data, int dtype, int64_t n, int64_t ld,
                        int64_t index_base);
 
-/* As b200knn_query with DEVICE query / output buffers; asynchronous on the handle's stream unless
- * an exact second pass is needed (then it synchronises once).  d_out_idx: int32 nq x kk,
+/* As b200knn_query with DEVICE query / output buffers (single-device handles; the row-sharded form is
+ * b200knn_exchange_query_device); synchronises the handle's stream once, at the end.  d_out_idx: int32 nq x kk,
  * d_out_dist: float64 nq x kk. */
 int b200knn_query_device(b200knn_index *index, const void *d_query, int dtype, int64_t nq, int64_t ld, int k,
                          unsigned flags, int32_t *d_out_idx, double *d_out_dist, int *out_kk);

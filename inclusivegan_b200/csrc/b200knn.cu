@@ -15,11 +15,9 @@ struct b200knn_index {
     // multi-device gather buffers on shard 0
     DevBuf<int32_t> g_idx;
     DevBuf<double> g_dist;
-    // random projection (single-device handles): projector [proj_in_dim][dim], staging for unprojected rows, projected queries
-    DevBuf<double> projector;
+    // random projection: every shard keeps the projector [proj_in_dim][dim], a staging buffer for unprojected rows and one
+    // for projected queries (Shard::projector / proj_stage / proj_rows)
     int64_t proj_in_dim = 0;
-    DevBuf<unsigned char> proj_stage;
-    DevBuf<double> proj_rows;
     // multi-device handles: one exchange per non-empty shard, wired together in-process (b200knn_exchange_connect_local);
     // add() and query() then run the same collective protocol a torchrun job runs, one host thread per shard
     std::vector<b200knn_exchange *> exch;
@@ -122,6 +120,148 @@ int for_each_rank(int W, Fn fn) {
     return B200KNN_OK;
 }
 
+// a failed add leaves no half-built pool behind (device memory released, handle reusable)
+int cleanup_failed_add(b200knn_index *ix, int rc) {
+    if (rc != B200KNN_OK && rc != B200KNN_ESTATE && ix && ix->n_total == 0) {
+        const std::string msg = g_last_error;
+        for (auto &s : ix->shards) s.clear_pool();
+        cudaGetLastError();
+        g_last_error = msg;
+    }
+    return rc;
+}
+
+// Row-shard n rows over the handle's devices and index them.  fill(shard, d_rows, r0, rows) brings rows [r0, r0 + rows)
+// of the caller's matrix into the shard's own store (packed, dim elements per row), asynchronously on the shard's stream:
+// an upload from host memory, a peer copy of device rows, or a projection of unprojected rows.  One host thread per
+// shard (the PCIe links of the GPUs are independent); then, collectively over the non-empty shards, the global column
+// means over peer memory and one convert pass.
+template <typename Fill>
+int add_sharded(b200knn_index *ix, int64_t n, int dtype, Fill fill) {
+    const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
+    const int G = static_cast<int>(ix->shards.size());
+    const int64_t per = (n + G - 1) / G;
+    auto shard_add = [&](int g) -> int {
+        Shard &s = ix->shards[g];
+        const int64_t r0 = std::min<int64_t>(n, per * g), r1 = std::min<int64_t>(n, per * (g + 1));
+        const int64_t rows = r1 - r0;
+        if (rows <= 0) { s.n = 0; return B200KNN_OK; }
+        CU_TRY(cudaSetDevice(s.device));
+        TRY(s.x_store.ensure(static_cast<size_t>(rows) * ix->dim * esz));
+        void *d_rows = s.x_store.p;
+        int r = s.attach_pool(d_rows, true, dtype, rows, ix->dim, ix->dim, ix->kp, r0);
+        if (r != B200KNN_OK) return r;
+        TRY(fill(s, d_rows, r0, rows));
+        if (G > 1) return B200KNN_OK;        // phase 2 below: the centring vector is the GLOBAL column mean
+        TRY(s.compute_mean(d_rows, dtype, rows, ix->dim, ix->dim));
+        TRY(s.launch_convert(d_rows, dtype, rows, ix->dim, ix->dim, ix->kp, s.x_bf.p, s.xnorm_bf.p, s.x_err.p, s.scalars.p));
+        TRY(s.convert_pool_tier(ix->dim, ix->kp));
+        return B200KNN_OK;
+    };
+    if (G == 1) {
+        TRY(shard_add(0));
+    } else {
+        std::vector<int> rcs(G, B200KNN_OK);
+        std::vector<std::string> errs(G);
+        const int saved_threads = ix->shards[0].copy_threads;
+        for (auto &s : ix->shards) s.copy_threads = std::max(1, saved_threads * 2 / G);
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; g++)
+            th.emplace_back([&, g]() {
+                rcs[g] = shard_add(g);
+                if (rcs[g] != B200KNN_OK) errs[g] = g_last_error;
+            });
+        for (auto &t : th) t.join();
+        for (auto &s : ix->shards) s.copy_threads = saved_threads;
+        for (int g = 0; g < G; g++)
+            if (rcs[g] != B200KNN_OK) return fail(rcs[g], "%s", errs[g].c_str());
+        // phase 2 (collective over the non-empty shards; every rank got this far): column sums gathered over peer memory ->
+        // global means -> BF16 convert + norms
+        std::vector<int> active;
+        for (int g = 0; g < G; g++)
+            if (ix->shards[g].n > 0) active.push_back(g);
+        TRY(ensure_group(ix, active));
+        TRY(for_each_rank(static_cast<int>(active.size()), [&](int i) -> int {
+            Shard &s = ix->shards[active[i]];
+            CU_TRY(cudaSetDevice(s.device));
+            return ex_finish_add(ix->exch[i], s, ix->dim, ix->kp);
+        }));
+    }
+    for (auto &s : ix->shards) {
+        CU_TRY(cudaSetDevice(s.device));
+        CU_TRY(cudaStreamSynchronize(s.stream));   // the caller may free / overwrite its rows after return
+    }
+    ix->n_total = n;
+    return B200KNN_OK;
+}
+
+// Self-kNN on a multi-device handle: the rows of every shard, chunk by chunk, are the queries of one collective call
+// (b200knn_exchange_query_device's protocol, one host thread per shard).  The chunk's ORIGINAL rows are replicated to the
+// other shards over NVLink first (peer copies into their stage buffers: the protocol takes replicated device rows; every
+// shard then converts 1/G of them and broadcasts the BF16 slice).  Results are bit-identical to a single-device handle.
+int query_self_sharded(b200knn_index *ix, int k, unsigned flags, int32_t *out_idx, double *out_dist, int *out_kk) {
+    std::vector<int> active;
+    for (size_t g = 0; g < ix->shards.size(); g++)
+        if (ix->shards[g].n > 0) active.push_back(static_cast<int>(g));
+    const int W = static_cast<int>(active.size());
+    if (ix->exch.empty() || ix->exch_shards != active) return fail(B200KNN_ESTATE, "the handle's device group is not set up (add() does that)");
+    const int kk = static_cast<int>(std::min<int64_t>(k, ix->n_total));
+    if (out_kk) *out_kk = kk;
+    if (kk > ix->exch[0]->max_kk) return fail(B200KNN_EINVAL, "query_self on a multi-device handle serves k <= %d (single-device handles: any k)", ix->exch[0]->max_kk);
+    const int dim = ix->dim;
+    const int64_t step_rows = std::min<int64_t>(ix->exch[0]->max_nq, QUERY_CHUNK);
+    Shard &s0 = ix->shards[active[0]];
+    // Every allocation of every rank FIRST, for every chunk size that will occur: once a rank's flag-waiting kernels are in
+    // flight no rank may allocate (with peer access enabled, cudaMalloc / cudaFree touch the peers' address spaces and can
+    // wait for a kernel that itself waits for this rank — the rule of ex_query_host_prepare)
+    {
+        std::vector<int64_t> sizes;
+        for (int r = 0; r < W; r++)
+            for (int64_t q0 = 0; q0 < ix->shards[active[r]].n; q0 += step_rows) {
+                const int64_t cq = std::min(step_rows, ix->shards[active[r]].n - q0);
+                if (std::find(sizes.begin(), sizes.end(), cq) == sizes.end()) sizes.push_back(cq);
+            }
+        const int64_t max_cq = *std::max_element(sizes.begin(), sizes.end());
+        for (int i = 0; i < W; i++) {
+            Shard &s = ix->shards[active[i]];
+            CU_TRY(cudaSetDevice(s.device));
+            TRY(s.out_idx.ensure(static_cast<size_t>(max_cq) * kk));
+            TRY(s.out_dist.ensure(static_cast<size_t>(max_cq) * kk));
+            TRY(s.q_stage.ensure(static_cast<size_t>(max_cq) * dim * 8));
+            ExCall scratch;
+            TRY(ex_begin_query(ix->exch[i], s, max_cq, k, flags, scratch));
+            for (int64_t cq : sizes) TRY(s.reserve_pass(cq, ix->kp, scratch.kk_l, W > 1 && s.tier == 0));
+        }
+    }
+    for (int r = 0; r < W; r++) {
+        Shard &src = ix->shards[active[r]];
+        const size_t esz = src.x_dtype == B200KNN_F64 ? 8 : 4;
+        for (int64_t q0 = 0; q0 < src.n; q0 += step_rows) {
+            const int64_t cq = std::min(step_rows, src.n - q0);
+            const char *rows_src = static_cast<const char *>(src.x_raw) + static_cast<size_t>(q0) * src.ld_x * esz;
+            for (int i = 0; i < W; i++) {           // replicate the chunk's original rows (peer copies on the receivers' streams)
+                Shard &s = ix->shards[active[i]];
+                if (i == r) continue;
+                CU_TRY(cudaSetDevice(s.device));
+                CU_TRY(cudaMemcpy2DAsync(s.q_stage.p, static_cast<size_t>(dim) * esz, rows_src, static_cast<size_t>(src.ld_x) * esz, static_cast<size_t>(dim) * esz,
+                                         static_cast<size_t>(cq), cudaMemcpyDefault, s.stream));
+            }
+            TRY(for_each_rank(W, [&](int i) -> int {
+                Shard &s = ix->shards[active[i]];
+                CU_TRY(cudaSetDevice(s.device));
+                const void *dq = (i == r) ? static_cast<const void *>(rows_src) : static_cast<const void *>(s.q_stage.p);
+                return ex_query_device(ix->exch[i], s, dim, ix->kp, dq, src.x_dtype, cq, (i == r) ? src.ld_x : dim, k, flags, s.out_idx.p, s.out_dist.p, nullptr);
+            }));
+            CU_TRY(cudaSetDevice(s0.device));        // every rank holds the merged lists; shard 0's copy goes to the caller
+            const int64_t g0 = src.index_base + q0;
+            CU_TRY(cudaMemcpyAsync(out_idx + g0 * kk, s0.out_idx.p, static_cast<size_t>(cq) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s0.stream));
+            CU_TRY(cudaMemcpyAsync(out_dist + g0 * kk, s0.out_dist.p, static_cast<size_t>(cq) * kk * sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
+            CU_TRY(cudaStreamSynchronize(s0.stream));
+        }
+    }
+    return B200KNN_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -171,9 +311,6 @@ int b200knn_destroy(b200knn_index *ix) {
         cudaSetDevice(ix->shards[0].device);
         ix->g_idx.release();
         ix->g_dist.release();
-        ix->projector.release();
-        ix->proj_stage.release();
-        ix->proj_rows.release();
     }
     delete ix;
     return B200KNN_OK;
@@ -268,9 +405,20 @@ static int check_matrix_args(const b200knn_index *ix, const void *p, int dtype, 
 int b200knn_add_device(b200knn_index *ix, const void *d_data, int dtype, int64_t n, int64_t ld, int64_t index_base) {
     TRY(check_matrix_args(ix, d_data, dtype, n, ld, "data"));
     if (ix->n_total > 0) return fail(B200KNN_ESTATE, "index already holds %lld points; clear() it first", (long long)ix->n_total);
-    if (ix->device_ids.size() > 1) return fail(B200KNN_EINVAL, "add_device is only valid for single-device handles");
     if (n == 0) return B200KNN_OK;
     TRY(ix->ensure_devices());
+    if (ix->shards.size() > 1) {
+        // multi-device handle: the rows (on any device of the process) are COPIED into the shards, slice by slice over
+        // NVLink, then indexed like a host add (global column means over peer memory, convert)
+        if (index_base != 0) return fail(B200KNN_EINVAL, "index_base must be 0 on a multi-device handle (it shards the rows itself)");
+        const int rc = add_sharded(ix, n, dtype, [&](Shard &s, void *d_rows, int64_t r0, int64_t rows) -> int {
+            const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
+            CU_TRY(cudaMemcpy2DAsync(d_rows, static_cast<size_t>(ix->dim) * esz, static_cast<const char *>(d_data) + static_cast<size_t>(r0) * ld * esz,
+                                     static_cast<size_t>(ld) * esz, static_cast<size_t>(ix->dim) * esz, static_cast<size_t>(rows), cudaMemcpyDefault, s.stream));
+            return B200KNN_OK;
+        });
+        return cleanup_failed_add(ix, rc);
+    }
     Shard &s = ix->shards[0];
     CU_TRY(cudaSetDevice(s.device));
     TRY(s.attach_pool(d_data, false, dtype, n, ld, ix->dim, ix->kp, index_base));
@@ -287,75 +435,14 @@ static int add_impl(b200knn_index *ix, const void *data, int dtype, int64_t n, i
     if (n == 0) return B200KNN_OK;
     TRY(ix->ensure_devices());
     const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
-    const int G = static_cast<int>(ix->shards.size());
-    const int64_t per = (n + G - 1) / G;
-    // one host thread per shard: the PCIe links of the GPUs are independent, and the per-shard work is
-    // upload (pinned ring for pageable sources) -> column means -> one convert pass
-    auto shard_add = [&](int g) -> int {
-        Shard &s = ix->shards[g];
-        const int64_t r0 = std::min<int64_t>(n, per * g), r1 = std::min<int64_t>(n, per * (g + 1));
-        const int64_t rows = r1 - r0;
-        if (rows <= 0) { s.n = 0; return B200KNN_OK; }
-        CU_TRY(cudaSetDevice(s.device));
-        TRY(s.x_store.ensure(static_cast<size_t>(rows) * ix->dim * esz));
-        void *d_rows = s.x_store.p;
-        int r = s.attach_pool(d_rows, true, dtype, rows, ix->dim, ix->dim, ix->kp, r0);
-        if (r != B200KNN_OK) return r;
-        const char *src = static_cast<const char *>(data) + static_cast<size_t>(r0) * ld * esz;
-        TRY(s.upload_rows(d_rows, src, rows, ix->dim * esz, ld * esz, s.stream));
-        if (G > 1) return B200KNN_OK;        // phase 2 below: the centring vector is the GLOBAL column mean
-        TRY(s.compute_mean(d_rows, dtype, rows, ix->dim, ix->dim));
-        TRY(s.launch_convert(d_rows, dtype, rows, ix->dim, ix->dim, ix->kp, s.x_bf.p, s.xnorm_bf.p, s.x_err.p, s.scalars.p));
-        TRY(s.convert_pool_tier(ix->dim, ix->kp));
-        return B200KNN_OK;
-    };
-    if (G == 1) {
-        TRY(shard_add(0));
-    } else {
-        std::vector<int> rcs(G, B200KNN_OK);
-        std::vector<std::string> errs(G);
-        const int saved_threads = ix->shards[0].copy_threads;
-        for (auto &s : ix->shards) s.copy_threads = std::max(1, saved_threads * 2 / G);
-        std::vector<std::thread> th;
-        for (int g = 0; g < G; g++)
-            th.emplace_back([&, g]() {
-                rcs[g] = shard_add(g);
-                if (rcs[g] != B200KNN_OK) errs[g] = g_last_error;
-            });
-        for (auto &t : th) t.join();
-        for (auto &s : ix->shards) s.copy_threads = saved_threads;
-        for (int g = 0; g < G; g++)
-            if (rcs[g] != B200KNN_OK) return fail(rcs[g], "%s", errs[g].c_str());
-        // phase 2 (collective over the non-empty shards; every rank got this far): column sums gathered over peer memory ->
-        // global means -> BF16 convert + norms
-        std::vector<int> active;
-        for (int g = 0; g < G; g++)
-            if (ix->shards[g].n > 0) active.push_back(g);
-        TRY(ensure_group(ix, active));
-        TRY(for_each_rank(static_cast<int>(active.size()), [&](int i) -> int {
-            Shard &s = ix->shards[active[i]];
-            CU_TRY(cudaSetDevice(s.device));
-            return ex_finish_add(ix->exch[i], s, ix->dim, ix->kp);
-        }));
-    }
-    for (auto &s : ix->shards) {
-        CU_TRY(cudaSetDevice(s.device));
-        CU_TRY(cudaStreamSynchronize(s.stream));   // the caller may free / overwrite `data` after return
-    }
-    ix->n_total = n;
-    return B200KNN_OK;
+    return add_sharded(ix, n, dtype, [&](Shard &s, void *d_rows, int64_t r0, int64_t rows) -> int {
+        // upload (pinned ring for pageable sources)
+        return s.upload_rows(d_rows, static_cast<const char *>(data) + static_cast<size_t>(r0) * ld * esz, rows, ix->dim * esz, ld * esz, s.stream);
+    });
 }
 
 int b200knn_add(b200knn_index *ix, const void *data, int dtype, int64_t n, int64_t ld) {
-    const int rc = add_impl(ix, data, dtype, n, ld);
-    if (rc != B200KNN_OK && rc != B200KNN_ESTATE && ix && ix->n_total == 0) {
-        // a failed add leaves no half-built pool behind (device memory released, handle reusable)
-        const std::string msg = g_last_error;
-        for (auto &s : ix->shards) s.clear_pool();
-        cudaGetLastError();
-        g_last_error = msg;
-    }
-    return rc;
+    return cleanup_failed_add(ix, add_impl(ix, data, dtype, n, ld));
 }
 
 int b200knn_debug_plan(int64_t n, int64_t nq, int kp, int num_sms, int cta_group, int max_slots, int a_budget_mb, int wide_mode,
@@ -591,8 +678,8 @@ int b200knn_query_self(b200knn_index *ix, int k, unsigned flags, int32_t *out_id
     if (!ix) return fail(B200KNN_EINVAL, "index is NULL");
     if (k <= 0) return fail(B200KNN_EINVAL, "k must be positive (got %d)", k);
     if (ix->n_total <= 0) return fail(B200KNN_ESTATE, "query on an empty index");
-    if (ix->shards.size() != 1) return fail(B200KNN_EINVAL, "query_self is only valid for single-device handles");
     if (!out_idx || !out_dist) return fail(B200KNN_EINVAL, "output buffer is NULL");
+    if (ix->shards.size() != 1) return query_self_sharded(ix, k, flags, out_idx, out_dist, out_kk);
     Shard &s = ix->shards[0];
     const int kk = static_cast<int>(std::min<int64_t>(k, s.n));
     if (out_kk) *out_kk = kk;
@@ -642,7 +729,6 @@ int b200knn_query_self(b200knn_index *ix, int k, unsigned flags, int32_t *out_id
 // ---- random projection on the device ----
 static int check_projected_args(b200knn_index *ix, const void *p, int dtype, int64_t rows, int64_t ld, const char *what) {
     if (!ix) return fail(B200KNN_EINVAL, "index is NULL");
-    if (ix->device_ids.size() > 1) return fail(B200KNN_EINVAL, "the projected entry points are only valid for single-device handles");
     if (ix->proj_in_dim <= 0) return fail(B200KNN_ESTATE, "no projector set (b200knn_set_projector)");
     if (!p && rows > 0) return fail(B200KNN_EINVAL, "%s pointer is NULL", what);
     if (dtype != B200KNN_F64 && dtype != B200KNN_F32) return fail(B200KNN_EINVAL, "%s dtype %d is not B200KNN_F64/F32", what, dtype);
@@ -652,23 +738,24 @@ static int check_projected_args(b200knn_index *ix, const void *p, int dtype, int
     return B200KNN_OK;
 }
 
-// rows [n][in_dim] on the HOST -> d_out [n][dim] float64 on the device, in row chunks through the staging buffer
+// rows [n][in_dim] on the HOST -> d_out [n][dim] float64 on shard s's device, in row chunks through its staging buffer
+// (every shard holds its own copy of the projector)
 static int project_host_rows(b200knn_index *ix, Shard &s, const void *rows, int dtype, int64_t n, int64_t ld, double *d_out) {
     const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
     const int64_t in_dim = ix->proj_in_dim;
     const int64_t chunk = std::max<int64_t>(PJ_T, std::min<int64_t>((n + PJ_T - 1) / PJ_T * PJ_T, (512ll << 20) / (in_dim * static_cast<int64_t>(esz)) / PJ_T * PJ_T));
-    TRY(ix->proj_stage.ensure(static_cast<size_t>(std::min(chunk, n)) * in_dim * esz));
+    TRY(s.proj_stage.ensure(static_cast<size_t>(std::min(chunk, n)) * in_dim * esz));
     for (int64_t r0 = 0; r0 < n; r0 += chunk) {
         const int64_t cr = std::min(chunk, n - r0);
-        TRY(s.upload_rows(ix->proj_stage.p, static_cast<const char *>(rows) + static_cast<size_t>(r0) * ld * esz, cr, static_cast<size_t>(in_dim) * esz,
+        TRY(s.upload_rows(s.proj_stage.p, static_cast<const char *>(rows) + static_cast<size_t>(r0) * ld * esz, cr, static_cast<size_t>(in_dim) * esz,
                           static_cast<size_t>(ld) * esz, s.stream));
         const dim3 grid(static_cast<unsigned>((ix->dim + PJ_T - 1) / PJ_T), static_cast<unsigned>((cr + PJ_T - 1) / PJ_T));
         s.stats.kernel_launches++;
         if (dtype == B200KNN_F64)
-            project_kernel<double><<<grid, 256, 0, s.stream>>>(reinterpret_cast<const double *>(ix->proj_stage.p), in_dim, static_cast<int>(cr), ix->projector.p,
+            project_kernel<double><<<grid, 256, 0, s.stream>>>(reinterpret_cast<const double *>(s.proj_stage.p), in_dim, static_cast<int>(cr), s.projector.p,
                                                                static_cast<int>(in_dim), ix->dim, d_out + r0 * ix->dim, ix->dim);
         else
-            project_kernel<float><<<grid, 256, 0, s.stream>>>(reinterpret_cast<const float *>(ix->proj_stage.p), in_dim, static_cast<int>(cr), ix->projector.p,
+            project_kernel<float><<<grid, 256, 0, s.stream>>>(reinterpret_cast<const float *>(s.proj_stage.p), in_dim, static_cast<int>(cr), s.projector.p,
                                                               static_cast<int>(in_dim), ix->dim, d_out + r0 * ix->dim, ix->dim);
         CU_TRY(cudaGetLastError());
         // the next chunk's upload reuses the staging buffer: its DMA is enqueued on the same stream, behind this kernel
@@ -678,17 +765,18 @@ static int project_host_rows(b200knn_index *ix, Shard &s, const void *rows, int 
 
 int b200knn_set_projector(b200knn_index *ix, const double *projector, int64_t in_dim, int64_t ld) {
     if (!ix) return fail(B200KNN_EINVAL, "index is NULL");
-    if (ix->device_ids.size() > 1) return fail(B200KNN_EINVAL, "the projected entry points are only valid for single-device handles");
     if (!projector) return fail(B200KNN_EINVAL, "projector pointer is NULL");
     if (in_dim <= 0 || in_dim > 0x7fffffffll) return fail(B200KNN_EINVAL, "projector input dim %lld out of range", (long long)in_dim);
     if (ld < ix->dim) return fail(B200KNN_EINVAL, "projector leading dimension %lld < dim %d", (long long)ld, ix->dim);
     TRY(ix->ensure_devices());
-    Shard &s = ix->shards[0];
-    CU_TRY(cudaSetDevice(s.device));
-    CU_TRY(cudaStreamSynchronize(s.stream));          // nothing in flight may still read the previous projector
-    TRY(ix->projector.ensure(static_cast<size_t>(in_dim) * ix->dim));
-    TRY(s.upload_rows(ix->projector.p, reinterpret_cast<const char *>(projector), in_dim, static_cast<size_t>(ix->dim) * 8, static_cast<size_t>(ld) * 8, s.stream));
-    CU_TRY(cudaStreamSynchronize(s.stream));
+    ix->proj_in_dim = 0;
+    for (auto &s : ix->shards) {       // every device of the handle keeps a copy (a few MB: in_dim x dim float64)
+        CU_TRY(cudaSetDevice(s.device));
+        CU_TRY(cudaStreamSynchronize(s.stream));          // nothing in flight may still read the previous projector
+        TRY(s.projector.ensure(static_cast<size_t>(in_dim) * ix->dim));
+        TRY(s.upload_rows(s.projector.p, reinterpret_cast<const char *>(projector), in_dim, static_cast<size_t>(ix->dim) * 8, static_cast<size_t>(ld) * 8, s.stream));
+        CU_TRY(cudaStreamSynchronize(s.stream));
+    }
     ix->proj_in_dim = in_dim;
     return B200KNN_OK;
 }
@@ -699,41 +787,22 @@ int b200knn_project_rows(b200knn_index *ix, const void *rows, int dtype, int64_t
     if (!out) return fail(B200KNN_EINVAL, "output buffer is NULL");
     Shard &s = ix->shards[0];
     CU_TRY(cudaSetDevice(s.device));
-    TRY(ix->proj_rows.ensure(static_cast<size_t>(n) * ix->dim));
-    TRY(project_host_rows(ix, s, rows, dtype, n, ld, ix->proj_rows.p));
-    CU_TRY(cudaMemcpyAsync(out, ix->proj_rows.p, static_cast<size_t>(n) * ix->dim * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    TRY(s.proj_rows.ensure(static_cast<size_t>(n) * ix->dim));
+    TRY(project_host_rows(ix, s, rows, dtype, n, ld, s.proj_rows.p));
+    CU_TRY(cudaMemcpyAsync(out, s.proj_rows.p, static_cast<size_t>(n) * ix->dim * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     CU_TRY(cudaStreamSynchronize(s.stream));
     return B200KNN_OK;
 }
 
-static int add_projected_impl(b200knn_index *ix, const void *rows, int dtype, int64_t n, int64_t ld) {
+int b200knn_add_projected(b200knn_index *ix, const void *rows, int dtype, int64_t n, int64_t ld) {
     TRY(check_projected_args(ix, rows, dtype, n, ld, "rows"));
     if (ix->n_total > 0) return fail(B200KNN_ESTATE, "index already holds %lld points; clear() it first", (long long)ix->n_total);
     if (n == 0) return B200KNN_OK;
-    Shard &s = ix->shards[0];
-    CU_TRY(cudaSetDevice(s.device));
-    TRY(s.x_store.ensure(static_cast<size_t>(n) * ix->dim * sizeof(double)));
-    void *d_pool = s.x_store.p;
-    int r = s.attach_pool(d_pool, true, B200KNN_F64, n, ix->dim, ix->dim, ix->kp, 0);   // the shard owns d_pool from here
-    if (r != B200KNN_OK) return r;
-    TRY(project_host_rows(ix, s, rows, dtype, n, ld, static_cast<double *>(d_pool)));
-    TRY(s.compute_mean(d_pool, B200KNN_F64, n, ix->dim, ix->dim));
-    TRY(s.launch_convert(d_pool, B200KNN_F64, n, ix->dim, ix->dim, ix->kp, s.x_bf.p, s.xnorm_bf.p, s.x_err.p, s.scalars.p));
-    TRY(s.convert_pool_tier(ix->dim, ix->kp));
-    CU_TRY(cudaStreamSynchronize(s.stream));          // the caller may free / overwrite `rows` after return
-    ix->n_total = n;
-    return B200KNN_OK;
-}
-
-int b200knn_add_projected(b200knn_index *ix, const void *rows, int dtype, int64_t n, int64_t ld) {
-    const int rc = add_projected_impl(ix, rows, dtype, n, ld);
-    if (rc != B200KNN_OK && rc != B200KNN_ESTATE && ix && ix->n_total == 0) {
-        const std::string msg = g_last_error;
-        for (auto &s : ix->shards) s.clear_pool();
-        cudaGetLastError();
-        g_last_error = msg;
-    }
-    return rc;
+    const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
+    // every shard projects its own slice of the rows straight into its store (float64), then the usual indexing
+    return cleanup_failed_add(ix, add_sharded(ix, n, B200KNN_F64, [&](Shard &s, void *d_rows, int64_t r0, int64_t cnt) -> int {
+        return project_host_rows(ix, s, static_cast<const char *>(rows) + static_cast<size_t>(r0) * ld * esz, dtype, cnt, ld, static_cast<double *>(d_rows));
+    }));
 }
 
 int b200knn_query_projected(b200knn_index *ix, const void *rows, int dtype, int64_t nq, int64_t ld, int k, unsigned flags,
@@ -742,19 +811,41 @@ int b200knn_query_projected(b200knn_index *ix, const void *rows, int dtype, int6
     if (k <= 0) return fail(B200KNN_EINVAL, "k must be positive (got %d)", k);
     if (ix->n_total <= 0) return fail(B200KNN_ESTATE, "query on an empty index");
     if (nq > 0 && (!out_idx || !out_dist)) return fail(B200KNN_EINVAL, "output buffer is NULL");
-    Shard &s = ix->shards[0];
-    const int kk = static_cast<int>(std::min<int64_t>(k, s.n));
+    const int kk = static_cast<int>(std::min<int64_t>(k, ix->n_total));
     if (out_kk) *out_kk = kk;
     if (nq == 0) return B200KNN_OK;
+    Shard &s = ix->shards[0];
+    const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
     CU_TRY(cudaSetDevice(s.device));
+    TRY(s.proj_rows.ensure(static_cast<size_t>(std::min(nq, QUERY_CHUNK)) * ix->dim));
+    if (ix->shards.size() > 1) {
+        // multi-device handle: shard 0 projects a chunk, the projected rows go through pinned host memory into the
+        // collective query (every shard uploads 1/G of them over its own link) — same answers as on one device
+        const int64_t step = std::min(nq, QUERY_CHUNK);
+        double *h_rows = nullptr;
+        CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&h_rows), static_cast<size_t>(step) * ix->dim * sizeof(double)));
+        int rc = B200KNN_OK;
+        for (int64_t q0 = 0; q0 < nq && rc == B200KNN_OK; q0 += step) {
+            const int64_t cq = std::min(step, nq - q0);
+            rc = project_host_rows(ix, s, static_cast<const char *>(rows) + static_cast<size_t>(q0) * ld * esz, dtype, cq, ld, s.proj_rows.p);
+            if (rc == B200KNN_OK && (cudaMemcpyAsync(h_rows, s.proj_rows.p, static_cast<size_t>(cq) * ix->dim * sizeof(double), cudaMemcpyDeviceToHost, s.stream) != cudaSuccess ||
+                                     cudaStreamSynchronize(s.stream) != cudaSuccess))
+                rc = fail(B200KNN_ECUDA, "reading back the projected rows failed: %s", cudaGetErrorString(cudaGetLastError()));
+            if (rc == B200KNN_OK) rc = b200knn_query(ix, h_rows, B200KNN_F64, cq, ix->dim, k, flags, out_idx + q0 * kk, out_dist + q0 * kk, nullptr);
+            cudaSetDevice(s.device);
+        }
+        const std::string msg = g_last_error;
+        cudaSetDevice(s.device);
+        cudaFreeHost(h_rows);
+        g_last_error = msg;
+        return rc;
+    }
     TRY(s.out_idx.ensure(static_cast<size_t>(std::min(nq, QUERY_CHUNK)) * kk));
     TRY(s.out_dist.ensure(static_cast<size_t>(std::min(nq, QUERY_CHUNK)) * kk));
-    TRY(ix->proj_rows.ensure(static_cast<size_t>(std::min(nq, QUERY_CHUNK)) * ix->dim));
-    const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
     for (int64_t q0 = 0; q0 < nq; q0 += QUERY_CHUNK) {
         const int64_t cq = std::min(QUERY_CHUNK, nq - q0);
-        TRY(project_host_rows(ix, s, static_cast<const char *>(rows) + static_cast<size_t>(q0) * ld * esz, dtype, cq, ld, ix->proj_rows.p));
-        TRY(s.query_device_sync(ix->proj_rows.p, B200KNN_F64, cq, ix->dim, ix->dim, ix->kp, k, flags, s.out_idx.p, s.out_dist.p));
+        TRY(project_host_rows(ix, s, static_cast<const char *>(rows) + static_cast<size_t>(q0) * ld * esz, dtype, cq, ld, s.proj_rows.p));
+        TRY(s.query_device_sync(s.proj_rows.p, B200KNN_F64, cq, ix->dim, ix->dim, ix->kp, k, flags, s.out_idx.p, s.out_dist.p));
         CU_TRY(cudaMemcpyAsync(out_idx + q0 * kk, s.out_idx.p, static_cast<size_t>(cq) * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         CU_TRY(cudaMemcpyAsync(out_dist + q0 * kk, s.out_dist.p, static_cast<size_t>(cq) * kk * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         CU_TRY(cudaStreamSynchronize(s.stream));

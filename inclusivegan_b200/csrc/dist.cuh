@@ -66,6 +66,7 @@ struct PlanParams {
     unsigned int *stream_sync;     // [sync_entries] zeroed
     int sync_entries;
     unsigned int *zero_a;          // nullable single counters to zero (first pass: the uncertified count)
+    unsigned int *zero_b;          // (first pass: the work counter of the persistent re-rank warps)
     int *zero_list;                // nullable [zero_list_n] (second pass: coll_count)
     int zero_list_n;
     unsigned int *total_uncertified;   // nullable: += count (second pass accounting)
@@ -77,6 +78,7 @@ plan_pass_kernel(const PlanParams p) {
         if (p.total_uncertified && cnt > 0) atomicAdd(p.total_uncertified, static_cast<unsigned int>(cnt));
         *p.round_counter = 0u;
         if (p.zero_a) *p.zero_a = 0u;
+        if (p.zero_b) *p.zero_b = 0u;
     }
     for (int i = threadIdx.x; i < p.sync_entries; i += blockDim.x) p.stream_sync[i] = 0u;
     for (int i = threadIdx.x; i < p.zero_list_n; i += blockDim.x) p.zero_list[i] = 0;

@@ -56,30 +56,37 @@ __device__ __forceinline__ double canon_d2(const TX *__restrict__ xr, const TQ *
 }
 
 // bit-identical to canon_d2, no block barrier — lets the warps of a block work on different candidates.
+// U: 256-element groups per step.  Every step issues all its loads (16 U per lane) before any arithmetic, and a step cannot
+// start before the previous one has consumed its values: one memory latency per step.  float32 rows take two groups per
+// step (the same bytes in flight as one group of float64); the order of additions into each accumulator is unchanged.
 template <typename TX, typename TQ>
 __device__ __forceinline__ double canon_d2_warp(const TX *__restrict__ xr, const TQ *__restrict__ qr, int dim, int lane) {
+    constexpr int U = (sizeof(TX) + sizeof(TQ) <= 8) ? 2 : 1;
     double a[4][2] = {};
-    for (int base = 0; base < dim; base += 256) {
-        // all sixteen loads of the step first (see keep()), then the arithmetic
-        TQ qv[8];
-        TX xv[8];
+    for (int base = 0; base < dim; base += 256 * U) {
+        TQ qv[8 * U];
+        TX xv[8 * U];
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
-            const int e0 = base + lane + 32 * g, e1 = e0 + 128;
-            qv[2 * g] = (e0 < dim) ? qr[e0] : TQ(0);
-            xv[2 * g] = (e0 < dim) ? xr[e0] : TX(0);
-            qv[2 * g + 1] = (e1 < dim) ? qr[e1] : TQ(0);
-            xv[2 * g + 1] = (e1 < dim) ? xr[e1] : TX(0);
-        }
+        for (int u = 0; u < U; u++)
 #pragma unroll
-        for (int i = 0; i < 8; i++) { keep(qv[i]); keep(xv[i]); }
+            for (int g = 0; g < 4; g++) {
+                const int e0 = base + 256 * u + lane + 32 * g, e1 = e0 + 128;
+                qv[8 * u + 2 * g] = (e0 < dim) ? qr[e0] : TQ(0);
+                xv[8 * u + 2 * g] = (e0 < dim) ? xr[e0] : TX(0);
+                qv[8 * u + 2 * g + 1] = (e1 < dim) ? qr[e1] : TQ(0);
+                xv[8 * u + 2 * g + 1] = (e1 < dim) ? xr[e1] : TX(0);
+            }
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
-            const double d0 = static_cast<double>(qv[2 * g]) - static_cast<double>(xv[2 * g]);
-            const double d1 = static_cast<double>(qv[2 * g + 1]) - static_cast<double>(xv[2 * g + 1]);
-            a[g][0] = fma(d0, d0, a[g][0]);      // out-of-range elements are 0 - 0: they add nothing
-            a[g][1] = fma(d1, d1, a[g][1]);
-        }
+        for (int i = 0; i < 8 * U; i++) { keep(qv[i]); keep(xv[i]); }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const double d0 = static_cast<double>(qv[8 * u + 2 * g]) - static_cast<double>(xv[8 * u + 2 * g]);
+                const double d1 = static_cast<double>(qv[8 * u + 2 * g + 1]) - static_cast<double>(xv[8 * u + 2 * g + 1]);
+                a[g][0] = fma(d0, d0, a[g][0]);      // out-of-range elements are 0 - 0: they add nothing
+                a[g][1] = fma(d1, d1, a[g][1]);
+            }
     }
     const double w0 = warp_sum(a[0][0] + a[0][1]), w1 = warp_sum(a[1][0] + a[1][1]);
     const double w2 = warp_sum(a[2][0] + a[2][1]), w3 = warp_sum(a[3][0] + a[3][1]);
@@ -499,16 +506,10 @@ __device__ __forceinline__ int tighten_survivors_warp(const RerankParams &p, int
     return p.kk + cnt;
 }
 
-template <typename TX, typename TQ, int C, int WPB>
-__global__ void __launch_bounds__(WPB * 32, 3)
-rerank_warp_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const RerankParams p, int nq, int P /* pow2 >= max_slots * C */) {
-    extern __shared__ unsigned long long keys_all[];   // [WPB][P]
-    __shared__ double d2s_all[WPB][C];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = blockIdx.x * WPB + warp;
-    if (q >= nq) return;                               // (the warps of a block never meet at a barrier)
-    unsigned long long *keys = keys_all + static_cast<size_t>(warp) * P;
-    double *d2s = d2s_all[warp];
+// one query, one warp; keys: P entries of this warp's shared memory, d2s: C entries
+template <typename TX, typename TQ, int C>
+__device__ __forceinline__ void rerank_one_query_warp(const TX *__restrict__ x, const TQ *__restrict__ qmat, const RerankParams &p, int q, int lane,
+                                                      unsigned long long *keys, double *d2s) {
     if (p.ext_bounds && p.min_score) {                 // row-sharded pools: no candidate survives the global bound (see rerank_kernel)
         const double u = ext_bound_of(p, q);
         const float ms = __ldg(p.min_score + q);
@@ -574,6 +575,28 @@ rerank_warp_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const 
     }
     __syncwarp();
     rerank_finish<C>(p, q, keys, d2s, lane, u_ext);
+    __syncwarp();                                      // keys / d2s are reused by this warp's next query
+}
+
+// Persistent warps: every warp draws its next query from a device counter (zeroed by the pass's plan_pass_kernel), so a
+// query with sixteen surviving candidates does not hold back seven warps that drew easy ones (ncu of the first version,
+// 8 queries per block, one block per 8 queries: achieved occupancy 21.7 % of a theoretical 37.5 %).
+template <typename TX, typename TQ, int C, int WPB>
+__global__ void __launch_bounds__(WPB * 32, 3)
+rerank_warp_kernel(const TX *__restrict__ x, const TQ *__restrict__ qmat, const RerankParams p, int nq, int P /* pow2 >= max_slots * C */,
+                   unsigned int *__restrict__ next_query) {
+    extern __shared__ unsigned long long keys_all[];   // [WPB][P]
+    __shared__ double d2s_all[WPB][C];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long *keys = keys_all + static_cast<size_t>(warp) * P;
+    double *d2s = d2s_all[warp];
+    for (;;) {                                         // (the warps of a block never meet at a barrier)
+        unsigned int q = 0;
+        if (lane == 0) q = atomicAdd(next_query, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= static_cast<unsigned int>(nq)) break;
+        rerank_one_query_warp<TX, TQ, C>(x, qmat, p, static_cast<int>(q), lane, keys, d2s);
+    }
 }
 
 // Second pass, part 2: exact re-rank of the collected lists.  The number of lists is read from device memory (the

@@ -38,7 +38,8 @@ struct Shard {
                                      // the pass in flight, [5] overflow count of the call, [6] grid-barrier counter of the distance kernel,
                                      // [7] max (r_j + e_j) bits (ball membership), [8] uncertified queries since the last stats reset,
                                      // [9] done counter of bound_publish_kernel, [10..12] tier maxima of the pool (||x^||^2, ||x - x^||,
-                                     // ||x_lo||), [13..15] the same for the queries of the pass (unused)
+                                     // ||x_lo||), [13..15] the same for the queries of the pass (unused), [16] next query of the
+                                     // persistent re-rank warps
     CUtensorMap tmap_x;              // pool, 256-row box (1-CTA kernel)
     CUtensorMap tmap_x128;           // pool, 128-row box (each CTA of a pair stages half of the 256-row tile)
     int forced_cg = 0;               // $B200KNN_CTA_GROUP=1|2 pins the kernel flavour (A/B measurements)
@@ -68,6 +69,9 @@ struct Shard {
     DevBuf<double> scan_d2;
     DevBuf<unsigned long long> scan_key;   // k > 32: (key, index) scratch of scan_topk_kernel, [queries][2][kk]
     DevBuf<int> scan_idx;
+    DevBuf<double> projector;        // random projection (b200knn_set_projector): this device's copy of the projector [in_dim][dim],
+    DevBuf<unsigned char> proj_stage;   // staging for unprojected rows, projected query rows
+    DevBuf<double> proj_rows;
     DevBuf<unsigned char> q_stage;   // host API: device copy of the caller's query rows
     DevBuf<unsigned char> q_stage2;  // second buffer: the upload of chunk i+1 overlaps the compute of chunk i
     cudaStream_t copy_stream = nullptr;
@@ -105,8 +109,8 @@ struct Shard {
             CU_TRY(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
             CU_TRY(cudaEventCreateWithFlags(&ev_consumed[i], cudaEventDisableTiming));
         }
-        TRY(scalars.ensure(16));
-        CU_TRY(cudaMemsetAsync(scalars.p, 0, 16 * sizeof(unsigned int), stream));
+        TRY(scalars.ensure(32));
+        CU_TRY(cudaMemsetAsync(scalars.p, 0, 32 * sizeof(unsigned int), stream));
         CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&h_count), 4 * sizeof(int)));
         TRY(set_kernel_attrs());
         ready = true;
@@ -269,6 +273,7 @@ struct Shard {
         drain_events();
         q_bf.release(); qnorm_bf.release(); q_err.release(); q_bf2.release(); uncert_thr.release(); min_score.release(); coll_count.release(); coll_idx.release(); overflow_list.release(); sched_items.release(); sched_items2.release(); sched_slots.release(); stream_sync.release(); radius2.release(); colterm.release(); rowthr.release(); member.release(); cand_s.release(); cand_i.release(); uncert_list.release();
         scan_d2.release(); scan_key.release(); scan_idx.release();
+        projector.release(); proj_stage.release(); proj_rows.release();
         q_stage.release(); q_stage2.release(); out_idx.release(); out_dist.release(); pad_idx.release(); pad_dist.release(); scalars.release();
         if (h_count) cudaFreeHost(h_count);
         if (own_stream) cudaStreamDestroy(own_stream);
@@ -665,17 +670,19 @@ struct Shard {
     static constexpr int RR_WPB = 8;
     template <int C>
     void launch_rerank_warp(const void *d_query, int q_dtype, int64_t nq, int pk, const RerankParams &rp) {
-        const unsigned g = static_cast<unsigned>((nq + RR_WPB - 1) / RR_WPB);
+        // persistent: as many blocks as can be resident (3 per SM at 80 registers), every warp draws queries from scalars[16]
+        const unsigned g = static_cast<unsigned>(std::min<int64_t>((nq + RR_WPB - 1) / RR_WPB, static_cast<int64_t>(num_sms) * 3));
         const size_t sm = static_cast<size_t>(RR_WPB) * pk * sizeof(unsigned long long);
         const int inq = static_cast<int>(nq);
+        unsigned int *ctr = scalars.p + 16;
         if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F64)
-            rerank_warp_kernel<double, double, C, RR_WPB><<<g, RR_WPB * 32, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), rp, inq, pk);
+            rerank_warp_kernel<double, double, C, RR_WPB><<<g, RR_WPB * 32, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const double *>(d_query), rp, inq, pk, ctr);
         else if (x_dtype == B200KNN_F64 && q_dtype == B200KNN_F32)
-            rerank_warp_kernel<double, float, C, RR_WPB><<<g, RR_WPB * 32, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), rp, inq, pk);
+            rerank_warp_kernel<double, float, C, RR_WPB><<<g, RR_WPB * 32, sm, stream>>>(static_cast<const double *>(x_raw), static_cast<const float *>(d_query), rp, inq, pk, ctr);
         else if (x_dtype == B200KNN_F32 && q_dtype == B200KNN_F64)
-            rerank_warp_kernel<float, double, C, RR_WPB><<<g, RR_WPB * 32, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), rp, inq, pk);
+            rerank_warp_kernel<float, double, C, RR_WPB><<<g, RR_WPB * 32, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const double *>(d_query), rp, inq, pk, ctr);
         else
-            rerank_warp_kernel<float, float, C, RR_WPB><<<g, RR_WPB * 32, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), rp, inq, pk);
+            rerank_warp_kernel<float, float, C, RR_WPB><<<g, RR_WPB * 32, sm, stream>>>(static_cast<const float *>(x_raw), static_cast<const float *>(d_query), rp, inq, pk, ctr);
     }
     template <int C>
     int launch_rerank(const void *d_query, int q_dtype, int64_t nq, const RerankParams &rp) {
@@ -1022,6 +1029,7 @@ struct Shard {
             pp.stream_sync = stream_sync.p;
             pp.sync_entries = s.nrounds * s.max_slots;
             pp.zero_a = (acc && !accum.first) ? nullptr : scalars.p + 4;      // (postponed second pass: the queue grows over the chunks)
+            pp.zero_b = scalars.p + 16;
             stats.kernel_launches++;
             plan_pass_kernel<<<1, 256, 0, stream>>>(pp);
             CU_TRY(cudaGetLastError());

@@ -472,7 +472,7 @@ class DCI(object):
 
     def query_self_arrays(self, num_neighbours, squared=False):
         """Extension: kNN of every indexed row among the indexed rows (itself first), without re-uploading them
-        (b200knn_query_self).  Falls back to a plain query of the original array on multi-device handles."""
+        (b200knn_query_self; multi-device handles answer k <= 32 natively, larger k by a plain query of the original array)."""
         _require_positive_int(num_neighbours)
         n = self.num_points
         kk = min(num_neighbours, n)

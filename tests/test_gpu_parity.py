@@ -380,6 +380,68 @@ def test_multi_device_handle_if_available(lib):
     assert ok, msg
 
 
+def test_multi_device_next_entry_points_if_available(lib):
+    """Self-kNN, the projected entry points and ball membership on a multi-device handle (SURVEY 8f rows on the row-sharded
+    pool): bit-identical to the single-device handle.  Skipped on a 1-GPU box."""
+    if lib.b200knn_device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from inclusivegan_b200 import DCI
+    devs = list(range(min(4, lib.b200knn_device_count())))
+    # ---- self-kNN (k + self), float32 features, ragged shards, duplicated rows across a shard boundary
+    x, _ = make("relu", 9001, 1, 512, seed=60, dtype=np.float32)
+    x[len(x) // len(devs)] = x[len(x) // len(devs) - 1]          # first row of shard 1 == last row of shard 0
+    one, many = DCI(512), DCI(512, devices=devs)
+    one.add(x)
+    many.add(x)
+    i0, d0 = one.query_self_arrays(4, squared=True)
+    i1, d1 = many.query_self_arrays(4, squared=True)
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+    ri, rd = ko.exact_knn_numpy(x, x[:700], 4, squared=True)
+    ok, msg = ko.compare_knn(i1[:700], np.sqrt(d1[:700]), ri, np.sqrt(rd), x, x[:700])
+    assert ok, msg
+    # ---- ball membership against the sharded pool
+    probe = np.ascontiguousarray(np.maximum(np.random.default_rng(61).standard_normal((900, 512)), 0).astype(np.float32))
+    r2 = np.ascontiguousarray(d0[:, 3])
+    assert np.array_equal(one.ball_membership(probe, r2), many.ball_membership(probe, r2))
+    # ---- random projection on every shard: add_projected / query_projected
+    rng = np.random.default_rng(62)
+    proj = rng.normal(0.0, 1.0 / 256, size=(1536, 256))
+    pool = rng.standard_normal((7000, 1536)).astype(np.float32)
+    reals = rng.standard_normal((600, 1536)).astype(np.float32)
+    a, b = DCI(256), DCI(256, devices=devs)
+    for h in (a, b):
+        h.set_projector(proj)
+        h.add_projected(pool)
+    ia, da = a.query_projected_arrays(reals, 5)
+    ib, dbb = b.query_projected_arrays(reals, 5)
+    assert np.array_equal(ia, ib) and np.array_equal(da, dbb)
+    xp, yp = pool.astype(np.float64) @ proj, reals.astype(np.float64) @ proj
+    ri, rd = ko.exact_knn_numpy(xp, yp, 5)
+    ok, msg = ko.compare_knn(ib, dbb, ri, rd, xp, yp)
+    assert ok, msg
+
+
+def test_add_device_on_a_multi_device_handle_if_available(lib):
+    """b200knn_add_device with rows resident on one GPU, handle sharded over several: the library copies the slices over
+    NVLink; answers equal the host add()."""
+    if lib.b200knn_device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch
+    from inclusivegan_b200 import DCI
+    devs = list(range(min(4, lib.b200knn_device_count())))
+    x, y = make("cluster", 30000, 400, 320, seed=63)
+    ref = DCI(320, devices=devs)
+    ref.add(x)
+    i0, d0 = ref.query_arrays(y, 3)
+    h = DCI(320, devices=devs)
+    xd = torch.from_numpy(x).to("cuda:0")
+    rc = lib.b200knn_add_device(h._handle, ctypes.c_void_p(xd.data_ptr()), 0, x.shape[0], x.shape[1], 0)
+    assert rc == 0, lib.b200knn_last_error()
+    assert h.num_points == x.shape[0]
+    i1, d1 = h.query_arrays(y, 3)
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+
+
 # ------------------------------------------------------------------------------------------------ full size
 def test_full_size_config3_properties(lib):
     """BASELINE config 3 shape (300k pool x 30k queries, d=3072, k=1) through size-independent properties:
