@@ -258,6 +258,12 @@ int b200knn_debug_plan(int64_t n, int64_t nq, int kp, int num_sms, int cta_group
  * {first row, rows, then per rank: slice begin, slice end (chunk-relative)}; *count = number of chunks. */
 int b200knn_debug_chunks(int64_t n, int64_t nq, int kp, int num_sms, int64_t cap_rows, int world, int64_t *out, int64_t capacity, int64_t *count);
 
+/* Test hook (pure host code): how b200knn_query cuts a single-device host-row call of nq rows into chunks (an upload ramp
+ * sized on the distance kernel's schedule and the host link speed; csrc/b200knn.cu plan_host_chunks).  out receives
+ * {first row, rows} per chunk; *count = number of chunks.  pinned: the query rows are in page-locked host memory. */
+int b200knn_debug_host_chunks(int64_t n, int64_t nq, int kp, int dim, int elem_bytes, int k, int num_sms, int pinned, int64_t *out, int64_t capacity,
+                              int64_t *count);
+
 /* Test hook: copy out the BF16-pass shortlists of the LAST tensor pass of a single-device handle (the last query
  * chunk): scores[nq][slots][C] (s~ = ||x~||^2 - 2 q~.x~ as computed on the tensor cores) and rows[nq][slots][C]
  * (shard-local pool row, -1 = empty).  *nq, *slots, *c receive the geometry; the HOST buffers must hold `capacity`

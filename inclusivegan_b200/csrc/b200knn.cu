@@ -262,6 +262,117 @@ int query_self_sharded(b200knn_index *ix, int k, unsigned flags, int32_t *out_id
     return B200KNN_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Chunks of a single-device host-row call in whole-call mode (every chunk has its own slice of one device buffer, the
+// uploads run back to back on the copy stream, the call has ONE second pass): which cut hides most of the upload?
+// The first chunk's upload is the only one nothing can hide, so it should be small; every later chunk must have arrived
+// before the chunk before it has been computed, so chunks may grow by about the ratio of the compute to the upload time
+// per row (2.8 at config 3 from pinned memory) — a ramp.  Not every size is a good one: a chunk of h query tiles runs as
+// rounds of the distance kernel's schedule (Shard::plan_schedule), and h x (pool streams) should fill the workers
+// (8 x 9, 12 x 6, 24 x 3, 37 x 2 of 74).  So: keep the tail of full groups, cut the head (one group plus the ragged
+// remainder) into up to four parts by exhaustive search over a timeline model — upload time per tile from the link speed,
+// compute time from the ACTUAL schedule of that chunk size — and take the cut that finishes first.
+// Pure host arithmetic (b200knn_debug_host_chunks exposes it to the CPU tests).
+struct HostChunkModel {
+    double upload_gbs = 50.0;        // pinned host memory over PCIe 5 x16 (measured 52-55 GB/s); pageable through the ring: ~22
+    double tile_us = 20.8;           // one 256 x 256 x 3072 BF16 tile pair on the tcgen05 pipe, power-capped clocks (bench.py, config 3)
+    double chunk_overhead_ms = 0.15; // convert + plan + re-rank launches and the round barrier tail of a chunk
+};
+
+double sched_cost_tiles(const Shard::Sched &s) {     // pool tiles swept by the busiest worker, summed over the rounds
+    double total = 0.0;
+    for (int r = 0; r < s.nrounds; r++) {
+        int mx = 0;
+        for (int w = 0; w < s.workers; w++) {
+            const WorkItem &it = s.items[static_cast<size_t>(r) * s.workers + w];
+            if (it.qtile >= 0) mx = std::max(mx, it.t1 - it.t0);
+        }
+        total += mx;
+    }
+    return total;
+}
+
+int plan_host_chunks(int64_t n, int64_t nq, int kp_plan, int dim, size_t esz, int max_slots, int forced_cg, int max_pairs, int num_sms,
+                     int a_budget_mb, int wide_mode, int64_t cap_rows, const HostChunkModel &m, int tier_mmas,
+                     std::vector<std::pair<int64_t, int64_t>> &chunks) {
+    chunks.clear();
+    Shard::Sched full;
+    TRY(Shard::plan_schedule(full, n, nq, kp_plan, max_slots, forced_cg, max_pairs, num_sms, a_budget_mb, wide_mode));
+    const int64_t qrows = static_cast<int64_t>(BM) * full.cg;
+    const int qt = static_cast<int>((nq + qrows - 1) / qrows);
+    int G = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(full.qg, std::max<int64_t>(1, cap_rows / qrows))));
+    if (qt < 4 || full.wide) {                       // tiny calls, long rows (grid schedule): the ragged remainder, then whole groups
+        const int64_t group_rows = std::max<int64_t>(qrows, std::min<int64_t>(static_cast<int64_t>(full.qg) * qrows, cap_rows / qrows * qrows));
+        if (nq <= group_rows + group_rows / 4) {
+            chunks.emplace_back(0, nq);
+        } else {
+            const int64_t rem = nq % group_rows;
+            int64_t q0 = 0;
+            if (rem > 0) { chunks.emplace_back(0, rem); q0 = rem; }
+            for (; q0 < nq; q0 += group_rows) chunks.emplace_back(q0, std::min(group_rows, nq - q0));
+        }
+        return B200KNN_OK;
+    }
+    const double up_ms_per_tile = static_cast<double>(qrows) * dim * static_cast<double>(esz) / (m.upload_gbs * 1e6);
+    const double tile_ms = m.tile_us * 1e-3 * (static_cast<double>(kp_plan) / 3072.0) * tier_mmas;
+    // compute time of a chunk of h tiles, from its real schedule
+    const int k_tail = std::max(0, qt / G - 1);      // full groups kept at the end
+    const int H = qt - k_tail * G;                   // head: G .. 2G-1 tiles (or the whole call when it is shorter than 2 groups)
+    std::vector<double> comp(static_cast<size_t>(std::max(H, G)) + 1, 0.0);
+    for (int h = 1; h <= std::max(H, G); h++) {
+        Shard::Sched sc;
+        TRY(Shard::plan_schedule(sc, n, static_cast<int64_t>(h) * qrows, kp_plan, max_slots, forced_cg, max_pairs, num_sms, a_budget_mb, wide_mode));
+        comp[h] = sched_cost_tiles(sc) * tile_ms + m.chunk_overhead_ms;
+    }
+    auto finish_time = [&](const int *parts, int np) {
+        double up = 0.0, done = 0.0;
+        for (int i = 0; i < np; i++) {
+            up += parts[i] * up_ms_per_tile;
+            done = std::max(done, up) + comp[parts[i]];
+        }
+        for (int i = 0; i < k_tail; i++) {
+            up += G * up_ms_per_tile;
+            done = std::max(done, up) + comp[G];
+        }
+        return done;
+    };
+    int best[4] = {H, 0, 0, 0}, nbest = 1;
+    double best_t = finish_time(best, 1);
+    const int max_part = static_cast<int>(std::max<int64_t>(1, cap_rows / qrows));
+    for (int a = 1; a <= H; a++) {
+        if (a > max_part) break;
+        for (int b = 0; a + b <= H; b++) {
+            if (b > max_part) break;
+            if (b == 0) {
+                if (a != H) continue;
+                const int p[1] = {a};
+                const double t = finish_time(p, 1);
+                if (t < best_t - 1e-9) { best_t = t; nbest = 1; best[0] = a; }
+                continue;
+            }
+            for (int c = 0; a + b + c <= H; c++) {
+                if (c > max_part) break;
+                const int d = H - a - b - c;
+                if (d > max_part) continue;
+                if (c == 0 && d != 0) continue;
+                int p[4] = {a, b, c, d};
+                const int np = c == 0 ? 2 : (d == 0 ? 3 : 4);
+                const double t = finish_time(p, np);
+                if (t < best_t - 1e-9) { best_t = t; nbest = np; for (int i = 0; i < 4; i++) best[i] = p[i]; }
+            }
+        }
+    }
+    int64_t q0 = 0;
+    auto push = [&](int tiles) {
+        const int64_t rows = std::min<int64_t>(static_cast<int64_t>(tiles) * qrows, nq - q0);
+        if (rows > 0) { chunks.emplace_back(q0, rows); q0 += rows; }
+    };
+    for (int i = 0; i < nbest; i++) push(best[i]);
+    for (int i = 0; i < k_tail; i++) push(G);
+    if (q0 != nq) return fail(B200KNN_EINVAL, "internal: host chunk plan covers %lld of %lld rows", (long long)q0, (long long)nq);
+    return B200KNN_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -481,6 +592,24 @@ int b200knn_debug_chunks(int64_t n, int64_t nq, int kp, int num_sms, int64_t cap
                 *o++ = std::min(c.second, slice * (r + 1));
             }
         }
+    }
+    return B200KNN_OK;
+}
+
+int b200knn_debug_host_chunks(int64_t n, int64_t nq, int kp, int dim, int elem_bytes, int k, int num_sms, int pinned, int64_t *out, int64_t capacity,
+                              int64_t *count) {
+    if (n <= 0 || nq <= 0 || kp <= 0 || dim <= 0 || num_sms <= 0 || k <= 0 || k > 32 || !count || (elem_bytes != 4 && elem_bytes != 8))
+        return fail(B200KNN_EINVAL, "host chunk arguments out of range");
+    const int C = k <= 4 ? 16 : (k <= 16 ? 32 : 64);
+    HostChunkModel m;
+    if (!pinned) m.upload_gbs = 22.0;
+    std::vector<std::pair<int64_t, int64_t>> chunks;
+    const int64_t cap_rows = std::max<int64_t>(BM * 2, std::min<int64_t>(QUERY_CHUNK, (512ll << 20) / (static_cast<int64_t>(dim) * elem_bytes) / (BM * 2) * (BM * 2)));
+    TRY(plan_host_chunks(n, nq, kp, dim, static_cast<size_t>(elem_bytes), MAX_KEYS / C, 0, std::max(1, num_sms / 2), num_sms, 64, 1, cap_rows, m, 1, chunks));
+    *count = static_cast<int64_t>(chunks.size());
+    if (out) {
+        if (capacity < *count * 2) return fail(B200KNN_EINVAL, "capacity too small");
+        for (size_t i = 0; i < chunks.size(); i++) { out[2 * i] = chunks[i].first; out[2 * i + 1] = chunks[i].second; }
     }
     return B200KNN_OK;
 }
@@ -909,12 +1038,34 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
         CU_TRY(cudaSetDevice(s.device));
         // Chunking follows the kernel's schedule: one chunk = one full group of query tiles (a round that keeps every
         // SM busy); the ragged remainder goes FIRST, so the first upload - the only one nothing can hide - is short.
+        // Whole-call mode: when the call's query rows fit a device buffer ($B200KNN_CALL_BUFFER_MB, default 4096) every
+        // chunk is uploaded into its own slice of it — no stage buffer is recycled, so no upload ever waits for a compute
+        // pass — and the call runs ONE second pass at its end instead of one per chunk (Shard::CallAccum).
+        static const int64_t call_buffer_mb = []() { const char *e = getenv("B200KNN_CALL_BUFFER_MB"); return e ? std::max<int64_t>(0, atoll(e)) : 4096ll; }();
+        static const bool ramp_on = []() { const char *e = getenv("B200KNN_UPLOAD_RAMP"); return !e || atoi(e) != 0; }();
+        const bool can_whole = kk <= 32 && !(flags & B200KNN_FLAG_FORCE_SCAN) &&
+                               static_cast<int64_t>(nq) * dim * static_cast<int64_t>(esz) <= (call_buffer_mb << 20);
         std::vector<std::pair<int64_t, int64_t>> chunks;   // (first row, rows)
-        {
+        const int64_t cap_rows = std::max<int64_t>(BM * 2, std::min<int64_t>(QUERY_CHUNK, (512ll << 20) / (static_cast<int64_t>(dim) * esz) / (BM * 2) * (BM * 2)));
+        if (can_whole && ramp_on && nq >= 4 * BM * 2) {
+            // a ramp of growing chunks sized on the kernel's schedule and the link speed (plan_host_chunks)
+            HostChunkModel hm;
+            cudaPointerAttributes attr;
+            const bool pinned = cudaPointerGetAttributes(&attr, query) == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+            cudaGetLastError();
+            if (!pinned) hm.upload_gbs = 22.0;
+            const int C = kk <= 4 ? 16 : (kk <= 16 ? 32 : 64);
+            const int64_t key[8] = {s.n, nq, ix->kp, dim, static_cast<int64_t>(esz), C, pinned ? 1 : 0, s.tier};
+            if (std::memcmp(key, s.host_chunk_key, sizeof(key)) != 0 || s.host_chunks.empty()) {      // (the search costs ~0.1 ms of host time: cached per shape)
+                TRY(plan_host_chunks(s.n, nq, s.tier ? 2 * ix->kp : ix->kp, dim, esz, MAX_KEYS / C, s.forced_cg, s.max_pairs, s.num_sms, s.a_budget_mb, s.wide_mode,
+                                     cap_rows, hm, s.tier == 1 ? 3 : (s.tier == 2 ? 2 : 1), s.host_chunks));
+                std::memcpy(s.host_chunk_key, key, sizeof(key));
+            }
+            chunks = s.host_chunks;
+        } else {
             Shard::Sched sch;
             TRY(s.plan(sch, nq, ix->kp, 64));
             int64_t group_rows = static_cast<int64_t>(sch.qg) * BM * sch.cg;
-            const int64_t cap_rows = std::max<int64_t>(BM * 2, (512ll << 20) / (static_cast<int64_t>(dim) * esz) / (BM * 2) * (BM * 2));
             group_rows = std::max<int64_t>(BM * 2, std::min(group_rows, cap_rows));
             if (nq <= group_rows + group_rows / 4) {
                 chunks.emplace_back(0, nq);
@@ -928,12 +1079,7 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
         int64_t max_rows = 0;
         for (auto &c : chunks) max_rows = std::max(max_rows, c.second);
         const int64_t nchunks = static_cast<int64_t>(chunks.size());
-        // Whole-call mode: when the call's query rows fit a device buffer ($B200KNN_CALL_BUFFER_MB, default 4096) every
-        // chunk is uploaded into its own slice of it — no stage buffer is recycled, so no upload ever waits for a compute
-        // pass — and the call runs ONE second pass at its end instead of one per chunk (Shard::CallAccum).
-        static const int64_t call_buffer_mb = []() { const char *e = getenv("B200KNN_CALL_BUFFER_MB"); return e ? std::max<int64_t>(0, atoll(e)) : 4096ll; }();
-        const bool whole = nchunks > 1 && kk <= 32 && !(flags & B200KNN_FLAG_FORCE_SCAN) &&
-                           static_cast<int64_t>(nq) * dim * static_cast<int64_t>(esz) <= (call_buffer_mb << 20);
+        const bool whole = can_whole && nchunks > 1;
         if (whole) {
             TRY(s.q_stage.ensure(static_cast<size_t>(nq) * dim * esz));
         } else {

@@ -74,6 +74,8 @@ struct Shard {
     DevBuf<double> proj_rows;
     DevBuf<unsigned char> q_stage;   // host API: device copy of the caller's query rows
     DevBuf<unsigned char> q_stage2;  // second buffer: the upload of chunk i+1 overlaps the compute of chunk i
+    int64_t host_chunk_key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};      // b200knn_query: cached upload ramp (plan_host_chunks) of the last call shape
+    std::vector<std::pair<int64_t, int64_t>> host_chunks;
     cudaStream_t copy_stream = nullptr;
     int copy_threads = 8;            // $B200KNN_COPY_THREADS
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};

@@ -193,12 +193,18 @@ def _draw_unit_directions(rows, dim):
 class DCI(object):
     """Exact k-nearest-neighbour index with the reference `DCI` interface (dci.py:61-340)."""
 
-    def __init__(self, dim, num_comp_indices=2, num_simp_indices=7, devices=None, strict=False, precision=None):
+    def __init__(self, dim, num_comp_indices=2, num_simp_indices=7, devices=None, strict=False, precision=None, audit=None):
         """dim, num_comp_indices, num_simp_indices: as dci.py:63.  Extensions (keyword-only in spirit):
         devices   — GPU ids to row-shard the pool over (None: $B200KNN_DEVICES or the current device);
         strict    — refuse non-float64 data like the reference (dci.py:116-117);
         precision — tier of the tensor pass: 'bf16' (default), 'bf16x3' (split BF16, three MMAs) or 'tf32'; results are
-                    exact in every tier, the tier only decides how much exact re-ranking the tensor scores leave."""
+                    exact in every tier, the tier only decides how much exact re-ranking the tensor scores leave;
+        audit     — N > 0 (None: $B200KNN_AUDIT, default 0): after every query, N evenly spaced rows of it are answered
+                    again by the exact float64 CUDA-core scan (no tensor scores, no certificate) and compared; a
+                    difference raises RuntimeError.  A run-time cross-check of the certificate's one empirical premise
+                    (the accumulation model of the tensor core)."""
+        self._audit = int(os.environ.get("B200KNN_AUDIT", "0") or 0) if audit is None else int(audit)
+        self.audited_queries = 0
         self._dim = int(dim)
         self._num_comp_indices = num_comp_indices
         self._num_simp_indices = num_simp_indices
@@ -448,6 +454,7 @@ class DCI(object):
         _check(self._lib.b200knn_query(self._handle, q.ctypes.data, self._dtype_code(q), nq, self._dim, int(num_neighbours),
                                        0, idx.ctypes.data, dist.ctypes.data, ctypes.byref(out_kk)))
         assert out_kk.value == kk
+        self._audit_answers(q, int(num_neighbours), 0, idx, dist)
         if self._orig_indices is not None:
             idx = self._orig_indices[idx].astype(np.int32, copy=False)
         elif self._offset:
@@ -464,11 +471,32 @@ class DCI(object):
         dist = np.empty((nq, kk), dtype=np.float64)
         _check(self._lib.b200knn_query(self._handle, q.ctypes.data, self._dtype_code(q), nq, self._dim, int(num_neighbours),
                                        int(flags) | (FLAG_SQUARED if squared else 0), idx.ctypes.data, dist.ctypes.data, None))
+        self._audit_answers(q, int(num_neighbours), int(flags) | (FLAG_SQUARED if squared else 0), idx, dist)
         if self._orig_indices is not None:
             idx = self._orig_indices[idx].astype(np.int32, copy=False)
         elif self._offset:
             idx += np.int32(self._offset)
         return idx, dist
+
+    def _audit_answers(self, q, k, flags, idx, dist):
+        """audit > 0: re-answer a sample of the call's rows by the exact scan (B200KNN_FLAG_FORCE_SCAN) and compare the
+        library's raw output.  The scan sums a distance sequentially, the tensor paths in the canonical tree order:
+        distances agree to float64 rounding, indices exactly unless two rows tie within that rounding."""
+        if self._audit <= 0 or q.shape[0] == 0 or idx.shape[1] == 0 or (flags & (FLAG_FORCE_SCAN | FLAG_NO_CERTIFY)) or idx.shape[1] > 32:
+            return                                   # (scan answers and deliberately uncertified ones: nothing to cross-check)
+        rows = np.unique(np.linspace(0, q.shape[0] - 1, min(self._audit, q.shape[0])).astype(np.int64))
+        sub = np.ascontiguousarray(q[rows])
+        ai = np.empty((len(rows), idx.shape[1]), dtype=np.int32)
+        ad = np.empty((len(rows), idx.shape[1]), dtype=np.float64)
+        _check(self._lib.b200knn_query(self._handle, sub.ctypes.data, self._dtype_code(sub), len(rows), self._dim, k,
+                                       flags | FLAG_FORCE_SCAN, ai.ctypes.data, ad.ctypes.data, None))
+        self.audited_queries += len(rows)
+        gi, gd = idx[rows], dist[rows]
+        bad = np.abs(gd - ad) > 1e-9 * np.maximum(np.abs(ad), 1e-300)      # same distance, other row: a tie within rounding
+        if bad.any():
+            r, c = np.argwhere(bad)[0]
+            raise RuntimeError("b200knn audit: query row %d rank %d: tensor path returned (%d, %r), exact scan (%d, %r)"
+                               % (rows[r], c, gi[r, c], gd[r, c], ai[r, c], ad[r, c]))
 
     def query_self_arrays(self, num_neighbours, squared=False):
         """Extension: kNN of every indexed row among the indexed rows (itself first), without re-uploading them

@@ -250,6 +250,28 @@ def test_large_k_ties_come_out_in_index_order(lib):
         assert np.array_equal(dist, np.take_along_axis(d2, order, axis=1)), k
 
 
+def test_audit_cross_checks_a_sample_by_the_exact_scan(lib, monkeypatch):
+    """DCI(audit=N) / $B200KNN_AUDIT: N rows of every query call answered again by the float64 scan and compared."""
+    from inclusivegan_b200 import DCI
+    x, y = make("cluster", 20000, 900, 256, seed=77)
+    db = DCI(256, audit=50)
+    db.add(x)
+    check(db, x, y, 3)
+    assert db.audited_queries == 50
+    db.query(y[:24], num_neighbours=1)                 # the list-returning face audits too (24 rows: all of them)
+    assert db.audited_queries == 74
+    monkeypatch.setenv("B200KNN_AUDIT", "7")
+    db2 = DCI(256)
+    db2.add(x)
+    db2.query_arrays(y, 1, squared=True)
+    assert db2.audited_queries == 7
+    # a corrupted answer is caught: feed the audit a result whose first distance is off
+    i, d = db.query_arrays(y, 3)
+    d[0, 0] *= 1.001
+    with pytest.raises(RuntimeError, match="audit"):
+        db._audit_answers(np.ascontiguousarray(y), 3, 0, i, d)
+
+
 def test_non_contiguous_and_mixed_dtype_queries(lib):
     from inclusivegan_b200 import DCI
     x, y = make("gauss", 3000, 64, 128, seed=33)

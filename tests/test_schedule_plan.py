@@ -107,3 +107,36 @@ def test_collective_query_chunks_and_slices(native_lib, n, nq, kp, cap, world):
     assert pos == nq
     if count.value > 1:                                        # the ragged remainder goes first, the rest are equal
         assert len({int(c) for c in rows[1:, 1]}) == 1 and rows[0, 1] <= rows[1, 1]
+
+
+@pytest.mark.parametrize("n,nq,dim,esz,k,pinned", [(300000, 30000, 3072, 8, 1, 1), (300000, 30000, 3072, 8, 1, 0), (240000, 24000, 3072, 8, 1, 1),
+                                                   (300000, 9472, 3072, 8, 1, 1), (50000, 50000, 2048, 4, 4, 1), (10000, 100, 5000, 8, 10, 1),
+                                                   (20000, 30011, 512, 8, 25, 1), (300000, 1025, 3072, 4, 1, 0), (1000000, 30000, 49152, 4, 10, 1)])
+def test_host_upload_ramp_covers_the_call(native_lib, n, nq, dim, esz, k, pinned):
+    """b200knn_query's chunk plan for a single-device host-row call (csrc/b200knn.cu plan_host_chunks): consecutive chunks
+    that cover every row once, whole query tiles except the last, bounded by the stage budget; when the call is
+    compute-bound (big pool) the first chunk — the only upload nothing hides — is a small share of the call."""
+    native_lib.b200knn_debug_host_chunks.restype = ctypes.c_int
+    native_lib.b200knn_debug_host_chunks.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
+    kp = (dim + 7) // 8 * 8
+    count = ctypes.c_int64(0)
+    assert native_lib.b200knn_debug_host_chunks(n, nq, kp, dim, esz, k, 148, pinned, None, 0, ctypes.byref(count)) == 0
+    out = np.zeros(2 * count.value, dtype=np.int64)
+    assert native_lib.b200knn_debug_host_chunks(n, nq, kp, dim, esz, k, 148, pinned, out.ctypes.data, out.size, ctypes.byref(count)) == 0
+    rows = out.reshape(-1, 2)
+    cap = max(256, min(32768, (512 << 20) // (dim * esz) // 256 * 256))
+    pos = 0
+    for first, cnt in rows.tolist():
+        assert first == pos and 0 < cnt <= cap
+        pos += cnt
+    assert pos == nq
+    # whole 256-row query tiles (the 2-CTA kernel's tile) except for one ragged chunk: the last of a ramp, the first of the
+    # long-row fallback (remainder first, then whole groups)
+    assert sum(1 for c in rows[:, 1].tolist() if c % 256) <= 1
+    if n >= 240000 and nq >= 20000 and dim == 3072:             # compute-bound: a ramp, not equal chunks
+        assert len(rows) >= 4 and rows[0, 1] <= nq // 10 and rows[0, 1] <= rows[1, 1] <= rows[2, 1]
+    # deterministic
+    out2 = np.zeros_like(out)
+    assert native_lib.b200knn_debug_host_chunks(n, nq, kp, dim, esz, k, 148, pinned, out2.ctypes.data, out2.size, ctypes.byref(count)) == 0
+    assert np.array_equal(out, out2)
