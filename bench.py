@@ -15,6 +15,7 @@ resident generated pool (exact kNN).  Prints ONE JSON line (rank 0).
   roofline  the tcgen05 distance kernel: 2*Q*N*d FLOPs per launch / its CUDA-event time, vs MEASURED_PEAKS.json.
   add_s     DCI.add() of the workload's pool from pageable host memory (H2D + centre + BF16 convert + norms).
   small_call  the trainer's call granularity (training_loop.py:374-403): 24-row b200knn_query calls, back to back.
+  e2e_pageable  the e2e call again with pageable NumPy buffers (what DCI.query hands over), N = 1.
   cpu_baseline / --impl reference
             the UNMODIFIED reference DCI (oracle/_ref/_dci.so) on this box's host cores with the trainer's
             hyper-parameters, FULL pool, bounded query sample per step; its approximate answers are scored as
@@ -567,6 +568,26 @@ def run_b200(args):
                       "queries_per_s": nsc * SMALL_CALL_ROWS / float(tl.item()),
                       "api": "%s, host rows, one call per %d rows, back to back (training_loop.py:374-403)" % (
                           "b200knn_query" if world == 1 else "b200knn_exchange_query (collective: slice upload, broadcast, bound + list exchange)", SMALL_CALL_ROWS)}
+    # ---- the same call from PAGEABLE memory (what a NumPy caller of DCI.query hands over): uploads go through the library's
+    # pinned ring, slower than the DMA from page-locked memory, so the cut of the call into chunks matters more ----
+    e2e_pageable = None
+    if not self_knn and world == 1 and args.workload not in ("c5", "c5s") and not args.no_secondaries:
+        q_np = np.array(hq.numpy(), copy=True)                  # fresh pageable allocation
+        o_i = np.empty((q, kk), dtype=np.int32)
+        o_d = np.empty((q, kk), dtype=np.float64)
+
+        def numpy_call():
+            check_rc(lib.b200knn_query(hx, ctypes.c_void_p(q_np.ctypes.data), FT, q, d, k, 0, ctypes.c_void_p(o_i.ctypes.data),
+                                       ctypes.c_void_p(o_d.ctypes.data), None))
+        numpy_call()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            numpy_call()
+            ts.append(time.perf_counter() - t0)
+        e2e_pageable = {"ms_per_step": 1e3 * float(np.median(ts)), "value": q / float(np.median(ts)), "unit": "queries/s", "steps": 3,
+                        "api": "b200knn_query, pageable NumPy query rows and results (host wall clock, median of 3)"}
+        del q_np
     lib.b200knn_destroy(hx)
     if not self_knn and args.workload not in ("c5", "c5s") and (r1 - r0) * d * fbytes < 40e9 and not args.no_secondaries:
         pool_np = pool.cpu().numpy()             # pageable, like the trainer's np.zeros + fill (training_loop.py:358-365)
@@ -702,6 +723,7 @@ def run_b200(args):
                             "copy engines broadcast BF16 rows + norms and (behind the tensor pass) the original rows over NVLink; merged result copied to the host")},
             "add_s": add_s,
             "small_call": small_call,
+            "e2e_pageable": e2e_pageable,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "self_check": check, "self_check_queries": int(nchk), "self_check_rule": "top-%d vs torch float64 brute force (direct differences): index equal or distance tie <= 1e-6 rel, distances <= 1e-5 rel" % kk,

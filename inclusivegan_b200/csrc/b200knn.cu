@@ -1042,17 +1042,21 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
         // chunk is uploaded into its own slice of it — no stage buffer is recycled, so no upload ever waits for a compute
         // pass — and the call runs ONE second pass at its end instead of one per chunk (Shard::CallAccum).
         static const int64_t call_buffer_mb = []() { const char *e = getenv("B200KNN_CALL_BUFFER_MB"); return e ? std::max<int64_t>(0, atoll(e)) : 4096ll; }();
-        static const bool ramp_on = []() { const char *e = getenv("B200KNN_UPLOAD_RAMP"); return !e || atoi(e) != 0; }();
+        // $B200KNN_UPLOAD_RAMP: 0 never, 1 (default) for pageable sources, 2 also for page-locked ones.  Measured at config 3 on
+        // one GPU (bench.py e2e / e2e_pageable, ms per 30k-query call, device-resident 38.1): pageable 43.3 -> 41.0 with the
+        // ramp; page-locked 39.9 -> 40.4 (the DMA is fast enough that remainder-first + whole groups leaves nothing to hide,
+        // and every extra chunk costs its launches and pipeline fill).
+        static const int ramp_mode = []() { const char *e = getenv("B200KNN_UPLOAD_RAMP"); return e ? atoi(e) : 1; }();
         const bool can_whole = kk <= 32 && !(flags & B200KNN_FLAG_FORCE_SCAN) &&
                                static_cast<int64_t>(nq) * dim * static_cast<int64_t>(esz) <= (call_buffer_mb << 20);
         std::vector<std::pair<int64_t, int64_t>> chunks;   // (first row, rows)
         const int64_t cap_rows = std::max<int64_t>(BM * 2, std::min<int64_t>(QUERY_CHUNK, (512ll << 20) / (static_cast<int64_t>(dim) * esz) / (BM * 2) * (BM * 2)));
-        if (can_whole && ramp_on && nq >= 4 * BM * 2) {
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, query) == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+        cudaGetLastError();
+        if (can_whole && (ramp_mode >= 2 || (ramp_mode == 1 && !pinned)) && nq >= 4 * BM * 2) {
             // a ramp of growing chunks sized on the kernel's schedule and the link speed (plan_host_chunks)
             HostChunkModel hm;
-            cudaPointerAttributes attr;
-            const bool pinned = cudaPointerGetAttributes(&attr, query) == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
-            cudaGetLastError();
             if (!pinned) hm.upload_gbs = 22.0;
             const int C = kk <= 4 ? 16 : (kk <= 16 ? 32 : 64);
             const int64_t key[8] = {s.n, nq, ix->kp, dim, static_cast<int64_t>(esz), C, pinned ? 1 : 0, s.tier};
