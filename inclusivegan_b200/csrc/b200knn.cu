@@ -787,7 +787,7 @@ int b200knn_query_device(b200knn_index *ix, const void *d_query, int dtype, int6
     const size_t esz = dtype == B200KNN_F64 ? 8 : 4;
     if (nq == 0) return B200KNN_OK;
     TRY(s.begin_call(nq));
-    const bool whole = nq > QUERY_CHUNK;       // several passes: one second pass for all of them, at the end
+    const bool whole = nq > QUERY_CHUNK && nq <= WHOLE_CALL_MAX_ROWS;       // several passes: one second pass for all of them, at the end
     s.accum = Shard::CallAccum{};
     for (int64_t q0 = 0; q0 < nq; q0 += QUERY_CHUNK) {
         const int64_t cq = std::min(QUERY_CHUNK, nq - q0);
@@ -828,7 +828,7 @@ int b200knn_query_self(b200knn_index *ix, int k, unsigned flags, int32_t *out_id
         return pre;
     };
     const QuerySide base = pool_side(0);
-    const bool whole = s.n > QUERY_CHUNK;       // several passes: one second pass for all of them, at the end
+    const bool whole = s.n > QUERY_CHUNK && s.n <= WHOLE_CALL_MAX_ROWS;       // several passes: one second pass for all of them, at the end
     s.accum = Shard::CallAccum{};
     for (int64_t q0 = 0; q0 < s.n; q0 += QUERY_CHUNK) {
         const int64_t cq = std::min(QUERY_CHUNK, s.n - q0);
@@ -1041,13 +1041,13 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
         // Whole-call mode: when the call's query rows fit a device buffer ($B200KNN_CALL_BUFFER_MB, default 4096) every
         // chunk is uploaded into its own slice of it — no stage buffer is recycled, so no upload ever waits for a compute
         // pass — and the call runs ONE second pass at its end instead of one per chunk (Shard::CallAccum).
-        static const int64_t call_buffer_mb = []() { const char *e = getenv("B200KNN_CALL_BUFFER_MB"); return e ? std::max<int64_t>(0, atoll(e)) : 4096ll; }();
+        const int64_t call_buffer_mb = []() { const char *e = getenv("B200KNN_CALL_BUFFER_MB"); return e ? std::max<int64_t>(0, atoll(e)) : 4096ll; }();
         // $B200KNN_UPLOAD_RAMP: 0 never, 1 (default) for pageable sources, 2 also for page-locked ones.  Measured at config 3 on
         // one GPU (bench.py e2e / e2e_pageable, ms per 30k-query call, device-resident 38.1): pageable 43.3 -> 41.0 with the
         // ramp; page-locked 39.9 -> 40.4 (the DMA is fast enough that remainder-first + whole groups leaves nothing to hide,
         // and every extra chunk costs its launches and pipeline fill).
-        static const int ramp_mode = []() { const char *e = getenv("B200KNN_UPLOAD_RAMP"); return e ? atoi(e) : 1; }();
-        const bool can_whole = kk <= 32 && !(flags & B200KNN_FLAG_FORCE_SCAN) &&
+        const int ramp_mode = []() { const char *e = getenv("B200KNN_UPLOAD_RAMP"); return e ? atoi(e) : 1; }();
+        const bool can_whole = kk <= 32 && !(flags & B200KNN_FLAG_FORCE_SCAN) && nq <= WHOLE_CALL_MAX_ROWS &&
                                static_cast<int64_t>(nq) * dim * static_cast<int64_t>(esz) <= (call_buffer_mb << 20);
         std::vector<std::pair<int64_t, int64_t>> chunks;   // (first row, rows)
         const int64_t cap_rows = std::max<int64_t>(BM * 2, std::min<int64_t>(QUERY_CHUNK, (512ll << 20) / (static_cast<int64_t>(dim) * esz) / (BM * 2) * (BM * 2)));

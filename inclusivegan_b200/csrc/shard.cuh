@@ -1326,5 +1326,8 @@ struct Shard {
 };
 
 constexpr int64_t QUERY_CHUNK = 32768;   // query rows per device pass (bounds workspace; 256 query tiles)
+// largest call that runs ONE second pass over all its passes (Shard::CallAccum): the collection lists are sized for the
+// worst case, every row uncertified (4 KB per row: 1 GB here), as are the whole-call copies of the converted rows
+constexpr int64_t WHOLE_CALL_MAX_ROWS = 262144;
 
 }  // namespace
