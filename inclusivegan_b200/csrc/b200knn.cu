@@ -1042,11 +1042,12 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
         // chunk is uploaded into its own slice of it — no stage buffer is recycled, so no upload ever waits for a compute
         // pass — and the call runs ONE second pass at its end instead of one per chunk (Shard::CallAccum).
         const int64_t call_buffer_mb = []() { const char *e = getenv("B200KNN_CALL_BUFFER_MB"); return e ? std::max<int64_t>(0, atoll(e)) : 4096ll; }();
-        // $B200KNN_UPLOAD_RAMP: 0 never, 1 (default) for pageable sources, 2 also for page-locked ones.  Measured at config 3 on
-        // one GPU (bench.py e2e / e2e_pageable, ms per 30k-query call, device-resident 38.1): pageable 43.3 -> 41.0 with the
-        // ramp; page-locked 39.9 -> 40.4 (the DMA is fast enough that remainder-first + whole groups leaves nothing to hide,
-        // and every extra chunk costs its launches and pipeline fill).
-        const int ramp_mode = []() { const char *e = getenv("B200KNN_UPLOAD_RAMP"); return e ? atoi(e) : 1; }();
+        // $B200KNN_UPLOAD_RAMP: 0 (default) never, 1 for pageable sources, 2 also for page-locked ones.  OFF by default: measured at
+        // config 3 on one GPU (bench.py e2e / e2e_pageable, ms per 30k-query call, device-resident 38.1-38.7) the ramp gave
+        // pageable 43.3 -> 41.0 on one box and 43.0 -> 43.2 on another, page-locked 39.9 -> 40.4: chunks of 1-12 query tiles cost
+        // more than the timeline model charges them (many pool streams per tile: more shortlists to write, sort and bound; a
+        // pipeline fill per chunk), which eats what the earlier start buys.  Kept as an option with its CPU test.
+        const int ramp_mode = []() { const char *e = getenv("B200KNN_UPLOAD_RAMP"); return e ? atoi(e) : 0; }();
         const bool can_whole = kk <= 32 && !(flags & B200KNN_FLAG_FORCE_SCAN) && nq <= WHOLE_CALL_MAX_ROWS &&
                                static_cast<int64_t>(nq) * dim * static_cast<int64_t>(esz) <= (call_buffer_mb << 20);
         std::vector<std::pair<int64_t, int64_t>> chunks;   // (first row, rows)

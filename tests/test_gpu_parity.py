@@ -768,20 +768,20 @@ def test_one_second_pass_per_call_over_several_chunks(lib, monkeypatch):
     and without the whole-call buffers, from pageable and from page-locked rows."""
     import torch
     from inclusivegan_b200 import DCI
-    x, y = make("gauss", 6000, 2600, 2048, seed=91)           # high-d i.i.d.: a share of the rows is uncertified in every chunk
-    db = DCI(2048)
+    x, y = make("gauss", 4000, 2600, 4096, seed=91)           # high-d i.i.d. (as in test_results_do_not_depend_on_batching_or_path):
+    db = DCI(4096)                                              # a share of the rows is uncertified
     db.add(x)
-    i_all, d_all = check(db, x, y, 3)                          # pageable rows: upload ramp, several chunks
+    i_all, d_all = check(db, x, y, 10)                         # pageable rows: upload ramp, several chunks
     unc = db.stats()["uncertified"]
-    assert unc > 3
-    parts = [db.query_arrays(y[s:s + 500], 3) for s in range(0, 2600, 500)]
+    assert unc >= 2
+    parts = [db.query_arrays(y[s:s + 500], 10) for s in range(0, 2600, 500)]
     assert np.array_equal(i_all, np.concatenate([p[0] for p in parts])) and np.array_equal(d_all, np.concatenate([p[1] for p in parts]))
     yp = torch.from_numpy(y).pin_memory().numpy()              # page-locked rows: remainder first, then whole groups
-    i_pin, d_pin = db.query_arrays(yp, 3)
+    i_pin, d_pin = db.query_arrays(yp, 10)
     assert np.array_equal(i_all, i_pin) and np.array_equal(d_all, d_pin)
     monkeypatch.setenv("B200KNN_CALL_BUFFER_MB", "0")          # the round-2-first-session path: stage buffers recycled, a pass per chunk
     monkeypatch.setenv("B200KNN_UPLOAD_RAMP", "0")
-    i_old, d_old = db.query_arrays(y, 3)
+    i_old, d_old = db.query_arrays(y, 10)
     assert np.array_equal(i_all, i_old) and np.array_equal(d_all, d_old)
 
 
