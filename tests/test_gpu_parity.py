@@ -771,12 +771,13 @@ def test_one_second_pass_per_call_over_several_chunks(lib, monkeypatch):
     x, y = make("gauss", 4000, 2600, 4096, seed=91)           # high-d i.i.d. (as in test_results_do_not_depend_on_batching_or_path):
     db = DCI(4096)                                              # a share of the rows is uncertified
     db.add(x)
-    i_all, d_all = check(db, x, y, 10)                         # pageable rows: upload ramp, several chunks
+    monkeypatch.setenv("B200KNN_UPLOAD_RAMP", "2")             # cut the call into several (growing) chunks whatever the source
+    i_all, d_all = check(db, x, y, 10)
     unc = db.stats()["uncertified"]
     assert unc >= 2
     parts = [db.query_arrays(y[s:s + 500], 10) for s in range(0, 2600, 500)]
     assert np.array_equal(i_all, np.concatenate([p[0] for p in parts])) and np.array_equal(d_all, np.concatenate([p[1] for p in parts]))
-    yp = torch.from_numpy(y).pin_memory().numpy()              # page-locked rows: remainder first, then whole groups
+    yp = torch.from_numpy(y).pin_memory().numpy()              # page-locked rows
     i_pin, d_pin = db.query_arrays(yp, 10)
     assert np.array_equal(i_all, i_pin) and np.array_equal(d_all, d_pin)
     monkeypatch.setenv("B200KNN_CALL_BUFFER_MB", "0")          # the round-2-first-session path: stage buffers recycled, a pass per chunk
