@@ -522,8 +522,8 @@ def run_b200(args):
                 check_rc(lib.b200knn_add(hx, ctypes.c_void_p(rows.data_ptr()), FT, nrows, d))
                 check_rc(lib.b200knn_query_self(hx, k, 0, ctypes.c_void_p(oi.data_ptr()), ctypes.c_void_p(od.data_ptr()), None))
         elif world > 1:
-            # b200knn_exchange_query: every rank uploads 1/N of every query chunk from the (same) pinned host matrix; BF16 rows and,
-            # behind the tensor pass, the original rows are broadcast by the copy engines; merged result lands in host memory
+            # b200knn_exchange_query: every rank uploads 1/N of every query chunk from the (same) pinned host matrix and broadcasts
+            # the BF16 rows by peer stores; original rows are read from their owner by the re-rank; merged result lands in host memory
             exchange.query_host(ix, hq.data_ptr(), FT, q, k, h_i.data_ptr(), h_d.data_ptr())
         else:
             check_rc(lib.b200knn_query(hx, ctypes.c_void_p(hq.data_ptr()), FT, q, d, k, 0, ctypes.c_void_p(h_i.data_ptr()),
