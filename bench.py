@@ -720,7 +720,8 @@ def run_b200(args):
                     "api": "per feature set: b200knn_clear + b200knn_add (host rows) + b200knn_query_self (what ManifoldEstimator.__init__ does)" if self_knn else
                            ("b200knn_query (host buffers; the call inclusivegan_b200.dci.DCI.query makes)" if world == 1 else
                             "b200knn_exchange_query (host buffers, collective): per chunk every rank uploads 1/N of the rows from pinned host memory, converts them, "
-                            "copy engines broadcast BF16 rows + norms and (behind the tensor pass) the original rows over NVLink; merged result copied to the host")},
+                            "broadcasts the BF16 rows + norms by peer stores over NVLink; the exact re-rank reads original rows from the rank that uploaded them; "
+                            "merged result copied to the host")},
             "add_s": add_s,
             "small_call": small_call,
             "e2e_pageable": e2e_pageable,
