@@ -696,7 +696,8 @@ struct Shard {
         // Three flavours, bit-identical results.  Many queries: one warp per query (24 resident per SM, their latency
         // chains overlap).  Few queries: a block per query (128 lanes stream a candidate row at once: lowest latency) —
         // and when those few queries merge many shortlists (many pool streams), a latency-bound sort, 32 warps per query.
-        const bool warp_flavour = rerank_warp_mode == 2 || (rerank_warp_mode == 1 && nq >= 2048);
+        // (long rows — config 5's 196 KB — keep the block flavour: its 128-lane sweep was tuned and measured there, the warp flavour was not)
+        const bool warp_flavour = rerank_warp_mode == 2 || (rerank_warp_mode == 1 && nq >= 2048 && rp.dim <= 8192);
         if (warp_flavour && pk <= 512) launch_rerank_warp<C>(d_query, q_dtype, nq, pk, rp);
         else if (pk >= 1024 && nq <= 4096) launch_rerank_nt<C, 1024>(d_query, q_dtype, g, sm, rp);
         else launch_rerank_nt<C, 128>(d_query, q_dtype, g, sm, rp);
