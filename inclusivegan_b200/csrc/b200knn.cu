@@ -274,9 +274,11 @@ int query_self_sharded(b200knn_index *ix, int k, unsigned flags, int32_t *out_id
 // compute time from the ACTUAL schedule of that chunk size — and take the cut that finishes first.
 // Pure host arithmetic (b200knn_debug_host_chunks exposes it to the CPU tests).
 struct HostChunkModel {
-    double upload_gbs = 50.0;        // pinned host memory over PCIe 5 x16 (measured 52-55 GB/s); pageable through the ring: ~22
+    double upload_gbs = 55.0;        // pinned host memory over PCIe 5 x16 (measured 52-60 GB/s); pageable through the ring: ~40
     double tile_us = 20.8;           // one 256 x 256 x 3072 BF16 tile pair on the tcgen05 pipe, power-capped clocks (bench.py, config 3)
-    double chunk_overhead_ms = 0.15; // convert + plan + re-rank launches and the round barrier tail of a chunk
+    double chunk_overhead_ms = 0.30; // convert + plan + re-rank launches, pipeline fill and the round barrier tail of a chunk
+    int min_part_tiles = 6;          // no chunk below this many query tiles: with fewer, every query has dozens of pool streams, i.e.
+                                     // shortlists to write, sort and bound (the first model allowed 1-tile chunks and lost 1 ms to them)
 };
 
 double sched_cost_tiles(const Shard::Sched &s) {     // pool tiles swept by the busiest worker, summed over the rounds
@@ -339,10 +341,12 @@ int plan_host_chunks(int64_t n, int64_t nq, int kp_plan, int dim, size_t esz, in
     int best[4] = {H, 0, 0, 0}, nbest = 1;
     double best_t = finish_time(best, 1);
     const int max_part = static_cast<int>(std::max<int64_t>(1, cap_rows / qrows));
-    for (int a = 1; a <= H; a++) {
+    const int mp = std::min(m.min_part_tiles, H);
+    for (int a = mp; a <= H; a++) {
         if (a > max_part) break;
         for (int b = 0; a + b <= H; b++) {
             if (b > max_part) break;
+            if (b != 0 && b < mp) continue;
             if (b == 0) {
                 if (a != H) continue;
                 const int p[1] = {a};
@@ -352,9 +356,11 @@ int plan_host_chunks(int64_t n, int64_t nq, int kp_plan, int dim, size_t esz, in
             }
             for (int c = 0; a + b + c <= H; c++) {
                 if (c > max_part) break;
+                if (c != 0 && c < mp) continue;
                 const int d = H - a - b - c;
                 if (d > max_part) continue;
                 if (c == 0 && d != 0) continue;
+                if (d != 0 && d < mp) continue;
                 int p[4] = {a, b, c, d};
                 const int np = c == 0 ? 2 : (d == 0 ? 3 : 4);
                 const double t = finish_time(p, np);
@@ -602,7 +608,7 @@ int b200knn_debug_host_chunks(int64_t n, int64_t nq, int kp, int dim, int elem_b
         return fail(B200KNN_EINVAL, "host chunk arguments out of range");
     const int C = k <= 4 ? 16 : (k <= 16 ? 32 : 64);
     HostChunkModel m;
-    if (!pinned) m.upload_gbs = 22.0;
+    if (!pinned) m.upload_gbs = 40.0;
     std::vector<std::pair<int64_t, int64_t>> chunks;
     const int64_t cap_rows = std::max<int64_t>(BM * 2, std::min<int64_t>(QUERY_CHUNK, (512ll << 20) / (static_cast<int64_t>(dim) * elem_bytes) / (BM * 2) * (BM * 2)));
     TRY(plan_host_chunks(n, nq, kp, dim, static_cast<size_t>(elem_bytes), MAX_KEYS / C, 0, std::max(1, num_sms / 2), num_sms, 64, 1, cap_rows, m, 1, chunks));
@@ -1042,12 +1048,12 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
         // chunk is uploaded into its own slice of it — no stage buffer is recycled, so no upload ever waits for a compute
         // pass — and the call runs ONE second pass at its end instead of one per chunk (Shard::CallAccum).
         const int64_t call_buffer_mb = []() { const char *e = getenv("B200KNN_CALL_BUFFER_MB"); return e ? std::max<int64_t>(0, atoll(e)) : 4096ll; }();
-        // $B200KNN_UPLOAD_RAMP: 0 (default) never, 1 for pageable sources, 2 also for page-locked ones.  OFF by default: measured at
-        // config 3 on one GPU (bench.py e2e / e2e_pageable, ms per 30k-query call, device-resident 38.1-38.7) the ramp gave
-        // pageable 43.3 -> 41.0 on one box and 43.0 -> 43.2 on another, page-locked 39.9 -> 40.4: chunks of 1-12 query tiles cost
-        // more than the timeline model charges them (many pool streams per tile: more shortlists to write, sort and bound; a
-        // pipeline fill per chunk), which eats what the earlier start buys.  Kept as an option with its CPU test.
-        const int ramp_mode = []() { const char *e = getenv("B200KNN_UPLOAD_RAMP"); return e ? atoi(e) : 0; }();
+        // $B200KNN_UPLOAD_RAMP: 0 never, 1 for pageable sources only, 2 (default) for every source.  Measured at config 3 on one
+        // GPU, A/B on one box (bench.py e2e / e2e_pageable, ms per 30k-query call): page-locked rows 39.81 -> 39.28 (gap to the
+        // device-resident step 1.76 -> 0.95 ms), pageable NumPy rows 42.36 -> 40.34.  A first version of the model allowed chunks
+        // of 1-4 query tiles and lost what the earlier start bought (40.4 against 39.9): such chunks have dozens of pool streams
+        // per query tile - shortlists to write, sort and bound - and a pipeline fill each; hence min_part_tiles.
+        const int ramp_mode = []() { const char *e = getenv("B200KNN_UPLOAD_RAMP"); return e ? atoi(e) : 2; }();
         const bool can_whole = kk <= 32 && !(flags & B200KNN_FLAG_FORCE_SCAN) && nq <= WHOLE_CALL_MAX_ROWS &&
                                static_cast<int64_t>(nq) * dim * static_cast<int64_t>(esz) <= (call_buffer_mb << 20);
         std::vector<std::pair<int64_t, int64_t>> chunks;   // (first row, rows)
@@ -1058,7 +1064,7 @@ int b200knn_query(b200knn_index *ix, const void *query, int dtype, int64_t nq, i
         if (can_whole && (ramp_mode >= 2 || (ramp_mode == 1 && !pinned)) && nq >= 4 * BM * 2) {
             // a ramp of growing chunks sized on the kernel's schedule and the link speed (plan_host_chunks)
             HostChunkModel hm;
-            if (!pinned) hm.upload_gbs = 22.0;
+            if (!pinned) hm.upload_gbs = 40.0;
             const int C = kk <= 4 ? 16 : (kk <= 16 ? 32 : 64);
             const int64_t key[8] = {s.n, nq, ix->kp, dim, static_cast<int64_t>(esz), C, pinned ? 1 : 0, s.tier};
             if (std::memcmp(key, s.host_chunk_key, sizeof(key)) != 0 || s.host_chunks.empty()) {      // (the search costs ~0.1 ms of host time: cached per shape)
