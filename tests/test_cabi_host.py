@@ -247,3 +247,22 @@ def test_reference_wrapper_runs_on_the_extension_stand_in(native_lib):
             sys.modules.pop("_dci", None)
         else:
             sys.modules["_dci"] = saved
+
+
+def test_audit_switch_is_parsed_without_a_device(native_lib, monkeypatch):
+    """DCI(audit=N) / $B200KNN_AUDIT (run-time cross-check of N rows per call against the exact scan): the switch is host state
+    of the Python layer; the handle is created lazily, so this needs no GPU."""
+    from inclusivegan_b200 import DCI
+    monkeypatch.delenv("B200KNN_AUDIT", raising=False)
+    assert DCI(8)._audit == 0
+    monkeypatch.setenv("B200KNN_AUDIT", "32")
+    assert DCI(8)._audit == 32
+    assert DCI(8, audit=5)._audit == 5 and DCI(8, audit=0)._audit == 0
+    db = DCI(8, audit=4)
+    assert db.audited_queries == 0
+    # nothing to audit: empty answers, scan answers, deliberately uncertified answers
+    q = np.zeros((3, 8))
+    db._audit_answers(q, 1, 4, np.zeros((3, 1), np.int32), np.zeros((3, 1)))       # FLAG_FORCE_SCAN
+    db._audit_answers(q, 1, 2, np.zeros((3, 1), np.int32), np.zeros((3, 1)))       # FLAG_NO_CERTIFY
+    db._audit_answers(q[:0], 1, 0, np.zeros((0, 1), np.int32), np.zeros((0, 1)))
+    assert db.audited_queries == 0
